@@ -1,0 +1,468 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the VFIDKR hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--table PATH]
+
+Workload (BASELINE.json configs[3], the largest single-GPU configuration; named in config.workload):
+one "step" is the hot path of a 1080p frame-pair inference batch, B = 8 pairs padded to 1152x1984
+(demo_MiddleBury.py:294-312), in the order the networks call it:
+    10 x Correlation forward      (5 PWC-Net levels x 2 directions; C = 196,128,96,64,32; PWCNet.py:230-300)
+     2 x DepthFlowProjection fwd  (fillhole = 1, inference; DAIN_slowmotion.py:156-159)
+     2 x FilterInterpolation fwd  ("_ori", C = 3, F = 4; DAIN.py:560-573)
+and produces 8 interpolated frames.  metric = interpolated Mpixel/s = frames x 1920 x 1080 / s / 1e6.
+Frame pairs are independent: with N GPUs every rank runs its own batch of 8 pairs (weak scaling), no
+collective on the data path; NCCL only reduces the timing / unit counts.
+
+`value`    inputs resident in HBM, timed with CUDA events on the launch stream, max over ranks.
+`e2e`      the same step through the public Python API with HOST buffers: pinned host -> device copies
+           of every input and the device -> host read of the interpolated frames are inside the timed region.
+`roofline` FilterInterpolation "_ori" forward kernel: algorithmic bytes (96 B/pixel) / its
+           average duration measured with CUDA events inside the timed region, against the measured HBM copy peak.
+`cpu_baseline` / `--impl reference`: the float64 CPU oracle (a port; the reference has no CPU implementation
+           and its CUDA extensions do not build in this image) on the host cores, on a bounded sample (one pair).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+FRAME_PIXELS = 1920 * 1080
+PAD_H, PAD_W = 1152, 1984                 # 1080p after the /128 replication padding
+PAIRS_PER_GPU = 8
+PWC_LEVELS = [(196, 64), (128, 32), (96, 16), (64, 8), (32, 4)]   # (channels, downscale) levels 6..2
+FI_BYTES_PER_PIXEL = 4 * (2 * 3 + 18)     # 96 B/px at C = 3
+FALLBACK_HBM_GBS = 6650.0                 # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+# ----------------------------------------------------------------------------- sharding / reduction helpers
+def shard_pairs(n_pairs: int, rank: int, world: int) -> list[int]:
+    """Round-robin assignment of independent frame pairs to ranks."""
+    return list(range(rank, n_pairs, world))
+
+
+def reduce_timing(t_ms, units):
+    """max over ranks of the elapsed time, sum over ranks of the processed units (tensors of shape [1])."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(units, op=dist.ReduceOp.SUM)
+    return t_ms, units
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the FI kernel from the committed ncu capture, if one has been recorded."""
+    p = ROOT / "profiles" / "traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("fi_forward_ori_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+# ----------------------------------------------------------------------------- clock sampling
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (NVML, else nvidia-smi)."""
+
+    def __init__(self, index: int, period=0.2):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.backend = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.backend = "nvml"
+        except Exception:
+            self.nv = None
+
+    _BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+             0x80: "hw_power_brake_slowdown"}
+
+    def run(self):
+        if self.nv is None:
+            return
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                try:
+                    bits = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    bits = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for b, name in self._BITS.items():
+                    if bits & b:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no clock samples available"}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ----------------------------------------------------------------------------- the workload
+def build_inputs(torch, device, seed, pinned_host=False):
+    """Synthetic inputs of one step.  Returns a dict of tensors; with pinned_host
+    they live in pinned host memory, else on `device`."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    B, H, W = PAIRS_PER_GPU, PAD_H, PAD_W
+
+    def make(shape, kind):
+        # generated on the device with a seeded generator; the pinned-host variant is then copied out, so the
+        # end-to-end loop really starts from host memory
+        if kind == "image":
+            x = torch.rand(shape, generator=g, device=device)
+        elif kind == "flow":
+            x = (torch.randn(shape, generator=g, device=device) * 4.0).clamp_(-20, 20)
+        elif kind == "filter":
+            x = torch.softmax(torch.randn(shape, generator=g, device=device), dim=1)
+        elif kind == "depth":
+            x = torch.rand(shape, generator=g, device=device) * 0.9 + 0.1
+        else:
+            x = torch.randn(shape, generator=g, device=device)
+        if not pinned_host:
+            return x
+        h = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+        h.copy_(x)
+        return h
+
+    d = {}
+    for k in (0, 1):   # the two temporal directions
+        d[f"frame{k}"] = make((B, 3, H, W), "image")
+        d[f"flow{k}"] = make((B, 2, H, W), "flow")
+        d[f"filter{k}"] = make((B, 16, H, W), "filter")
+        d[f"rawflow{k}"] = make((B, 2, H, W), "flow")
+    d["depth"] = make((B, 1, H, W), "depth")
+    for lvl, (C, s) in enumerate(PWC_LEVELS):
+        for k in (0, 1):
+            d[f"feat{lvl}_{k}"] = make((B, C, H // s, W // s), "normal")
+    return d
+
+
+def run_step(V, mods, d, fi_events=None):
+    """One pass of the hot path over one batch.  Returns the two warped frame batches."""
+    corr, dproj, fi = mods
+    outs = []
+    for lvl in range(len(PWC_LEVELS)):
+        a, b = d[f"feat{lvl}_0"], d[f"feat{lvl}_1"]
+        outs.append(corr(a, b))     # direction 0 -> 1
+        outs.append(corr(b, a))     # direction 1 -> 0
+    p0 = dproj(d["rawflow0"], d["depth"])
+    p1 = dproj(d["rawflow1"], d["depth"])
+    warped = []
+    for k in (0, 1):
+        if fi_events is not None:
+            fi_events[k][0].record()
+        warped.append(fi(d[f"frame{k}"], d[f"flow{k}"], d[f"filter{k}"]))
+        if fi_events is not None:
+            fi_events[k][1].record()
+    return warped, (p0, p1), outs
+
+
+def bench_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    import vfidkr_b200 as V
+    mods = (V.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1),
+            V.DepthFlowProjectionModule(requires_grad=False), V.FilterInterpolationModule())
+
+    d = build_inputs(torch, device, seed=1004 + rank)
+    n_px = PAIRS_PER_GPU * PAD_H * PAD_W
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            run_step(V, mods, d)
+        sync_all()
+
+        # ---- device-resident timing ----
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in (0, 1)]
+              for _ in range(args.steps)]
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = V.launch_count()
+        sync_all()
+        t0.record()
+        for s in range(args.steps):
+            run_step(V, mods, d, ev[s])
+        t1.record()
+        sync_all()
+        launches = V.launch_count() - launches0
+        clocks = sampler.stop()
+        ms_total = t0.elapsed_time(t1)
+        fi_ms = [e[0].elapsed_time(e[1]) for step in ev for e in step]
+        fi_avg_ms = sum(fi_ms) / len(fi_ms)
+
+        # ---- end to end: pinned host inputs -> device -> step -> frames back on the host ----
+        e2e = None
+        if not args.no_e2e:
+            hd = build_inputs(torch, device, seed=2004 + rank, pinned_host=True)
+            h2d = sum(t.numel() * 4 for t in hd.values())
+            host_out = torch.empty((2, PAIRS_PER_GPU, 3, PAD_H, PAD_W), dtype=torch.float32, pin_memory=True)
+            d2h = host_out.numel() * 4
+            e_steps = min(args.steps, args.e2e_steps)
+
+            def e2e_step():
+                dd = {k: t.to(device, non_blocking=True) for k, t in hd.items()}
+                warped, _, _ = run_step(V, mods, dd)
+                host_out[0].copy_(warped[0], non_blocking=True)
+                host_out[1].copy_(warped[1], non_blocking=True)
+            e2e_step()
+            sync_all()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(e_steps):
+                e2e_step()
+            e1.record()
+            sync_all()
+            e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+            e2e_units = torch.tensor([float(e_steps * PAIRS_PER_GPU)], dtype=torch.float64, device=device)
+            reduce_timing(e2e_ms, e2e_units)
+            e2e = {"value": float(e2e_units.item()) * FRAME_PIXELS / (e2e_ms.item() * 1e-3) / 1e6, "unit": "Mpixel/s",
+                   "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps}
+            del hd, host_out
+
+    t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
+    units = torch.tensor([float(args.steps * PAIRS_PER_GPU)], dtype=torch.float64, device=device)   # frames out
+    nl = torch.tensor([float(launches)], dtype=torch.float64, device=device)
+    reduce_timing(t_ms, units)
+    if world > 1:
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    value = float(units.item()) * FRAME_PIXELS / (t_ms.item() * 1e-3) / 1e6
+
+    peak, peak_src = measured_peak()
+    achieved = FI_BYTES_PER_PIXEL * n_px / (fi_avg_ms * 1e-3) / 1e9
+    line = {
+        "metric": "interpolated Mpixel/s (1080p)", "value": value, "unit": "Mpixel/s",
+        "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": t_ms.item() / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1080p_pair_inference_b8: 10x correlation fwd (5 PWC levels x 2 dirs) + "
+                               "2x DepthFlowProjection fwd (fillhole) + 2x FilterInterpolation_ori fwd (C=3,F=4)",
+                   "pairs_per_gpu": PAIRS_PER_GPU, "frame": "1920x1080 padded to 1152x1984",
+                   "parallelism": f"pair-sharded x{world}, no data-path collective",
+                   "l2": "inputs_exceed_l2 (one step streams > 4 GB, L2 is 126 MB)"},
+        "roofline": {"bound": "hbm", "kernel": "fi_forward_ori_kernel<4>", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": FI_BYTES_PER_PIXEL * n_px,
+                     "avg_launch_ms": fi_avg_ms},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(nl.item()),
+    }
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_arm(steps=5, warmup=1)
+        print(json.dumps(line), flush=True)
+    if args.table and rank == 0 and world == 1:
+        op_table(torch, V, device, args.table)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU arm (oracle port)
+def cpu_reference_arm(steps=1, warmup=0):
+    """Times the CPU oracle on a bounded sample of the same workload: ONE frame pair (of the 8 per step),
+    every op of the step, all host threads OpenMP gives it."""
+    import numpy as np
+    from oracle import oracle as O
+    O.build()
+    r = np.random.default_rng(1004)
+    H, W = PAD_H, PAD_W
+    frames = [r.random((1, 3, H, W), dtype=np.float32) for _ in (0, 1)]
+    flows = [np.clip(r.standard_normal((1, 2, H, W)) * 4, -20, 20).astype(np.float32) for _ in range(4)]
+    z = [r.standard_normal((1, 16, H, W)).astype(np.float32) for _ in (0, 1)]
+    filts = [np.exp(a - a.max(1, keepdims=True)) for a in z]
+    filts = [(a / a.sum(1, keepdims=True)).astype(np.float32) for a in filts]
+    depth = (0.1 + 0.9 * r.random((1, 1, H, W), dtype=np.float32)).astype(np.float32)
+    feats = [[r.standard_normal((1, C, H // s, W // s)).astype(np.float32) for _ in (0, 1)] for C, s in PWC_LEVELS]
+
+    def step():
+        for a, b in feats:
+            O.correlation_forward(a, b, 4, 1, 4, 1, 1)
+            O.correlation_forward(b, a, 4, 1, 4, 1, 1)
+        O.flowprojection_forward(flows[2], depth, 1)
+        O.flowprojection_forward(flows[3], depth, 1)
+        for k in (0, 1):
+            O.fi_forward("ori", frames[k], flows[k], filts[k])
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    return {"value": steps * 1 * FRAME_PIXELS / dt / 1e6, "unit": "Mpixel/s", "cores": O.num_threads(),
+            "kind": "port", "sample": "1 frame pair of the 8 per step (all 14 op calls of the step), float64 C oracle + OpenMP",
+            "seconds": dt, "steps": steps}
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    res = cpu_reference_arm(steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    line = {
+        "impl": "reference", "metric": "interpolated Mpixel/s (1080p)", "value": res["value"], "unit": "Mpixel/s",
+        "n_gpus": world, "steps": res["steps"], "warmup": 1 if args.warmup > 0 else 0,
+        "ms_per_step": res["seconds"] / res["steps"] * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "1080p_pair_inference_b8 (bounded sample: 1 pair per step)", "pairs_per_gpu": PAIRS_PER_GPU,
+                   "frame": "1920x1080 padded to 1152x1984",
+                   "note": "the reference has no CPU implementation of this path and its CUDA extensions do not build "
+                           "here; this arm is the float64 CPU oracle port on the host cores"},
+        "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": res["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- per-op table (not the bench line)
+def op_table(torch, V, device, path):
+    """Per-operator device timings at the config-4 shape with achieved GB/s against SURVEY.md 8a bytes/pixel.
+    Written to `path` as JSON lines; this is the optimisation dashboard, not the headline."""
+    B, H, W = PAIRS_PER_GPU, PAD_H, PAD_W
+    peak, _ = measured_peak()
+    rows = []
+
+    def timeit(fn, iters=5):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    def add(name, ms, bytes_per_px, px):
+        gbs = bytes_per_px * px / (ms * 1e-3) / 1e9
+        rows.append({"op": name, "ms": ms, "algorithmic_GB": bytes_per_px * px / 1e9, "GBps": gbs, "frac_of_hbm": gbs / peak})
+
+    px = B * H * W
+    I = torch.rand(B, 3, H, W, device=device)
+    fl = (torch.randn(B, 2, H, W, device=device) * 4).clamp_(-20, 20)
+    ft = torch.softmax(torch.randn(B, 16, H, W, device=device), 1)
+    off = (torch.rand(B, 32, H, W, device=device) - 0.5) * 0.9
+    dep = torch.rand(B, 1, H, W, device=device) * 0.9 + 0.1
+    g = torch.randn(B, 3, H, W, device=device)
+    g2 = torch.randn(B, 2, H, W, device=device)
+    with torch.no_grad():
+        add("FI_ori_fwd_C3", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl, ft)), 96, px)
+        add("FI_dkr_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDKR.apply(I, fl, ft, off)), 224, px)
+        add("FI_deforconv_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDeforConv.apply(I, fl, ft, off)), 224, px)
+        add("FI_nofilter_fwd_C3", timeit(lambda: V.FilterInterpolationLayerNoFilterWithDeforConv.apply(I, fl, off)), 160, px)
+        add("Interpolation_fwd_C3", timeit(lambda: V.InterpolationLayer.apply(I, fl)), 32, px)
+        add("FlowProjection_fwd_fill", timeit(lambda: V.FlowProjectionLayer.apply(fl, False)), 20, px)
+        add("FlowProjection_fwd", timeit(lambda: V.FlowProjectionLayer.apply(fl, True)), 20, px)
+        add("DepthFlowProjection_fwd_fill", timeit(lambda: V.DepthFlowProjectionLayer.apply(fl, dep, False)), 24, px)
+    # backward timings through the C ABI directly (no autograd bookkeeping in the timed region)
+    from vfidkr_b200 import _lib
+    from vfidkr_b200._common import ptr, stream_ptr
+    sp = stream_ptr(device)
+    gi1, gi2, gi3, gi4 = torch.empty_like(I), torch.empty_like(fl), torch.empty_like(ft), torch.empty_like(off)
+    add("FI_ori_bwd_C3", timeit(lambda: _lib.call("vfidkr_filterinterpolation_backward_ori", ptr(I), ptr(fl), ptr(ft), ptr(g),
+                                                   ptr(gi1), ptr(gi2), ptr(gi3), B, 3, H, W, 4, sp)), 180, px)
+    add("FI_dkr_bwd_C3", timeit(lambda: _lib.call("vfidkr_filterinterpolation_backward_dkr", ptr(I), ptr(fl), ptr(ft), ptr(off),
+                                                   ptr(g), ptr(gi1), ptr(gi2), ptr(gi3), ptr(gi4), B, 3, H, W, 4, sp)), 436, px)
+    add("FI_deforconv_bwd_C3", timeit(lambda: _lib.call("vfidkr_filterinterpolation_backward_deforconv", ptr(I), ptr(fl), ptr(ft),
+                                                         ptr(off), ptr(g), ptr(gi1), ptr(gi2), ptr(gi3), ptr(gi4), B, 3, H, W, 4, sp)), 436, px)
+    add("Interpolation_bwd_C3", timeit(lambda: _lib.call("vfidkr_interpolation_backward", ptr(I), ptr(fl), ptr(g), ptr(gi1), ptr(gi2),
+                                                          B, 3, H, W, 1, sp)), 52, px)
+    cnt = torch.empty(B, 1, H, W, device=device)
+    po = torch.empty(B, 2, H, W, device=device)
+    gd = torch.empty(B, 1, H, W, device=device)
+    _lib.call("vfidkr_depthflowprojection_forward", ptr(fl), ptr(dep), ptr(cnt), ptr(po), B, H, W, 0, sp)
+    add("DepthFlowProjection_bwd", timeit(lambda: _lib.call("vfidkr_depthflowprojection_backward", ptr(fl), ptr(dep), ptr(cnt), ptr(po),
+                                                             ptr(g2), ptr(gi2), ptr(gd), B, H, W, sp)), 44, px)
+    _lib.call("vfidkr_flowprojection_forward", ptr(fl), ptr(cnt), ptr(po), B, H, W, 0, sp)
+    add("FlowProjection_bwd", timeit(lambda: _lib.call("vfidkr_flowprojection_backward", ptr(fl), ptr(cnt), ptr(g2), ptr(gi2), B, H, W, sp)), 28, px)
+    del I, ft, off, g, gi1, gi3, gi4
+    torch.cuda.empty_cache()
+    with torch.no_grad():
+        corr = V.Correlation(4, 1, 4, 1, 1, 1)
+        for C, s in PWC_LEVELS:
+            a = torch.randn(B, C, H // s, W // s, device=device)
+            b = torch.randn_like(a)
+            add(f"Correlation_fwd_C{C}_{H // s}x{W // s}", timeit(lambda: corr(a, b)), 4 * (2 * C + 81), B * (H // s) * (W // s))
+        # the 196-channel context warp of DAIN_slowmotion, once (two batch items keep it at 7 GB)
+        Bc = 2
+        ctx = torch.rand(Bc, 196, H, W, device=device)
+        ftc = torch.softmax(torch.randn(Bc, 16, H, W, device=device), 1)
+        add("FI_ori_fwd_C196_B2", timeit(lambda: V.FilterInterpolationLayer.apply(ctx, fl[:Bc].contiguous(), ftc), iters=3),
+            4 * (2 * 196 + 18), Bc * H * W)
+    with open(path, "w") as f:
+        for r in rows:
+            f.write(json.dumps(r) + "\n")
+    for r in rows:
+        print(f"[op] {r['op']:34s} {r['ms']*1e3:10.1f} us  {r['GBps']:8.1f} GB/s  {100*r['frac_of_hbm']:5.1f} % of HBM peak", file=sys.stderr)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=5, help="cap on the (PCIe-bound) end-to-end steps")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--table", default=None, help="also write the per-operator timing table (JSON lines) here")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        bench_reference(args)
+    else:
+        bench_ours(args)
+
+
+if __name__ == "__main__":
+    main()

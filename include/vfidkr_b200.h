@@ -1,0 +1,179 @@
+/*
+ * vfidkr_b200.h -- C ABI of libvfidkr_b200.so: hand-written sm_100a CUDA kernels for the
+ * per-pixel sampling / warping hot path of VFIDKR.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one symbol of the reference's
+ * pybind11 extension modules (all citations relative to /root/reference/).  The reference
+ * symbols take at::Tensor&; these take the same tensors as raw DEVICE pointers + sizes, so
+ * the library has no torch (or any other framework) type in its signatures.
+ *
+ * Common contract
+ *   - All tensors are float32, NCHW, contiguous (the reference asserts is_contiguous() in
+ *     Python, e.g. FilterInterpolationLayer.py:16-18, and checks W-stride == 1 in C++,
+ *     filterinterpolation_cuda.cc:579-581).
+ *   - The caller owns every buffer; the library never allocates and never synchronises.
+ *     Work is enqueued on `stream` (the reference uses at::cuda::getCurrentCUDAStream(),
+ *     filterinterpolation_cuda.cc:590).
+ *   - Unlike the reference, outputs need NOT be zero-filled by the caller: every element
+ *     of every output/gradient buffer is written (accumulation targets are cleared on the
+ *     stream by the library itself).
+ *   - Return value: 0 on success; VFIDKR_ERR_ARG (1) for an argument the reference's .cc
+ *     glue rejects with `return error` (shape mismatch); VFIDKR_ERR_CUDA (2) when the launch
+ *     failed (the reference raises AT_ERROR("CUDA call failed") there).  The reference's
+ *     correlation module inverts the convention (1 = success, correlation_cuda_kernel.cu:417-426);
+ *     this ABI does not.
+ *   - Thread-safe: no global mutable state except a relaxed launch counter.
+ */
+#ifndef VFIDKR_B200_H_
+#define VFIDKR_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* cudaStream_t without pulling in the CUDA headers */
+typedef struct CUstream_st *vfidkr_stream_t;
+
+#define VFIDKR_OK 0
+#define VFIDKR_ERR_ARG 1
+#define VFIDKR_ERR_CUDA 2
+
+/* ---- library info ------------------------------------------------------------------- */
+/* ABI version (major*100+minor). */
+int vfidkr_abi_version(void);
+/* Number of kernel launches issued by this library since load (all threads). */
+unsigned long long vfidkr_launch_count(void);
+/* Text of the last CUDA error seen by the calling thread ("" if none). */
+const char *vfidkr_last_error(void);
+
+/* ---- FilterInterpolation: adaptive warping with per-pixel F x F filters ------------------
+ * input1 [B,C,H,W] image/features   input2 [B,2,H,W] flow (x,y)   input3 [B,F*F,H,W] filter
+ * input4 [B,2*F*F,H,W] DKR offset field (y-offsets in channels [0,F*F), x-offsets after)
+ * filter_size F: any F >= 1 (fast path for F == 4, the only size VFIDKR uses).
+ */
+
+/* replaces filterinterpolation_cuda.FilterInterpolationLayer_gpu_forward_ori
+ * (filterinterpolation_cuda.cc:537-606; kernel filterinterpolation_cuda_kernel.cu:2692-2823) */
+int vfidkr_filterinterpolation_forward_ori(const float *input1, const float *input2, const float *input3,
+                                           float *output, int B, int C, int H, int W, int filter_size,
+                                           vfidkr_stream_t stream);
+/* replaces ..._gpu_backward_ori (filterinterpolation_cuda.cc:608-687; kernel :2827-3125) */
+int vfidkr_filterinterpolation_backward_ori(const float *input1, const float *input2, const float *input3,
+                                            const float *gradoutput, float *gradinput1, float *gradinput2,
+                                            float *gradinput3, int B, int C, int H, int W, int filter_size,
+                                            vfidkr_stream_t stream);
+
+/* replaces FilterInterpolationLayer_gpu_forward / _gpu_backward, the 4-input DKR family with
+ * static quadrants (filterinterpolation_cuda.cc:11-187; kernels :29-426, :430-1215).
+ * As in the reference the forward only computes for F in {4,6} (:68) and writes zeros otherwise. */
+int vfidkr_filterinterpolation_forward_dkr(const float *input1, const float *input2, const float *input3,
+                                           const float *input4, float *output,
+                                           int B, int C, int H, int W, int filter_size, vfidkr_stream_t stream);
+int vfidkr_filterinterpolation_backward_dkr(const float *input1, const float *input2, const float *input3,
+                                            const float *input4, const float *gradoutput,
+                                            float *gradinput1, float *gradinput2, float *gradinput3,
+                                            float *gradinput4, int B, int C, int H, int W, int filter_size,
+                                            vfidkr_stream_t stream);
+
+/* replaces ..._gpu_forward_deforconv / _gpu_backward_deforconv, DKR with data-dependent quadrants
+ * (filterinterpolation_cuda.cc:191-367; kernels :1353-1496, :1500-1935) */
+int vfidkr_filterinterpolation_forward_deforconv(const float *input1, const float *input2, const float *input3,
+                                                 const float *input4, float *output,
+                                                 int B, int C, int H, int W, int filter_size,
+                                                 vfidkr_stream_t stream);
+int vfidkr_filterinterpolation_backward_deforconv(const float *input1, const float *input2, const float *input3,
+                                                  const float *input4, const float *gradoutput,
+                                                  float *gradinput1, float *gradinput2, float *gradinput3,
+                                                  float *gradinput4, int B, int C, int H, int W, int filter_size,
+                                                  vfidkr_stream_t stream);
+
+/* replaces ..._gpu_forward_nofilterwithdeforconv / _gpu_backward_nofilterwithdeforconv
+ * (filterinterpolation_cuda.cc:374-533; kernels :2070-2191, :2195-2567).
+ * Here input3 / gradinput3 are the [B,2*F*F,H,W] offset field and its gradient. */
+int vfidkr_filterinterpolation_forward_nofilterwithdeforconv(const float *input1, const float *input2,
+                                                             const float *input3, float *output,
+                                                             int B, int C, int H, int W, int filter_size,
+                                                             vfidkr_stream_t stream);
+int vfidkr_filterinterpolation_backward_nofilterwithdeforconv(const float *input1, const float *input2,
+                                                              const float *input3, const float *gradoutput,
+                                                              float *gradinput1, float *gradinput2,
+                                                              float *gradinput3, int B, int C, int H, int W,
+                                                              int filter_size, vfidkr_stream_t stream);
+
+/* ---- FlowProjection / DepthFlowProjection: forward splat of -flow with atomics -----------
+ * input1 [B,2,H,W] flow; input2 [B,1,H,W] inverse depth (> 0); count [B,1,H,W]; output [B,2,H,W].
+ * fillhole != 0 runs the hole-filling pass (inference; FlowProjectionLayer.py:23).
+ */
+/* replaces flowprojection_cuda.FlowProjectionLayer_gpu_forward / _gpu_backward
+ * (flowprojection_cuda.cc:9-114; kernels flowprojection_cuda_kernel.cu:29-301) */
+int vfidkr_flowprojection_forward(const float *input1, float *count, float *output,
+                                  int B, int H, int W, int fillhole, vfidkr_stream_t stream);
+int vfidkr_flowprojection_backward(const float *input1, const float *count, const float *gradoutput,
+                                   float *gradinput1, int B, int H, int W, vfidkr_stream_t stream);
+/* replaces depthflowprojection_cuda.DepthFlowProjectionLayer_gpu_forward / _gpu_backward
+ * (depthflowprojection_cuda.cc:10-143; kernels depthflowprojection_cuda_kernel.cu:29-341) */
+int vfidkr_depthflowprojection_forward(const float *input1, const float *input2, float *count, float *output,
+                                       int B, int H, int W, int fillhole, vfidkr_stream_t stream);
+int vfidkr_depthflowprojection_backward(const float *input1, const float *input2, const float *count,
+                                        const float *output, const float *gradoutput,
+                                        float *gradinput1, float *gradinput2,
+                                        int B, int H, int W, vfidkr_stream_t stream);
+
+/* ---- Interpolation / InterpolationCh: bilinear backward warp, zero fill ---------------------
+ * replaces interpolation_cuda.InterpolationLayer_gpu_forward / _gpu_backward
+ * (interpolation_cuda.cc:10-121; kernels interpolation_cuda_kernel.cu:29-204) and the identical
+ * interpolationch_cuda twins.  `require_c3` != 0 reproduces Interpolation's C == 3 check
+ * (interpolation_cuda.cc:19); InterpolationCh passes 0.
+ */
+int vfidkr_interpolation_forward(const float *input1, const float *input2, float *output,
+                                 int B, int C, int H, int W, int require_c3, vfidkr_stream_t stream);
+int vfidkr_interpolation_backward(const float *input1, const float *input2, const float *gradoutput,
+                                  float *gradinput1, float *gradinput2,
+                                  int B, int C, int H, int W, int require_c3, vfidkr_stream_t stream);
+
+/* ---- SeparableConv / SeparableConvFlow ---------------------------------------------------------
+ * input1 [B,C,H,W]; input2 (vertical) / input3 (horizontal) [B,F,H-F+1,W-F+1].
+ * replaces separableconv_cuda.SeparableConvLayer_gpu_forward / _gpu_backward
+ * (separableconv_cuda.cc:10-176, C == 3 enforced at :21; kernels separableconv_cuda_kernel.cu:29-135)
+ */
+int vfidkr_separableconv_forward(const float *input1, const float *input2, const float *input3, float *output,
+                                 int B, int C, int H, int W, int filter_size, vfidkr_stream_t stream);
+int vfidkr_separableconv_backward(const float *input1, const float *input2, const float *input3,
+                                  const float *gradoutput, float *gradinput1, float *gradinput2,
+                                  float *gradinput3, int B, int C, int H, int W, int filter_size,
+                                  vfidkr_stream_t stream);
+/* replaces separableconvflow_cuda.SeparableConvFlowLayer_gpu_forward / _gpu_backward
+ * (separableconvflow_cuda.cc; kernels separableconvflow_cuda_kernel.cu:29-174).
+ * flow_output [B,2,Ho,Wo]; input1 only contributes its shape (H = Ho+F-1, W = Wo+F-1) and a zero gradient. */
+int vfidkr_separableconvflow_forward(const float *input2, const float *input3, float *flow_output,
+                                     int B, int Ho, int Wo, int filter_size, vfidkr_stream_t stream);
+int vfidkr_separableconvflow_backward(const float *input2, const float *input3, const float *gradflow_output,
+                                      float *gradinput2, float *gradinput3,
+                                      int B, int Ho, int Wo, int filter_size, vfidkr_stream_t stream);
+
+/* ---- Correlation (FlowNet / PWC-Net cost volume) -----------------------------------------------
+ * replaces correlation_cuda.forward / backward (correlation_cuda.cc:8-165; kernels
+ * correlation_cuda_kernel.cu:47-334).  Reads NCHW directly: the reference's rbot1/rbot2 padded
+ * NHWC scratch tensors are not needed.  output [B,OC,OH,OW] with the shape rules of
+ * correlation_cuda.cc:23-36 (use vfidkr_correlation_outshape).  corr_type_multiply is accepted
+ * and ignored exactly as the reference ignores it.  Backward is in-contract for stride1 == 1
+ * and pad_size >= max_displacement (the reference reads out of bounds otherwise).
+ */
+int vfidkr_correlation_outshape(int H, int W, int pad_size, int kernel_size, int max_displacement,
+                                int stride1, int stride2, int *out_channels, int *out_h, int *out_w);
+int vfidkr_correlation_forward(const float *input1, const float *input2, float *output,
+                               int B, int C, int H, int W, int pad_size, int kernel_size,
+                               int max_displacement, int stride1, int stride2, int corr_type_multiply,
+                               vfidkr_stream_t stream);
+int vfidkr_correlation_backward(const float *input1, const float *input2, const float *gradoutput,
+                                float *gradinput1, float *gradinput2,
+                                int B, int C, int H, int W, int pad_size, int kernel_size,
+                                int max_displacement, int stride1, int stride2, int corr_type_multiply,
+                                vfidkr_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VFIDKR_B200_H_ */

@@ -36,6 +36,16 @@
 static inline int imin(int a, int b) { return a < b ? a : b; }
 static inline int imax(int a, int b) { return a > b ? a : b; }
 static inline int iclamp(int v, int lo, int hi) { return imin(imax(v, lo), hi); }
+/* float -> int truncation toward zero.  In C the conversion is undefined outside the int range; CUDA's
+ * cvt.rzi.s32.f32 saturates and maps NaN to 0.  The oracle adopts the CUDA definition so that
+ * out-of-contract offsets (DKR families) stay defined. */
+static inline int f2i_rz(float v)
+{
+    if (v != v) return 0;
+    if (v >= 2147483648.0f) return 2147483647;
+    if (v <= -2147483648.0f) return (-2147483647 - 1);
+    return (int)v;
+}
 
 /* ------------------------------------------------------------------------------------------
  * FilterInterpolation -- four kernel families behind one restatement.
@@ -91,11 +101,12 @@ static fi_deform_t fi_deform(int cy, int cx, float offY, float offX)
     volatile float fy = (float)cy + offY;   /* float fracY = _filter_j + input4[...]  :98 */
     volatile float fx = (float)cx + offX;   /* :99 */
     d.fracY = fy; d.fracX = fx;
-    d.Top = (int)fy; d.Left = (int)fx;      /* :102-103 truncation toward zero */
+    d.Top = f2i_rz(fy); d.Left = f2i_rz(fx); /* :102-103 truncation toward zero */
     volatile float py = fy - (float)d.Top;  /* :100 */
     volatile float px = fx - (float)d.Left; /* :101 */
     d.phiY = py; d.phiX = px;
-    d.Bottom = d.Top + 1; d.Right = d.Left + 1; /* :104-105, NOT clamped in the reference */
+    /* :104-105, NOT clamped in the reference (+1 guarded against int overflow) */
+    d.Bottom = d.Top < 2147483647 ? d.Top + 1 : d.Top; d.Right = d.Left < 2147483647 ? d.Left + 1 : d.Left;
     return d;
 }
 

@@ -1,0 +1,381 @@
+"""Parity of the sm_100a kernels (called through the reference-shaped Python API, which goes through the
+C ABI) against the float64 CPU oracle on identical seeded inputs.
+
+Tolerances (BASELINE.json north_star): 1e-5 for fp32 forward outputs and thread-private gradients,
+1e-4 for atomically accumulated results; exact for counts.  The error measure is
+|gpu - oracle| / (|oracle| + max|oracle|)  (tests/util.py)."""
+import numpy as np
+import pytest
+import torch
+
+import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _native_library_is_loaded(lib):
+    lib._lib.load()
+    before = lib.launch_count()
+    yield
+    assert lib.launch_count() > before, "no kernel of libvfidkr_b200.so was launched by the GPU tests"
+
+
+# ------------------------------------------------------------------------------ FilterInterpolation _ori
+FI_SHAPES = [  # B, C, H, W, flow kind, filter kind
+    (1, 3, 256, 448, "gauss", "softmax"),     # BASELINE config 1
+    (1, 3, 256, 448, "unit", "uniform"),      # test_module.py recipe
+    (2, 3, 37, 29, "stress", "uniform"),      # ragged, out-of-range pixels, border landings
+    (1, 1, 1, 1, "unit", "uniform"),
+    (1, 2, 3, 5, "unit", "softmax"),
+    (2, 5, 40, 70, "smooth", "softmax"),
+    (1, 196, 24, 40, "gauss", "softmax"),     # DAIN_slowmotion context width
+    (3, 4, 33, 130, "gauss", "uniform"),
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,fk,wk", FI_SHAPES)
+def test_fi_ori_forward_backward(lib, oracle, B, C, H, W, fk, wk):
+    r = U.rng(1001)
+    I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, fk), U.filt(r, B, 4, H, W, wk)
+    ti, tf, tw = cu(I).requires_grad_(), cu(fl).requires_grad_(), cu(ft).requires_grad_()
+    out = lib.FilterInterpolationModule()(ti, tf, tw)
+    U.assert_close(host(out), oracle.fi_forward("ori", I, fl, ft), U.RTOL_FWD, "fi_ori forward")
+    g = U.image(r, B, C, H, W, "normal")
+    out.backward(cu(g))
+    gi1, gi2, gi3, _ = oracle.fi_backward("ori", I, fl, ft, None, g)
+    U.assert_close(host(ti.grad), gi1, U.RTOL_ATOMIC, "fi_ori gradinput1 (atomic scatter)")
+    U.assert_close(host(tf.grad), gi2, U.RTOL_FWD, "fi_ori gradinput2")
+    U.assert_close(host(tw.grad), gi3, U.RTOL_FWD, "fi_ori gradinput3")
+
+
+@pytest.mark.parametrize("F", [2, 5, 6])
+def test_fi_ori_runtime_filter_sizes(lib, oracle, F):
+    r = U.rng(1002 + F)
+    B, C, H, W = 2, 3, 31, 45
+    I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "stress"), U.filt(r, B, F, H, W, "uniform")
+    ti, tf, tw = cu(I).requires_grad_(), cu(fl).requires_grad_(), cu(ft).requires_grad_()
+    out = lib.FilterInterpolationModule()(ti, tf, tw)
+    U.assert_close(host(out), oracle.fi_forward("ori", I, fl, ft), U.RTOL_FWD, f"fi_ori F={F} forward")
+    g = U.image(r, B, C, H, W, "normal")
+    out.backward(cu(g))
+    gi1, gi2, gi3, _ = oracle.fi_backward("ori", I, fl, ft, None, g)
+    U.assert_close(host(ti.grad), gi1, U.RTOL_ATOMIC, "gradinput1")
+    U.assert_close(host(tf.grad), gi2, U.RTOL_FWD, "gradinput2")
+    U.assert_close(host(tw.grad), gi3, U.RTOL_FWD, "gradinput3")
+
+
+def test_fi_ori_training_step_batch16(lib, oracle):
+    """BASELINE config 3: fwd+bwd at B=16, 256x448, upstream gradient = the output (test_module.py:226)."""
+    r = U.rng(1003)
+    B, C, H, W = 16, 3, 256, 448
+    I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "gauss"), U.filt(r, B, 4, H, W)
+    ti, tf, tw = cu(I).requires_grad_(), cu(fl).requires_grad_(), cu(ft).requires_grad_()
+    out = lib.FilterInterpolationModule()(ti, tf, tw)
+    ref = oracle.fi_forward("ori", I, fl, ft)
+    U.assert_close(host(out), ref, U.RTOL_FWD, "forward")
+    out.backward(out.detach())
+    g = host(out)
+    gi1, gi2, gi3, _ = oracle.fi_backward("ori", I, fl, ft, None, g)
+    U.assert_close(host(ti.grad), gi1, U.RTOL_ATOMIC, "gradinput1")
+    U.assert_close(host(tf.grad), gi2, U.RTOL_FWD, "gradinput2")
+    U.assert_close(host(tw.grad), gi3, U.RTOL_FWD, "gradinput3")
+
+
+def test_fi_known_answers_on_gpu(lib):
+    r = U.rng(1004)
+    I = U.image(r, 2, 3, 40, 52)
+    ft = np.zeros((2, 16, 40, 52), np.float32)
+    ft[:, 5] = 1
+    zero = np.zeros((2, 2, 40, 52), np.float32)
+    out = lib.FilterInterpolationModule()(cu(I), cu(zero), cu(ft))
+    assert torch.equal(out.cpu(), torch.from_numpy(I))                      # KAT 1, bit exact
+    far = zero.copy()
+    far[:, 0] = 26.0                                                         # |fx| >= W/2
+    out = lib.FilterInterpolationModule()(cu(I), cu(far), cu(U.filt(r, 2, 4, 40, 52)))
+    assert torch.equal(out.cpu(), torch.from_numpy(I))                      # KAT 3: copy, not zero
+    ft2 = np.zeros((2, 16, 40, 52), np.float32)
+    ft2[:, [5, 6, 9, 10]] = 1
+    fl = U.flow(r, 2, 40, 52, "gauss")
+    a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft2))
+    b = lib.InterpolationChModule(3)(cu(I), cu(fl))
+    x2 = np.arange(52, dtype=np.float32)[None, None, :] + fl[:, 0]
+    y2 = np.arange(40, dtype=np.float32)[None, :, None] + fl[:, 1]
+    m = (x2 >= 0) & (y2 >= 0) & (x2 <= 51) & (y2 <= 39) & (np.abs(fl[:, 0]) < 26) & (np.abs(fl[:, 1]) < 20)
+    m = np.broadcast_to(m[:, None], I.shape)
+    assert np.abs(host(a) - host(b))[m].max() < 1e-5                        # KAT 2
+
+
+# ------------------------------------------------------------------------------ DKR families
+DKR_SHAPES = [(1, 3, 256, 448), (2, 3, 37, 29), (1, 5, 20, 33), (1, 1, 2, 3)]
+
+
+@pytest.mark.parametrize("variant", ["dkr", "deforconv", "nofilterwithdeforconv"])
+@pytest.mark.parametrize("B,C,H,W", DKR_SHAPES)
+def test_fi_dkr_families(lib, oracle, variant, B, C, H, W):
+    r = U.rng(1100 + len(variant))
+    F = 4
+    I, fl = U.image(r, B, C, H, W), U.flow(r, B, H, W, "stress" if H > 8 else "unit")
+    ft, off = U.filt(r, B, F, H, W, "uniform"), U.offsets(r, B, F, H, W, 0.45)
+    ti, tf = cu(I).requires_grad_(), cu(fl).requires_grad_()
+    g = U.image(r, B, C, H, W, "normal")
+    if variant == "nofilterwithdeforconv":
+        to = cu(off).requires_grad_()
+        out = lib.FilterInterpolationModule(variant)(ti, tf, to)
+        U.assert_close(host(out), oracle.fi_forward(variant, I, fl, off), U.RTOL_FWD, f"{variant} forward")
+        out.backward(cu(g))
+        gi1, gi2, gi3, _ = oracle.fi_backward(variant, I, fl, off, None, g)
+        U.assert_close(host(to.grad), gi3, U.RTOL_FWD, "offset gradient")
+    else:
+        tw, to = cu(ft).requires_grad_(), cu(off).requires_grad_()
+        out = lib.FilterInterpolationModule(variant)(ti, tf, tw, to)
+        U.assert_close(host(out), oracle.fi_forward(variant, I, fl, ft, off), U.RTOL_FWD, f"{variant} forward")
+        out.backward(cu(g))
+        gi1, gi2, gi3, gi4 = oracle.fi_backward(variant, I, fl, ft, off, g)
+        U.assert_close(host(tw.grad), gi3, U.RTOL_FWD, "filter gradient")
+        U.assert_close(host(to.grad), gi4, U.RTOL_FWD, "offset gradient")
+    U.assert_close(host(ti.grad), gi1, U.RTOL_ATOMIC, "image gradient (atomic scatter)")
+    U.assert_close(host(tf.grad), gi2, U.RTOL_FWD, "flow gradient")
+
+
+@pytest.mark.parametrize("variant", ["dkr", "deforconv"])
+def test_fi_dkr_zero_offsets_equal_ori_on_gpu(lib, variant):
+    r = U.rng(1200)
+    B, C, H, W = 2, 3, 64, 80
+    I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "gauss"), U.filt(r, B, 4, H, W)
+    a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
+    b = lib.FilterInterpolationModule(variant)(cu(I), cu(fl), cu(ft), cu(np.zeros((B, 32, H, W), np.float32)))
+    assert U.max_err(host(b), host(a).astype(np.float64)) < 1e-6           # KAT 4
+
+
+def test_fi_dkr_wild_offsets_are_memory_safe_and_defined(lib, oracle):
+    """Outside the in-contract domain the reference reads out of the plane (undefined); the product and
+    the oracle define those reads by clamping the read index.  Runs without faulting and matches."""
+    r = U.rng(1201)
+    B, C, H, W, F = 1, 3, 24, 31, 4
+    I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "unit"), U.filt(r, B, F, H, W)
+    off = (r.standard_normal((B, 2 * F * F, H, W)) * 40).astype(np.float32)
+    for variant in ("dkr", "deforconv"):
+        out = lib.FilterInterpolationModule(variant)(cu(I), cu(fl), cu(ft), cu(off))
+        torch.cuda.synchronize()
+        ref = oracle.fi_forward(variant, I, fl, ft, off)
+        U.assert_close(host(out), ref, U.RTOL_ATOMIC, f"{variant} with out-of-contract offsets")
+
+
+def test_fi_dkr_forward_gate(lib, oracle):
+    r = U.rng(1202)
+    B, C, H, W, F = 1, 2, 16, 20, 5
+    args = [U.image(r, B, C, H, W), U.flow(r, B, H, W, "unit"), U.filt(r, B, F, H, W), U.offsets(r, B, F, H, W)]
+    out = lib.FilterInterpolationModule("dkr")(*map(cu, args))
+    assert not out.any()                                                    # F not in {4,6}: zeros
+    out = lib.FilterInterpolationModule("deforconv")(*map(cu, args))
+    U.assert_close(host(out), oracle.fi_forward("deforconv", *args), U.RTOL_FWD, "deforconv F=5")
+    args = [U.image(r, B, C, H, W), U.flow(r, B, H, W, "unit"), U.filt(r, B, 6, H, W), U.offsets(r, B, 6, H, W)]
+    out = lib.FilterInterpolationModule("dkr")(*map(cu, args))
+    U.assert_close(host(out), oracle.fi_forward("dkr", *args), U.RTOL_FWD, "dkr F=6")
+
+
+# ------------------------------------------------------------------------------ projection
+PROJ_SHAPES = [(1, 256, 448, "gauss"), (2, 37, 29, "stress"), (1, 1, 1, "unit"), (2, 64, 96, "smooth"), (1, 512, 704, "unit")]
+
+
+@pytest.mark.parametrize("B,H,W,fk", PROJ_SHAPES)
+@pytest.mark.parametrize("with_depth", [False, True])
+def test_projection_forward_backward(lib, oracle, B, H, W, fk, with_depth):
+    r = U.rng(1300)
+    fl = U.flow(r, B, H, W, fk)
+    d = U.depth_inv(r, B, H, W) if with_depth else None
+    for requires_grad in (True, False):      # False -> hole filling (inference)
+        tf = cu(fl).requires_grad_(requires_grad)
+        if with_depth:
+            td = cu(d).requires_grad_(requires_grad)
+            out = lib.DepthFlowProjectionModule(tf.requires_grad)(tf, td)
+        else:
+            out = lib.FlowProjectionModule(tf.requires_grad)(tf)
+        ref, cnt = oracle.flowprojection_forward(fl, d, 0 if requires_grad else 1)
+        U.assert_close(host(out), ref, U.RTOL_ATOMIC, f"projection forward fillhole={not requires_grad}")
+        if requires_grad:
+            g = r.standard_normal((B, 2, H, W)).astype(np.float32)
+            out.backward(cu(g))
+            # the backward consumes the forward's own fp32 count / output, as the reference does
+            gi1, gi2 = oracle.flowprojection_backward(fl, d, cnt.astype(np.float32), ref.astype(np.float32), g)
+            U.assert_close(host(tf.grad), gi1, U.RTOL_ATOMIC, "gradinput1")
+            if with_depth:
+                U.assert_close(host(td.grad), gi2, U.RTOL_ATOMIC, "gradinput2 (depth)")
+
+
+def test_flowprojection_count_is_bit_exact(lib, oracle):
+    """Counts are small integers in fp32: the splat targets (index arithmetic) must match exactly."""
+    from ctypes import c_void_p
+    from vfidkr_b200 import _lib
+    r = U.rng(1301)
+    B, H, W = 2, 97, 131
+    fl = U.flow(r, B, H, W, "stress")
+    tf = cu(fl)
+    count = torch.empty((B, 1, H, W), device="cuda")
+    out = torch.empty((B, 2, H, W), device="cuda")
+    _lib.call("vfidkr_flowprojection_forward", c_void_p(tf.data_ptr()), c_void_p(count.data_ptr()),
+              c_void_p(out.data_ptr()), B, H, W, 0, c_void_p(torch.cuda.current_stream().cuda_stream))
+    _, cnt = oracle.flowprojection_forward(fl, None, 0)
+    assert np.array_equal(host(count).astype(np.float64), cnt)
+
+
+def test_projection_known_answers_on_gpu(lib):
+    z = torch.zeros(1, 2, 6, 7, device="cuda")
+    out = lib.FlowProjectionModule(False)(z)
+    assert not out.any()
+    z[:, 0] = 1
+    out = lib.FlowProjectionModule(False)(z)
+    assert (out[0, 0] == -1).all() and (out[0, 1] == 0).all()               # KAT 6 incl. hole filling
+    fl = cu(U.flow(U.rng(5), 2, 30, 41, "unit"))
+    a = lib.FlowProjectionModule(True)(fl)
+    b = lib.DepthFlowProjectionModule(True)(fl, torch.ones(2, 1, 30, 41, device="cuda"))
+    assert U.max_err(host(b), host(a).astype(np.float64)) < 1e-6           # KAT 5
+
+
+# ------------------------------------------------------------------------------ Interpolation(Ch)
+@pytest.mark.parametrize("B,C,H,W,fk", [(1, 3, 256, 448, "gauss"), (2, 3, 37, 29, "stress"), (1, 7, 20, 33, "unit"), (1, 1, 1, 1, "unit")])
+def test_interpolation(lib, oracle, B, C, H, W, fk):
+    r = U.rng(1400)
+    I, fl = U.image(r, B, C, H, W), U.flow(r, B, H, W, fk)
+    ti, tf = cu(I).requires_grad_(), cu(fl).requires_grad_()
+    mod = lib.InterpolationModule() if C == 3 else lib.InterpolationChModule(C)
+    out = mod(ti, tf)
+    U.assert_close(host(out), oracle.interpolation_forward(I, fl), U.RTOL_FWD, "interpolation forward")
+    g = U.image(r, B, C, H, W, "normal")
+    out.backward(cu(g))
+    gi1, gi2 = oracle.interpolation_backward(I, fl, g)
+    U.assert_close(host(ti.grad), gi1, U.RTOL_ATOMIC, "gradinput1 (atomic scatter)")
+    U.assert_close(host(tf.grad), gi2, U.RTOL_FWD, "gradinput2")
+
+
+def test_interpolation_requires_three_channels(lib):
+    with pytest.raises(lib.VfidkrError):
+        lib.InterpolationModule()(torch.rand(1, 4, 8, 8, device="cuda"), torch.zeros(1, 2, 8, 8, device="cuda"))
+
+
+# ------------------------------------------------------------------------------ SeparableConv(Flow)
+@pytest.mark.parametrize("B,H,W,F", [(1, 128, 128, 51), (2, 20, 33, 5), (1, 9, 9, 9)])
+def test_separableconv(lib, oracle, B, H, W, F):
+    r = U.rng(1500)
+    C, Ho, Wo = 3, H - F + 1, W - F + 1
+    I = U.image(r, B, C, H, W)
+    v = (1.0 / F + 0.1 / F * r.random((B, F, Ho, Wo))).astype(np.float32)      # test_module.py:903-907
+    hz = (1.0 / F + 0.1 / F * r.random((B, F, Ho, Wo))).astype(np.float32)
+    ti, tv, th = cu(I).requires_grad_(), cu(v).requires_grad_(), cu(hz).requires_grad_()
+    out = lib.SeparableConvModule(F)(ti, tv, th)
+    U.assert_close(host(out), oracle.sepconv_forward(I, v, hz), U.RTOL_FWD * 3, "sepconv forward")
+    g = r.standard_normal((B, C, Ho, Wo)).astype(np.float32)
+    out.backward(cu(g))
+    gi1, gi2, gi3 = oracle.sepconv_backward(I, v, hz, g)
+    U.assert_close(host(ti.grad), gi1, U.RTOL_ATOMIC, "gradinput1")
+    U.assert_close(host(tv.grad), gi2, U.RTOL_ATOMIC, "gradinput2")
+    U.assert_close(host(th.grad), gi3, U.RTOL_ATOMIC, "gradinput3")
+
+
+@pytest.mark.parametrize("B,Ho,Wo,F", [(1, 78, 78, 51), (2, 16, 29, 5)])
+def test_separableconvflow(lib, oracle, B, Ho, Wo, F):
+    import warnings
+    r = U.rng(1600)
+    v = (1.0 / F + 0.1 / F * r.random((B, F, Ho, Wo))).astype(np.float32)
+    hz = (1.0 / F + 0.1 / F * r.random((B, F, Ho, Wo))).astype(np.float32)
+    v[0, :, 0, 0] = 0.0                                                      # sentinel pixel
+    I = U.image(r, B, 3, Ho + F - 1, Wo + F - 1)
+    ti, tv, th = cu(I).requires_grad_(), cu(v).requires_grad_(), cu(hz).requires_grad_()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mod = lib.SeparableConvFlowModule(F)
+    out = mod(ti, tv, th)
+    ref = oracle.sepconvflow_forward(v, hz)
+    assert host(out)[0, 1, 0, 0] == -2000.0
+    U.assert_close(host(out), ref, U.RTOL_FWD, "sepconvflow forward")
+    g = r.standard_normal((B, 2, Ho, Wo)).astype(np.float32)
+    out.backward(cu(g))
+    gi2, gi3 = oracle.sepconvflow_backward(v, hz, g)
+    U.assert_close(host(tv.grad), gi2, U.RTOL_FWD * 3, "gradinput2")
+    U.assert_close(host(th.grad), gi3, U.RTOL_FWD * 3, "gradinput3")
+    assert not ti.grad.any()
+
+
+# ------------------------------------------------------------------------------ Correlation
+@pytest.mark.parametrize("B,C,H,W", [(1, 32, 64, 112), (2, 196, 4, 7), (1, 64, 18, 31), (2, 5, 9, 13), (1, 128, 8, 14)])
+def test_correlation_pwc_configuration(lib, oracle, B, C, H, W):
+    r = U.rng(1700)
+    f1, f2 = U.image(r, B, C, H, W, "normal"), U.image(r, B, C, H, W, "normal")
+    t1, t2 = cu(f1).requires_grad_(), cu(f2).requires_grad_()
+    out = lib.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1)(t1, t2)
+    ref = oracle.correlation_forward(f1, f2, 4, 1, 4, 1, 1)
+    assert tuple(out.shape) == ref.shape
+    U.assert_close(host(out), ref, U.RTOL_FWD, "correlation forward")
+    g = r.standard_normal(ref.shape).astype(np.float32)
+    out.backward(cu(g))
+    gi1, gi2 = oracle.correlation_backward(f1, f2, g, 4, 1, 4, 1, 1)
+    U.assert_close(host(t1.grad), gi1, U.RTOL_FWD, "correlation gradinput1")
+    U.assert_close(host(t2.grad), gi2, U.RTOL_FWD, "correlation gradinput2")
+
+
+@pytest.mark.parametrize("pad,k,md,s1,s2", [(3, 3, 6, 1, 2), (2, 1, 2, 1, 1), (6, 1, 4, 1, 1), (4, 3, 4, 1, 1), (8, 1, 8, 2, 2)])
+def test_correlation_generic_configurations(lib, oracle, pad, k, md, s1, s2):
+    r = U.rng(1701)
+    B, C, H, W = 2, 6, 20, 27
+    f1, f2 = U.image(r, B, C, H, W, "normal"), U.image(r, B, C, H, W, "normal")
+    t1, t2 = cu(f1).requires_grad_(), cu(f2).requires_grad_()
+    out = lib.Correlation(pad, k, md, s1, s2, 1)(t1, t2)
+    ref = oracle.correlation_forward(f1, f2, pad, k, md, s1, s2)
+    assert tuple(out.shape) == ref.shape
+    U.assert_close(host(out), ref, U.RTOL_FWD, "correlation forward")
+    if s1 == 1 and pad >= md:      # in-contract domain of the reference backward
+        g = r.standard_normal(ref.shape).astype(np.float32)
+        out.backward(cu(g))
+        gi1, gi2 = oracle.correlation_backward(f1, f2, g, pad, k, md, s1, s2)
+        U.assert_close(host(t1.grad), gi1, U.RTOL_FWD, "gradinput1")
+        U.assert_close(host(t2.grad), gi2, U.RTOL_FWD, "gradinput2")
+
+
+def test_correlation_of_ones_on_gpu(lib):
+    f = torch.ones(1, 8, 10, 12, device="cuda")
+    out = lib.Correlation(4, 1, 4, 1, 1, 1)(f, f)
+    assert (out[0, 40] == 1).all()                                          # KAT 7
+    assert out[0, 0, 0, 0] == 0 and out[0, 0, 4, 4] == 1
+
+
+# ------------------------------------------------------------------------------ full-size properties
+def test_full_size_1080p_properties(lib, oracle):
+    """BASELINE config 4 shape (1080p padded to 1152x1984, B=8): size-independent properties, plus the
+    oracle on a crop-free sub-batch it can finish in seconds."""
+    r = U.rng(1800)
+    B, C, H, W = 8, 3, 1152, 1984
+    I = torch.rand(B, C, H, W, device="cuda")
+    fl = (torch.randn(B, 2, H, W, device="cuda") * 4).clamp_(-20, 20)
+    ft = torch.softmax(torch.randn(B, 16, H, W, device="cuda"), dim=1)
+    out = lib.FilterInterpolationModule()(I, fl, ft)
+    # (1) linearity in the image: FI(a*I + J) = a*FI(I) + FI(J) for in-range and copied pixels alike
+    J = torch.rand_like(I)
+    lhs = lib.FilterInterpolationModule()(2.5 * I + J, fl, ft)
+    rhs = 2.5 * out + lib.FilterInterpolationModule()(J, fl, ft)
+    assert (lhs - rhs).abs().max().item() < 2e-5
+    # (2) a convex filter (softmax) and convex bilinear blend keep the output inside the input range
+    assert out.min().item() >= -1e-6 and out.max().item() <= 1 + 1e-6
+    # (3) identity: zero flow + one-hot centre tap
+    onehot = torch.zeros_like(ft)
+    onehot[:, 5] = 1
+    assert torch.equal(lib.FilterInterpolationModule()(I, torch.zeros_like(fl), onehot), I)
+    # (4) oracle on the first batch item
+    ref = oracle.fi_forward("ori", host(I[:1]), host(fl[:1]), host(ft[:1]))
+    U.assert_close(host(out[:1]), ref, U.RTOL_FWD, "1080p forward, item 0")
+    # (5) projection: zero flow -> zero output, count 4 in the interior; mass conservation of the splat
+    z = torch.zeros(B, 2, H, W, device="cuda")
+    assert not lib.FlowProjectionModule(False)(z).any()
+    d = torch.rand(B, 1, H, W, device="cuda") * 0.9 + 0.1
+    po = lib.DepthFlowProjectionModule(True)(fl, d)
+    assert torch.isfinite(po).all()
+    ref, _ = oracle.flowprojection_forward(host(fl[:1]), host(d[:1]), 0)
+    U.assert_close(host(po[:1]), ref, U.RTOL_ATOMIC, "1080p depth projection, item 0")

@@ -1,0 +1,20 @@
+"""vfidkr_b200 -- B200-native (sm_100a) per-pixel sampling / warping operators of VFIDKR.
+
+The directory name carries the full reference name; import it as `vfidkr_b200` (a shim package at the
+repository root maps that name onto this directory).  Everything here is a thin Python front-end over the
+C ABI of libvfidkr_b200.so (include/vfidkr_b200.h); there is no CPU or framework fallback.
+"""
+from . import _lib
+from ._lib import VfidkrError, abi_version, launch_count
+from .correlation import Correlation, CorrelationFunction, correlation_output_shape
+from .filter_interpolation import (FilterInterpolationLayer, FilterInterpolationLayerDeforConv,
+                                   FilterInterpolationLayerDKR, FilterInterpolationLayerNoFilterWithDeforConv,
+                                   FilterInterpolationModule)
+from .flow_projection import (DepthFlowProjectionLayer, DepthFlowProjectionModule, FlowProjectionLayer,
+                              FlowProjectionModule)
+from .interpolation import InterpolationChLayer, InterpolationChModule, InterpolationLayer, InterpolationModule
+from .separable_conv import (SeparableConvFlowLayer, SeparableConvFlowModule, SeparableConvLayer,
+                             SeparableConvModule)
+from .compat import install_reference_aliases
+
+__version__ = "0.1.0"

@@ -1,0 +1,34 @@
+// common.cuh -- shared helpers for the sm_100a kernels of libvfidkr_b200.so
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "vfidkr_b200.h"
+
+#define VFIDKR_API extern "C" __attribute__((visibility("default")))
+
+namespace vfidkr {
+
+// ---- host side -----------------------------------------------------------------------
+void note_launch(int n = 1);              // relaxed launch counter (capi.cu)
+int  check_launch(const char *what);      // cudaGetLastError -> VFIDKR_OK / VFIDKR_ERR_CUDA
+int  set_error(cudaError_t e, const char *what);
+int  sm_count();                          // cached multiprocessor count of the current device
+
+static inline unsigned ceil_div(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---- device side ---------------------------------------------------------------------
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
+
+// streaming (read-once) loads / stores: keep them out of L1 so the gather working set stays resident
+__device__ __forceinline__ float ld_stream(const float *p) { return __ldcs(p); }
+__device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
+
+// fire-and-forget float add (RED.E.ADD.F32)
+__device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
+
+}  // namespace vfidkr

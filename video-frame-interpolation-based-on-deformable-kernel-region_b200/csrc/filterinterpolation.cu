@@ -1,0 +1,453 @@
+// filterinterpolation.cu -- adaptive warping with per-pixel F x F filters and its three
+// deformable-kernel-region (DKR) variants, forward and backward, for sm_100a.
+//
+// Behavioural contract (what is computed) follows the reference kernels
+//   my_package/FilterInterpolation/filterinterpolation_cuda_kernel.cu
+//     :2692-3125 "_ori"   :29-1215 4-input DKR   :1353-1935 "_deforconv"   :2070-2567 "_nofilterwithdeforconv"
+// The implementation is new:
+//   * one thread per output pixel keeps the F*F filter taps (and 2*F*F offsets) in registers
+//     and loops channels inside, instead of re-reading them from HBM for every channel;
+//   * the backward fuses the reference's 3 (ori) / 5 (DKR) passes over the taps into one and
+//     accumulates the thread-private gradients (flow, filter, offsets) in registers with plain
+//     stores -- only the image gradient, which really scatters, uses RED atomics;
+//   * out-of-range pixels write their zeros/copies themselves, so no buffer but gradinput1
+//     needs clearing;
+//   * 64-bit plane offsets (B*C*H*W exceeds 2^31 for the 196-channel context tensors at 1080p).
+#include "common.cuh"
+
+namespace vfidkr {
+namespace {
+
+enum { V_ORI = 0, V_DKR = 1, V_DEFOR = 2, V_NOFILT = 3 };
+
+constexpr int BX = 32, BY = 8;  // thread block = 32 x 8 output pixels
+
+struct FiPix {
+    bool in_range;
+    int ix, iy, L, T;
+    float x2, y2, alpha, beta;
+};
+
+// range test + window origin, float32 exactly as the reference writes it (:2731-2743)
+__device__ __forceinline__ FiPix fi_pixel(int w_i, int h_i, float fx, float fy, int W, int H, int F)
+{
+    FiPix p;
+    p.x2 = __fadd_rn((float)w_i, fx);
+    p.y2 = __fadd_rn((float)h_i, fy);
+    p.in_range = p.x2 >= 0.0f && p.y2 >= 0.0f && p.x2 <= (float)(W - 1) && p.y2 <= (float)(H - 1) &&
+                 fabsf(fx) < (float)W / 2.0f && fabsf(fy) < (float)H / 2.0f;
+    p.ix = (int)p.x2;
+    p.iy = (int)p.y2;
+    p.L = p.ix + 1 - F / 2;
+    p.T = p.iy + 1 - F / 2;
+    p.alpha = __fsub_rn(p.x2, (float)p.ix);
+    p.beta = __fsub_rn(p.y2, (float)p.iy);
+    return p;
+}
+
+// one deformed tap: the four read offsets inside a channel plane and the bilinear fractions
+struct Deform {
+    int aTL, aTR, aBL, aBR;
+    float phiX, phiY;
+    bool top, left;  // data-dependent quadrant (fracY <= y2, fracX <= x2)
+};
+
+__device__ __forceinline__ Deform fi_deform(int cy, int cx, float offY, float offX, const FiPix &p, int H, int W)
+{
+    Deform d;
+    const float fracY = __fadd_rn((float)cy, offY);  // :98
+    const float fracX = __fadd_rn((float)cx, offX);  // :99
+    const int Top = (int)fracY, Left = (int)fracX;   // :102-103 (cvt.rzi saturates, NaN -> 0)
+    d.phiY = __fsub_rn(fracY, (float)Top);           // :100
+    d.phiX = __fsub_rn(fracX, (float)Left);          // :101
+    // The reference leaves Top/Left/Bottom/Right unclamped (undefined behaviour outside the plane);
+    // reads are clamped to the plane here, weights are untouched ("in-contract domain").
+    const int t = clampi(Top, 0, H - 1), b = clampi(min(Top, H - 1) + 1, 0, H - 1);
+    const int l = clampi(Left, 0, W - 1), r = clampi(min(Left, W - 1) + 1, 0, W - 1);
+    d.aTL = t * W + l; d.aTR = t * W + r; d.aBL = b * W + l; d.aBR = b * W + r;
+    d.top = fracY <= p.y2;
+    d.left = fracX <= p.x2;
+    return d;
+}
+
+// per-tap blend coefficients selected by the tap's quadrant (0=TL 1=TR 2=BL 3=BR):
+//   q  : weight of the quadrant sum in the output            (:2789-2793)
+//   cx : coefficient of the tap in d(out)/d(flow_x)  = gamma*(TR-TL) + (1-gamma)*(BR-BL), gamma = 1-beta   (:2965-3013)
+//   cy : coefficient of the tap in d(out)/d(flow_y)  = gamma'*(BL-TL) + (1-gamma')*(BR-TR), gamma' = 1-alpha (:3036-3084)
+struct QuadCoef { float q, cx, cy; };
+__device__ __forceinline__ QuadCoef quad_coef(bool top, bool left, float alpha, float beta)
+{
+    QuadCoef r;
+    const float ax = left ? 1.0f - alpha : alpha;   // x-factor of q
+    const float by = top ? 1.0f - beta : beta;      // y-factor of q
+    r.q = top ? (left ? (1 - alpha) * (1 - beta) : alpha * (1 - beta)) : (left ? (1 - alpha) * beta : alpha * beta);
+    const float gam = 1.0f - beta, gam2 = 1.0f - alpha;
+    r.cx = (left ? -1.0f : 1.0f) * (top ? gam : 1.0f - gam);
+    r.cy = (top ? -1.0f : 1.0f) * (left ? gam2 : 1.0f - gam2);
+    (void)ax; (void)by;
+    return r;
+}
+
+// resident blocks per SM the register allocator must leave room for
+constexpr int MINB_FWD_ORI = 4, MINB_FWD_DKR = 3;
+__host__ __device__ constexpr int minb_bwd(int V) { return V == V_ORI ? 3 : 2; }
+
+// ------------------------------------------------------------------------------------------
+// "_ori" forward.  FT > 0: compile-time filter size, the F*F taps live in registers and the
+// channel loop is outermost (the reference re-reads the taps for every channel, :2755).
+// FT == 0: run-time filter size, taps re-read through L1.
+// ------------------------------------------------------------------------------------------
+template <int FT>
+__global__ void __launch_bounds__(BX *BY, MINB_FWD_ORI)
+fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ in2, const float *__restrict__ in3,
+                      float *__restrict__ out, int C, int H, int W, int Frt)
+{
+    const int F = FT > 0 ? FT : Frt;
+    const int w_i = blockIdx.x * BX + threadIdx.x;
+    const int h_i = blockIdx.y * BY + threadIdx.y;
+    if (w_i >= W || h_i >= H) return;
+    const int b = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)h_i * W + w_i;
+
+    const float fx = ld_stream(in2 + ((size_t)b * 2 + 0) * HW + pix);
+    const float fy = ld_stream(in2 + ((size_t)b * 2 + 1) * HW + pix);
+    const FiPix p = fi_pixel(w_i, h_i, fx, fy, W, H, F);
+
+    const float *img = in1 + (size_t)b * C * HW;
+    float *o = out + (size_t)b * C * HW + pix;
+    if (!p.in_range) {  // :2814-2819 copies input1
+        for (int c = 0; c < C; ++c) st_stream(o + (size_t)c * HW, __ldg(img + (size_t)c * HW + pix));
+        return;
+    }
+    const float *wp = in3 + (size_t)b * F * F * HW + pix;
+    const float qTL = (1 - p.alpha) * (1 - p.beta), qTR = p.alpha * (1 - p.beta);
+    const float qBL = (1 - p.alpha) * p.beta, qBR = p.alpha * p.beta;
+
+    if (FT > 0) {
+        constexpr int FN = FT > 0 ? FT : 1;
+        float w[FN * FN];
+#pragma unroll
+        for (int k = 0; k < FT * FT; ++k) w[k] = ld_stream(wp + (size_t)k * HW);
+        int ro[FN], co[FN];
+#pragma unroll
+        for (int j = 0; j < FT; ++j) {
+            ro[j] = clampi(p.T + j, 0, H - 1) * W;   // :2751
+            co[j] = clampi(p.L + j, 0, W - 1);       // :2753
+        }
+        for (int c = 0; c < C; ++c) {
+            const float *pl = img + (size_t)c * HW;
+            float Q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < FT; ++j)
+#pragma unroll
+                for (int i = 0; i < FT; ++i)
+                    Q[(j < FT / 2 ? 0 : 2) + (i < FT / 2 ? 0 : 1)] += __ldg(pl + ro[j] + co[i]) * w[j * FT + i];
+            st_stream(o + (size_t)c * HW, qTL * Q[0] + qTR * Q[1] + qBL * Q[2] + qBR * Q[3]);
+        }
+    } else {
+        for (int c = 0; c < C; ++c) {
+            const float *pl = img + (size_t)c * HW;
+            float TL = 0.f, TR = 0.f, BL = 0.f, BR = 0.f;
+            for (int j = 0; j < F; ++j) {
+                const int r = clampi(p.T + j, 0, H - 1) * W;
+                for (int i = 0; i < F; ++i) {
+                    const float t = __ldg(pl + r + clampi(p.L + i, 0, W - 1)) * __ldg(wp + (size_t)(j * F + i) * HW);
+                    const bool top = j < F / 2, left = i < F / 2;
+                    if (top) { if (left) TL += t; else TR += t; } else { if (left) BL += t; else BR += t; }
+                }
+            }
+            st_stream(o + (size_t)c * HW, qTL * TL + qTR * TR + qBL * BL + qBR * BR);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// DKR forward (4-input, "_deforconv", "_nofilterwithdeforconv").  Taps outermost: the deformed
+// sampling geometry of a tap is computed once and applied to CCH channels.  out = sum over taps of
+// q(quadrant) * S * w, which is the reference's q_TL*TL + ... regrouped per tap.
+// ------------------------------------------------------------------------------------------
+template <int V, int FT, int CCH>
+__global__ void __launch_bounds__(BX *BY, MINB_FWD_DKR)
+fi_forward_dkr_kernel(const float *__restrict__ in1, const float *__restrict__ in2, const float *__restrict__ in3,
+                      const float *__restrict__ in4, float *__restrict__ out, int C, int H, int W, int Frt)
+{
+    const int F = FT > 0 ? FT : Frt;
+    const int T2 = F * F;
+    const int w_i = blockIdx.x * BX + threadIdx.x;
+    const int h_i = blockIdx.y * BY + threadIdx.y;
+    if (w_i >= W || h_i >= H) return;
+    const int b = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)h_i * W + w_i;
+    const float *img = in1 + (size_t)b * C * HW;
+    float *o = out + (size_t)b * C * HW + pix;
+
+    if (V == V_DKR && !(F == 4 || F == 6)) {  // forward gate of the 4-input family (:68): output stays zero
+        for (int c = 0; c < C; ++c) st_stream(o + (size_t)c * HW, 0.0f);
+        return;
+    }
+    const float fx = ld_stream(in2 + ((size_t)b * 2 + 0) * HW + pix);
+    const float fy = ld_stream(in2 + ((size_t)b * 2 + 1) * HW + pix);
+    const FiPix p = fi_pixel(w_i, h_i, fx, fy, W, H, F);
+    if (!p.in_range) {  // :225-230 copies input1
+        for (int c = 0; c < C; ++c) st_stream(o + (size_t)c * HW, __ldg(img + (size_t)c * HW + pix));
+        return;
+    }
+    const float *wp = (V == V_NOFILT) ? nullptr : in3 + (size_t)b * T2 * HW + pix;
+    const float *op = (V == V_NOFILT ? in3 : in4) + (size_t)b * 2 * T2 * HW + pix;
+
+    for (int c0 = 0; c0 < C; c0 += CCH) {
+        float acc[CCH];
+#pragma unroll
+        for (int cc = 0; cc < CCH; ++cc) acc[cc] = 0.0f;
+        const float *pl = img + (size_t)c0 * HW;
+#pragma unroll 1
+        for (int j = 0; j < F; ++j) {
+            const int cy = clampi(p.T + j, 0, H - 1);
+#pragma unroll
+            for (int i = 0; i < (FT > 0 ? FT : F); ++i) {
+                const int cx = clampi(p.L + i, 0, W - 1);
+                const int k = j * F + i;
+                const float wgt = (V == V_NOFILT) ? 1.0f : __ldg(wp + (size_t)k * HW);
+                const float oy = __ldg(op + (size_t)k * HW), ox = __ldg(op + (size_t)(T2 + k) * HW);
+                const Deform d = fi_deform(cy, cx, oy, ox, p, H, W);
+                const bool top = (V == V_DKR) ? (j < F / 2) : d.top;
+                const bool left = (V == V_DKR) ? (i < F / 2) : d.left;
+                const QuadCoef qc = quad_coef(top, left, p.alpha, p.beta);
+                const float PTL = (1 - d.phiX) * (1 - d.phiY), PTR = d.phiX * (1 - d.phiY);
+                const float PBL = (1 - d.phiX) * d.phiY, PBR = d.phiY * d.phiX;
+#pragma unroll
+                for (int cc = 0; cc < CCH; ++cc)
+                    if (c0 + cc < C) {
+                        const float *q = pl + (size_t)cc * HW;
+                        const float S = PTL * __ldg(q + d.aTL) + PTR * __ldg(q + d.aTR) +
+                                        PBL * __ldg(q + d.aBL) + PBR * __ldg(q + d.aBR);   // :110-111
+                        acc[cc] += qc.q * (S * wgt);
+                    }
+            }
+        }
+#pragma unroll
+        for (int cc = 0; cc < CCH; ++cc)
+            if (c0 + cc < C) st_stream(o + (size_t)(c0 + cc) * HW, acc[cc]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, all four families: ONE pass over the taps per chunk of CCH channels (the reference makes
+// three passes for "_ori" and five for the DKR families).
+//   gi1  (image)   : RED scatter to the undeformed clamped tap -- the only real scatter
+//   gi2  (flow)    : register accumulation, one store per component
+//   gi3  (filter)  : thread-private: stored once per tap (first chunk) / own-pixel += (later chunks)
+//   goff (offsets) : likewise; gradinput3 for V_NOFILT, gradinput4 otherwise
+// gi1 must be zero on entry (the launcher clears it on the stream); nothing else needs clearing.
+// ------------------------------------------------------------------------------------------
+template <int V, int FT, int CCH>
+__global__ void __launch_bounds__(BX *BY, minb_bwd(V))
+fi_backward_kernel(const float *__restrict__ in1, const float *__restrict__ in2, const float *__restrict__ in3,
+                   const float *__restrict__ in4, const float *__restrict__ gout, float *__restrict__ gi1,
+                   float *__restrict__ gi2, float *__restrict__ gi3, float *__restrict__ gi4,
+                   int C, int H, int W, int Frt)
+{
+    const int F = FT > 0 ? FT : Frt;
+    const int T2 = F * F;
+    const int w_i = blockIdx.x * BX + threadIdx.x;
+    const int h_i = blockIdx.y * BY + threadIdx.y;
+    if (w_i >= W || h_i >= H) return;
+    const int b = blockIdx.z;
+    const size_t HW = (size_t)H * W;
+    const size_t pix = (size_t)h_i * W + w_i;
+
+    const float fx = ld_stream(in2 + ((size_t)b * 2 + 0) * HW + pix);
+    const float fy = ld_stream(in2 + ((size_t)b * 2 + 1) * HW + pix);
+    const FiPix p = fi_pixel(w_i, h_i, fx, fy, W, H, F);
+
+    float *g2 = gi2 + (size_t)b * 2 * HW + pix;
+    float *g3 = (V == V_NOFILT) ? nullptr : gi3 + (size_t)b * T2 * HW + pix;
+    float *go = (V == V_ORI) ? nullptr : (V == V_NOFILT ? gi3 : gi4) + (size_t)b * 2 * T2 * HW + pix;
+
+    if (!p.in_range) {  // contributes nothing; the reference leaves the caller's zeros (:2863)
+        st_stream(g2, 0.0f);
+        st_stream(g2 + HW, 0.0f);
+        for (int k = 0; k < T2; ++k) {
+            if (V != V_NOFILT) st_stream(g3 + (size_t)k * HW, 0.0f);
+            if (V != V_ORI) { st_stream(go + (size_t)k * HW, 0.0f); st_stream(go + (size_t)(T2 + k) * HW, 0.0f); }
+        }
+        return;
+    }
+
+    const float *img = in1 + (size_t)b * C * HW;
+    float *gimg = gi1 + (size_t)b * C * HW;
+    const float *gop = gout + (size_t)b * C * HW + pix;
+    const float *wp = (V == V_NOFILT) ? nullptr : in3 + (size_t)b * T2 * HW + pix;
+    const float *op = (V == V_ORI) ? nullptr
+                      : (V == V_NOFILT ? in3 : in4) + (size_t)b * 2 * T2 * HW + pix;
+    float gx = 0.0f, gy = 0.0f;
+
+    for (int c0 = 0; c0 < C; c0 += CCH) {
+        float g[CCH];
+#pragma unroll
+        for (int cc = 0; cc < CCH; ++cc) g[cc] = (c0 + cc < C) ? ld_stream(gop + (size_t)(c0 + cc) * HW) : 0.0f;
+        const float *pl = img + (size_t)c0 * HW;
+        float *gpl = gimg + (size_t)c0 * HW;
+        const bool first = (c0 == 0);
+
+#pragma unroll 1
+        for (int j = 0; j < F; ++j) {
+            const int cy = clampi(p.T + j, 0, H - 1);
+#pragma unroll
+            for (int i = 0; i < (FT > 0 ? FT : F); ++i) {
+                const int cx = clampi(p.L + i, 0, W - 1);
+                const int k = j * F + i;
+                const int a = cy * W + cx;
+                const float wgt = (V == V_NOFILT) ? 1.0f : __ldg(wp + (size_t)k * HW);
+                float s3 = 0.0f, soy = 0.0f, sox = 0.0f;
+                if (V == V_ORI) {
+                    const QuadCoef qc = quad_coef(j < F / 2, i < F / 2, p.alpha, p.beta);
+#pragma unroll
+                    for (int cc = 0; cc < CCH; ++cc)
+                        if (c0 + cc < C) {
+                            const float gq = g[cc] * qc.q;                       // TL_grad (:2885)
+                            const float v = __ldg(pl + (size_t)cc * HW + a);
+                            red_add(gpl + (size_t)cc * HW + a, gq * wgt);       // :2890-2892
+                            s3 += gq * v;                                       // :2893-2895
+                            const float t = g[cc] * (v * wgt);
+                            gx += qc.cx * t;
+                            gy += qc.cy * t;
+                        }
+                } else {
+                    const float oy = __ldg(op + (size_t)k * HW), ox = __ldg(op + (size_t)(T2 + k) * HW);
+                    const Deform d = fi_deform(cy, cx, oy, ox, p, H, W);
+                    const bool top = (V == V_DKR) ? (j < F / 2) : d.top;
+                    const bool left = (V == V_DKR) ? (i < F / 2) : d.left;
+                    const QuadCoef qc = quad_coef(top, left, p.alpha, p.beta);
+                    const float PTL = (1 - d.phiX) * (1 - d.phiY), PTR = d.phiX * (1 - d.phiY);
+                    const float PBL = (1 - d.phiX) * d.phiY, PBR = d.phiY * d.phiX;
+#pragma unroll
+                    for (int cc = 0; cc < CCH; ++cc)
+                        if (c0 + cc < C) {
+                            const float *qp = pl + (size_t)cc * HW;
+                            const float vTL = __ldg(qp + d.aTL), vTR = __ldg(qp + d.aTR);
+                            const float vBL = __ldg(qp + d.aBL), vBR = __ldg(qp + d.aBR);
+                            const float S = PTL * vTL + PTR * vTR + PBL * vBL + PBR * vBR;
+                            const float dSy = -(1 - d.phiX) * vTL + (1 - d.phiX) * vBL - d.phiX * vTR + d.phiX * vBR;  // :986-989
+                            const float dSx = -(1 - d.phiY) * vTL + (1 - d.phiY) * vTR - d.phiY * vBL + d.phiY * vBR;  // :1104-1107
+                            const float gq = g[cc] * qc.q;
+                            red_add(gpl + (size_t)cc * HW + a, gq * wgt);   // undeformed tap (:497-499, :2258)
+                            s3 += gq * S;                                   // :520-522
+                            soy += gq * dSy * wgt;                          // :990-993
+                            sox += gq * dSx * wgt;                          // :1108-1111
+                            const float t = g[cc] * (S * wgt);
+                            gx += qc.cx * t;
+                            gy += qc.cy * t;
+                        }
+                }
+                // thread-private gradients: plain stores, accumulate across channel chunks in place
+                if (V != V_NOFILT) {
+                    float *q3 = g3 + (size_t)k * HW;
+                    *q3 = first ? s3 : *q3 + s3;
+                }
+                if (V != V_ORI) {
+                    float *qy = go + (size_t)k * HW, *qx = go + (size_t)(T2 + k) * HW;
+                    *qy = first ? soy : *qy + soy;
+                    *qx = first ? sox : *qx + sox;
+                }
+            }
+        }
+    }
+    st_stream(g2, gx);
+    st_stream(g2 + HW, gy);
+}
+
+// ---- launchers -----------------------------------------------------------------------------
+template <int V>
+int launch_forward(const float *in1, const float *in2, const float *in3, const float *in4, float *out,
+                   int B, int C, int H, int W, int F, cudaStream_t s)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || F <= 0 || B > 65535) return VFIDKR_ERR_ARG;
+    if (!in1 || !in2 || !in3 || !out || ((V == V_DKR || V == V_DEFOR) && !in4)) return VFIDKR_ERR_ARG;
+    if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
+    dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
+    if constexpr (V == V_ORI) {
+        if (F == 4) fi_forward_ori_kernel<4><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
+        else        fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
+    } else if (F == 4) {
+        if (C == 3) fi_forward_dkr_kernel<V, 4, 3><<<grid, block, 0, s>>>(in1, in2, in3, in4, out, C, H, W, F);
+        else        fi_forward_dkr_kernel<V, 4, 4><<<grid, block, 0, s>>>(in1, in2, in3, in4, out, C, H, W, F);
+    } else {
+        fi_forward_dkr_kernel<V, 0, 4><<<grid, block, 0, s>>>(in1, in2, in3, in4, out, C, H, W, F);
+    }
+    note_launch();
+    return check_launch("filterinterpolation forward");
+}
+
+template <int V>
+int launch_backward(const float *in1, const float *in2, const float *in3, const float *in4, const float *gout,
+                    float *gi1, float *gi2, float *gi3, float *gi4,
+                    int B, int C, int H, int W, int F, cudaStream_t s)
+{
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || F <= 0 || B > 65535) return VFIDKR_ERR_ARG;
+    if (!in1 || !in2 || !in3 || !gout || !gi1 || !gi2 || !gi3) return VFIDKR_ERR_ARG;
+    if ((V == V_DKR || V == V_DEFOR) && (!in4 || !gi4)) return VFIDKR_ERR_ARG;
+    if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
+    int e = set_error(cudaMemsetAsync(gi1, 0, sizeof(float) * (size_t)B * C * H * W, s), "clear gradinput1");
+    if (e) return e;
+    dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
+    if (F == 4) {
+        if (C == 3) fi_backward_kernel<V, 4, 3><<<grid, block, 0, s>>>(in1, in2, in3, in4, gout, gi1, gi2, gi3, gi4, C, H, W, F);
+        else        fi_backward_kernel<V, 4, 4><<<grid, block, 0, s>>>(in1, in2, in3, in4, gout, gi1, gi2, gi3, gi4, C, H, W, F);
+    } else {
+        fi_backward_kernel<V, 0, 4><<<grid, block, 0, s>>>(in1, in2, in3, in4, gout, gi1, gi2, gi3, gi4, C, H, W, F);
+    }
+    note_launch();
+    return check_launch("filterinterpolation backward");
+}
+
+}  // namespace
+}  // namespace vfidkr
+
+using namespace vfidkr;
+
+VFIDKR_API int vfidkr_filterinterpolation_forward_ori(const float *i1, const float *i2, const float *i3, float *out,
+                                                      int B, int C, int H, int W, int F, vfidkr_stream_t s)
+{ return launch_forward<V_ORI>(i1, i2, i3, nullptr, out, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_backward_ori(const float *i1, const float *i2, const float *i3,
+                                                       const float *g, float *gi1, float *gi2, float *gi3,
+                                                       int B, int C, int H, int W, int F, vfidkr_stream_t s)
+{ return launch_backward<V_ORI>(i1, i2, i3, nullptr, g, gi1, gi2, gi3, nullptr, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_forward_dkr(const float *i1, const float *i2, const float *i3,
+                                                      const float *i4, float *out,
+                                                      int B, int C, int H, int W, int F, vfidkr_stream_t s)
+{ return launch_forward<V_DKR>(i1, i2, i3, i4, out, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_backward_dkr(const float *i1, const float *i2, const float *i3,
+                                                       const float *i4, const float *g, float *gi1, float *gi2,
+                                                       float *gi3, float *gi4,
+                                                       int B, int C, int H, int W, int F, vfidkr_stream_t s)
+{ return launch_backward<V_DKR>(i1, i2, i3, i4, g, gi1, gi2, gi3, gi4, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_forward_deforconv(const float *i1, const float *i2, const float *i3,
+                                                            const float *i4, float *out,
+                                                            int B, int C, int H, int W, int F, vfidkr_stream_t s)
+{ return launch_forward<V_DEFOR>(i1, i2, i3, i4, out, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_backward_deforconv(const float *i1, const float *i2, const float *i3,
+                                                             const float *i4, const float *g, float *gi1,
+                                                             float *gi2, float *gi3, float *gi4,
+                                                             int B, int C, int H, int W, int F, vfidkr_stream_t s)
+{ return launch_backward<V_DEFOR>(i1, i2, i3, i4, g, gi1, gi2, gi3, gi4, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_forward_nofilterwithdeforconv(const float *i1, const float *i2,
+                                                                        const float *i3, float *out,
+                                                                        int B, int C, int H, int W, int F,
+                                                                        vfidkr_stream_t s)
+{ return launch_forward<V_NOFILT>(i1, i2, i3, nullptr, out, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_backward_nofilterwithdeforconv(const float *i1, const float *i2,
+                                                                         const float *i3, const float *g,
+                                                                         float *gi1, float *gi2, float *gi3,
+                                                                         int B, int C, int H, int W, int F,
+                                                                         vfidkr_stream_t s)
+{ return launch_backward<V_NOFILT>(i1, i2, i3, nullptr, g, gi1, gi2, gi3, nullptr, B, C, H, W, F, (cudaStream_t)s); }

@@ -1,0 +1,98 @@
+"""FlowProjection / DepthFlowProjection -- forward-splatted flow projection.
+
+Reference surface (relative to /root/reference/):
+  my_package/FlowProjection/FlowProjectionLayer.py:10-87, FlowProjectionModule.py:5-17
+      FlowProjectionModule(requires_grad=True)(input1) -> FlowProjectionLayer.apply(input1, requires_grad)
+  my_package/DepthFlowProjection/DepthFlowProjectionLayer.py:7-98, DepthFlowProjectionModule.py:7-16
+      DepthFlowProjectionModule(requires_grad=True)(input1, input2)
+Hole filling runs only when requires_grad is False, i.e. at inference (FlowProjectionLayer.py:23).
+"""
+from __future__ import annotations
+
+import torch
+from torch.autograd import Function
+from torch.nn import Module
+
+from . import _lib
+from ._common import check_input, ptr, stream_ptr
+
+__all__ = ["FlowProjectionLayer", "FlowProjectionModule", "DepthFlowProjectionLayer", "DepthFlowProjectionModule"]
+
+
+class FlowProjectionLayer(Function):
+    @staticmethod
+    def forward(ctx, input1, requires_grad):
+        check_input(input1, "input1")
+        B, ch, H, W = input1.shape
+        if ch != 2:   # flowprojection_cuda.cc:20
+            raise _lib.VfidkrError("input1 must be a [B,2,H,W] flow")
+        fillhole = 1 if requires_grad == False else 0   # noqa: E712  (FlowProjectionLayer.py:23)
+        count = torch.empty((B, 1, H, W), dtype=input1.dtype, device=input1.device)
+        output = torch.empty_like(input1)
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_flowprojection_forward", ptr(input1), ptr(count), ptr(output), B, H, W, fillhole,
+                      stream_ptr(input1.device))
+        ctx.save_for_backward(input1, count)
+        ctx.fillhole = fillhole
+        return output
+
+    @staticmethod
+    def backward(ctx, gradoutput):
+        input1, count = ctx.saved_tensors
+        gradoutput = gradoutput.contiguous()
+        B, _, H, W = input1.shape
+        gradinput1 = torch.empty_like(input1)
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_flowprojection_backward", ptr(input1), ptr(count), ptr(gradoutput), ptr(gradinput1),
+                      B, H, W, stream_ptr(input1.device))
+        return gradinput1, None   # FlowProjectionLayer.py:87
+
+
+class FlowProjectionModule(Module):
+    def __init__(self, requires_grad=True):
+        super().__init__()
+        self.requires_grad = requires_grad
+
+    def forward(self, input1):
+        return FlowProjectionLayer.apply(input1, self.requires_grad)
+
+
+class DepthFlowProjectionLayer(Function):
+    @staticmethod
+    def forward(ctx, input1, input2, requires_grad):
+        check_input(input1, "input1")
+        check_input(input2, "input2")
+        B, ch, H, W = input1.shape
+        if ch != 2:   # depthflowprojection_cuda.cc:21
+            raise _lib.VfidkrError("input1 must be a [B,2,H,W] flow")
+        if input2.shape != (B, 1, H, W):   # :28
+            raise _lib.VfidkrError(f"input2 must be [B,1,H,W] = {(B, 1, H, W)}, got {tuple(input2.shape)}")
+        fillhole = 1 if requires_grad == False else 0   # noqa: E712  (DepthFlowProjectionLayer.py:27)
+        count = torch.empty((B, 1, H, W), dtype=input1.dtype, device=input1.device)
+        output = torch.empty_like(input1)
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_depthflowprojection_forward", ptr(input1), ptr(input2), ptr(count), ptr(output),
+                      B, H, W, fillhole, stream_ptr(input1.device))
+        ctx.save_for_backward(input1, input2, count, output)
+        ctx.fillhole = fillhole
+        return output
+
+    @staticmethod
+    def backward(ctx, gradoutput):
+        input1, input2, count, output = ctx.saved_tensors
+        gradoutput = gradoutput.contiguous()
+        B, _, H, W = input1.shape
+        gradinput1, gradinput2 = torch.empty_like(input1), torch.empty_like(input2)
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_depthflowprojection_backward", ptr(input1), ptr(input2), ptr(count), ptr(output),
+                      ptr(gradoutput), ptr(gradinput1), ptr(gradinput2), B, H, W, stream_ptr(input1.device))
+        return gradinput1, gradinput2, None   # DepthFlowProjectionLayer.py:98
+
+
+class DepthFlowProjectionModule(Module):
+    def __init__(self, requires_grad=True):
+        super().__init__()
+        self.requires_grad = requires_grad
+
+    def forward(self, input1, input2):
+        return DepthFlowProjectionLayer.apply(input1, input2, self.requires_grad)
