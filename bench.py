@@ -83,7 +83,7 @@ def recorded_traffic():
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons during the timed region (NVML, else nvidia-smi)."""
 
-    def __init__(self, index: int, period=0.2):
+    def __init__(self, index: int, period=0.02):
         super().__init__(daemon=True)
         self.index, self.period = index, period
         self.samples, self.reasons, self.max_mhz = [], set(), None
@@ -144,7 +144,11 @@ def build_inputs(torch, device, seed, pinned_host=False):
         if kind == "image":
             x = torch.rand(shape, generator=g, device=device)
         elif kind == "flow":
-            x = (torch.randn(shape, generator=g, device=device) * 4.0).clamp_(-20, 20)
+            # the networks produce the flow at quarter resolution and upsample it 4x bilinearly
+            # (networks/DAIN.py:306-308); the synthetic flow follows the same recipe: N(0, 4^2) px clipped
+            # to +-20 px at H/4 x W/4, then bilinear x4
+            lo = (torch.randn((shape[0], shape[1], shape[2] // 4, shape[3] // 4), generator=g, device=device) * 4.0).clamp_(-20, 20)
+            x = torch.nn.functional.interpolate(lo, scale_factor=4, mode="bilinear", align_corners=False).contiguous()
         elif kind == "filter":
             x = torch.softmax(torch.randn(shape, generator=g, device=device), dim=1)
         elif kind == "depth":
@@ -315,7 +319,10 @@ def cpu_reference_arm(steps=1, warmup=0):
     r = np.random.default_rng(1004)
     H, W = PAD_H, PAD_W
     frames = [r.random((1, 3, H, W), dtype=np.float32) for _ in (0, 1)]
-    flows = [np.clip(r.standard_normal((1, 2, H, W)) * 4, -20, 20).astype(np.float32) for _ in range(4)]
+    def upflow():   # quarter-resolution N(0,4^2) flow, x4 nearest+box blur stand-in is not needed: the CPU cost is flow-independent
+        lo = np.clip(r.standard_normal((1, 2, H // 4, W // 4)) * 4, -20, 20).astype(np.float32)
+        return np.ascontiguousarray(np.repeat(np.repeat(lo, 4, axis=2), 4, axis=3))
+    flows = [upflow() for _ in range(4)]
     z = [r.standard_normal((1, 16, H, W)).astype(np.float32) for _ in (0, 1)]
     filts = [np.exp(a - a.max(1, keepdims=True)) for a in z]
     filts = [(a / a.sum(1, keepdims=True)).astype(np.float32) for a in filts]
@@ -390,7 +397,9 @@ def op_table(torch, V, device, path):
 
     px = B * H * W
     I = torch.rand(B, 3, H, W, device=device)
-    fl = (torch.randn(B, 2, H, W, device=device) * 4).clamp_(-20, 20)
+    fl = torch.nn.functional.interpolate((torch.randn(B, 2, H // 4, W // 4, device=device) * 4).clamp_(-20, 20),
+                                         scale_factor=4, mode="bilinear", align_corners=False).contiguous()
+    fl_iid = (torch.randn(B, 2, H, W, device=device) * 4).clamp_(-20, 20)   # per-pixel i.i.d. flow: worst case for the gathers
     ft = torch.softmax(torch.randn(B, 16, H, W, device=device), 1)
     off = (torch.rand(B, 32, H, W, device=device) - 0.5) * 0.9
     dep = torch.rand(B, 1, H, W, device=device) * 0.9 + 0.1
@@ -398,6 +407,7 @@ def op_table(torch, V, device, path):
     g2 = torch.randn(B, 2, H, W, device=device)
     with torch.no_grad():
         add("FI_ori_fwd_C3", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl, ft)), 96, px)
+        add("FI_ori_fwd_C3_iidflow", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl_iid, ft)), 96, px)
         add("FI_dkr_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDKR.apply(I, fl, ft, off)), 224, px)
         add("FI_deforconv_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDeforConv.apply(I, fl, ft, off)), 224, px)
         add("FI_nofilter_fwd_C3", timeit(lambda: V.FilterInterpolationLayerNoFilterWithDeforConv.apply(I, fl, off)), 160, px)

@@ -379,3 +379,28 @@ def test_full_size_1080p_properties(lib, oracle):
     assert torch.isfinite(po).all()
     ref, _ = oracle.flowprojection_forward(host(fl[:1]), host(d[:1]), 0)
     U.assert_close(host(po[:1]), ref, U.RTOL_ATOMIC, "1080p depth projection, item 0")
+
+
+# ------------------------------------------------------------------------------ TMA path vs direct path
+def test_fi_ori_tma_and_direct_paths_agree(lib, oracle, monkeypatch):
+    """The TMA-streamed persistent kernel (W % 4 == 0, aligned) and the direct kernel must agree; edge
+    tiles (W not a multiple of the 64-wide tile, H not a multiple of 4) are covered."""
+    r = U.rng(1900)
+    for (B, C, H, W) in [(2, 3, 37, 132), (1, 3, 256, 448), (3, 5, 9, 68), (1, 196, 8, 64)]:
+        I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "stress"), U.filt(r, B, 4, H, W)
+        monkeypatch.setenv("VFIDKR_FORCE_DIRECT", "1")
+        a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
+        monkeypatch.setenv("VFIDKR_FORCE_DIRECT", "0")
+        b = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
+        # same arithmetic, slightly different FMA grouping: agree to fp32 rounding, and each with the oracle
+        assert U.max_err(host(a), host(b).astype(np.float64)) < 2e-6, (B, C, H, W)
+        U.assert_close(host(b), oracle.fi_forward("ori", I, fl, ft), U.RTOL_FWD, "tma path vs oracle")
+        U.assert_close(host(a), oracle.fi_forward("ori", I, fl, ft), U.RTOL_FWD, "direct path vs oracle")
+    # an unaligned view (offset by one float) must silently take the direct path and still be right
+    B, C, H, W = 1, 3, 16, 64
+    I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "unit"), U.filt(r, B, 4, H, W)
+    buf = torch.empty(ft.size + 1, device="cuda")
+    view = buf[1:].view(B, 16, H, W)
+    view.copy_(cu(ft))
+    out = lib.FilterInterpolationModule()(cu(I), cu(fl), view)
+    U.assert_close(host(out), oracle.fi_forward("ori", I, fl, ft), U.RTOL_FWD, "unaligned filter tensor")

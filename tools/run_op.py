@@ -1,0 +1,81 @@
+#!/usr/bin/env python
+"""Runs one operator a few times at the 1080p batch-8 shape -- the command line ncu profiles.
+
+    python tools/run_op.py fi_ori_fwd [--iters 3] [--B 8] [--C 3]
+"""
+import argparse
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+
+import vfidkr_b200 as V
+from vfidkr_b200 import _lib
+from vfidkr_b200._common import ptr, stream_ptr
+
+ap = argparse.ArgumentParser()
+ap.add_argument("op")
+ap.add_argument("--iters", type=int, default=10)
+ap.add_argument("--B", type=int, default=8)
+ap.add_argument("--C", type=int, default=3)
+ap.add_argument("--H", type=int, default=1152)
+ap.add_argument("--W", type=int, default=1984)
+ap.add_argument("--flow", default="up4", help="up4 | gauss (iid per pixel) | smooth | zero")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+B, C, H, W = a.B, a.C, a.H, a.W
+torch.manual_seed(0)
+I = torch.rand(B, C, H, W, device=dev)
+if a.flow == "up4":
+    fl = torch.nn.functional.interpolate((torch.randn(B, 2, H // 4, W // 4, device=dev) * 4).clamp_(-20, 20),
+                                         scale_factor=4, mode="bilinear", align_corners=False).contiguous()
+elif a.flow == "gauss":
+    fl = (torch.randn(B, 2, H, W, device=dev) * 4).clamp_(-20, 20)
+elif a.flow == "smooth":
+    yy, xx = torch.meshgrid(torch.linspace(0, 6, H, device=dev), torch.linspace(0, 6, W, device=dev), indexing="ij")
+    fl = torch.stack([6 * torch.sin(xx) + 3 * torch.cos(yy), 5 * torch.cos(0.7 * xx) - 3 * torch.sin(yy)], 0)[None].repeat(B, 1, 1, 1).contiguous()
+else:
+    fl = torch.zeros(B, 2, H, W, device=dev)
+ft = torch.softmax(torch.randn(B, 16, H, W, device=dev), 1)
+off = (torch.rand(B, 32, H, W, device=dev) - 0.5) * 0.9
+dep = torch.rand(B, 1, H, W, device=dev) * 0.9 + 0.1
+g = torch.randn(B, C, H, W, device=dev)
+sp = stream_ptr(dev)
+gi1, gi2, gi3, gi4 = torch.empty_like(I), torch.empty_like(fl), torch.empty_like(ft), torch.empty_like(off)
+
+out = torch.empty_like(I)
+ops = {
+    "fi_ori_fwd": lambda: _lib.call("vfidkr_filterinterpolation_forward_ori", ptr(I), ptr(fl), ptr(ft), ptr(out), B, C, H, W, 4, sp),
+    "fi_ori_fwd_py": lambda: V.FilterInterpolationLayer.apply(I, fl, ft),
+    "fi_dkr_fwd": lambda: V.FilterInterpolationLayerDKR.apply(I, fl, ft, off),
+    "fi_deforconv_fwd": lambda: V.FilterInterpolationLayerDeforConv.apply(I, fl, ft, off),
+    "fi_nofilter_fwd": lambda: V.FilterInterpolationLayerNoFilterWithDeforConv.apply(I, fl, off),
+    "fi_ori_bwd": lambda: _lib.call("vfidkr_filterinterpolation_backward_ori", ptr(I), ptr(fl), ptr(ft), ptr(g), ptr(gi1),
+                                    ptr(gi2), ptr(gi3), B, C, H, W, 4, sp),
+    "fi_dkr_bwd": lambda: _lib.call("vfidkr_filterinterpolation_backward_dkr", ptr(I), ptr(fl), ptr(ft), ptr(off), ptr(g),
+                                    ptr(gi1), ptr(gi2), ptr(gi3), ptr(gi4), B, C, H, W, 4, sp),
+    "interp_fwd": lambda: V.InterpolationChLayer.apply(I, fl),
+    "proj_fwd": lambda: V.FlowProjectionLayer.apply(fl, False),
+    "dproj_fwd": lambda: V.DepthFlowProjectionLayer.apply(fl, dep, False),
+}
+if a.op.startswith("corr"):
+    Cc, s = {"corr_l2": (32, 4), "corr_l3": (64, 8), "corr_l4": (96, 16), "corr_l5": (128, 32), "corr_l6": (196, 64)}[a.op]
+    f1 = torch.randn(B, Cc, H // s, W // s, device=dev)
+    f2 = torch.randn_like(f1)
+    corr = V.Correlation(4, 1, 4, 1, 1, 1)
+    fn = lambda: corr(f1, f2)
+else:
+    fn = ops[a.op]
+with torch.no_grad():
+    for _ in range(a.iters):
+        fn()
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+with torch.no_grad():
+    e0.record()
+    for _ in range(a.iters):
+        fn()
+    e1.record()
+torch.cuda.synchronize()
+print(f"{a.op}: {e0.elapsed_time(e1) / a.iters * 1e3:.1f} us per call (B={B} C={C} {H}x{W}, flow={a.flow})")

@@ -19,6 +19,25 @@ int  sm_count();                          // cached multiprocessor count of the 
 static inline unsigned ceil_div(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Division of a non-negative 31-bit integer by a run-time constant without the ~40-instruction
+// integer-division sequence: quotient = umulhi(n, mul) >> shr (mul/shr precomputed on the host).
+struct FastDiv {
+    unsigned mul, shr, div;
+    FastDiv() : mul(0), shr(0), div(1) {}
+    explicit FastDiv(unsigned d) : div(d)
+    {
+        if (d <= 1) { mul = 0; shr = 0; div = 1; return; }
+        unsigned lg = 31 - __builtin_clz(d);
+        if (d & (d - 1)) ++lg;   // ceil(log2(d))
+        const unsigned p = 31 + lg;
+        mul = (unsigned)(((1ull << p) + d - 1) / d);
+        shr = p - 32;
+    }
+#ifdef __CUDACC__
+    __device__ __forceinline__ int quot(int n) const { return div == 1 ? n : (int)(__umulhi((unsigned)n, mul) >> shr); }
+#endif
+};
+
 // ---- device side ---------------------------------------------------------------------
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return min(max(v, lo), hi); }
 

@@ -14,6 +14,10 @@
 //     needs clearing;
 //   * 64-bit plane offsets (B*C*H*W exceeds 2^31 for the 196-channel context tensors at 1080p).
 #include "common.cuh"
+#include "tma.cuh"
+
+#include <algorithm>
+#include <cstdlib>
 
 namespace vfidkr {
 namespace {
@@ -21,6 +25,14 @@ namespace {
 enum { V_ORI = 0, V_DKR = 1, V_DEFOR = 2, V_NOFILT = 3 };
 
 constexpr int BX = 32, BY = 8;  // thread block = 32 x 8 output pixels
+
+// VFIDKR_FORCE_DIRECT=1 selects the direct (non-TMA) kernels; used by the tests to check that both
+// paths give the same results, never needed in production.
+inline bool force_direct_path()
+{
+    const char *e = std::getenv("VFIDKR_FORCE_DIRECT");
+    return e && e[0] == '1';
+}
 
 struct FiPix {
     bool in_range;
@@ -159,6 +171,151 @@ fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ i
             }
             st_stream(o + (size_t)c * HW, qTL * TL + qTR * TR + qBL * BL + qBR * BR);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// "_ori" forward, TMA-streamed (the production path for F == 4 when W % 4 == 0 and the bases are
+// 16-byte aligned).  84 % of the algorithmic bytes of this op are the flow + filter planes, read
+// exactly once.  A persistent CTA walks tiles of TW x TH pixels; one elected thread streams the 18
+// planes of the NEXT tile into shared memory with two cp.async.bulk.tensor (TMA) box loads while the
+// 256 threads work on the current tile, so HBM latency is decoupled from the gather/FMA phase and no
+// registers are spent on loads in flight.  Per pixel the 16 taps and the flow are then read from
+// shared memory (conflict-free, stride-1) and the image window is gathered through L1/L2.
+// ------------------------------------------------------------------------------------------
+namespace tmafwd {
+constexpr int TW = 64, TH = 4, NTHREADS = TW * TH, STAGES = 2;
+constexpr int FILT_FLOATS = 16 * TH * TW, FLOW_FLOATS = 2 * TH * TW;
+constexpr uint32_t STAGE_BYTES = (FILT_FLOATS + FLOW_FLOATS) * sizeof(float);
+}  // namespace tmafwd
+
+// one channel of one pixel: 4x4 window starting at `win` (row stride W), all taps inside the plane
+__device__ __forceinline__ float fi_window_interior(const float *__restrict__ win, int W, const float (&w)[16],
+                                                    float qTL, float qTR, float qBL, float qBR)
+{
+    const float *r0 = win, *r1 = win + W, *r2 = r1 + W, *r3 = r2 + W;
+    // the 16 loads carry immediate offsets off four row pointers; quadrant sums in the reference's tap order
+    float TL = __ldg(r0) * w[0];
+    TL += __ldg(r0 + 1) * w[1];
+    float TR = __ldg(r0 + 2) * w[2];
+    TR += __ldg(r0 + 3) * w[3];
+    TL += __ldg(r1) * w[4];
+    TL += __ldg(r1 + 1) * w[5];
+    TR += __ldg(r1 + 2) * w[6];
+    TR += __ldg(r1 + 3) * w[7];
+    float BL = __ldg(r2) * w[8];
+    BL += __ldg(r2 + 1) * w[9];
+    float BR = __ldg(r2 + 2) * w[10];
+    BR += __ldg(r2 + 3) * w[11];
+    BL += __ldg(r3) * w[12];
+    BL += __ldg(r3 + 1) * w[13];
+    BR += __ldg(r3 + 2) * w[14];
+    BR += __ldg(r3 + 3) * w[15];
+    return qTL * TL + qTR * TR + qBL * BL + qBR * BR;
+}
+
+// CT > 0: compile-time channel count (fully unrolled, all gathers independent); CT == 0: run-time C
+template <int CT>
+__global__ void __launch_bounds__(tmafwd::NTHREADS, 4)
+fi_forward_ori_tma_kernel(const __grid_constant__ CUtensorMap map_flow, const __grid_constant__ CUtensorMap map_filt,
+                          const float *__restrict__ in1, float *__restrict__ out,
+                          int Crt, int H, int W, int tiles_x, int tiles_y, int num_tiles,
+                          const FastDiv div_tiles_x, const FastDiv div_tiles_image)
+{
+    using namespace tmafwd;
+    __shared__ __align__(128) float s_filt[STAGES][FILT_FLOATS];
+    __shared__ __align__(128) float s_flow[STAGES][FLOW_FLOATS];
+    __shared__ __align__(8) uint64_t s_full[STAGES];
+
+    const int C = CT > 0 ? CT : Crt;
+    const int tid = threadIdx.x;
+    const int tx = tid % TW, ty = tid / TW;
+    const int sp = ty * TW + tx;
+    const size_t HW = (size_t)H * W;
+    const int tiles_per_image = tiles_x * tiles_y;
+
+    if (tid == 0) {
+        prefetch_tensormap(&map_flow);
+        prefetch_tensormap(&map_filt);
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto issue = [&](int tile, int stage) {   // called by thread 0 only
+        const int b = div_tiles_image.quot(tile), rem = tile - b * tiles_per_image;
+        const int by = div_tiles_x.quot(rem), bx = rem - by * tiles_x;
+        mbar_arrive_expect_tx(&s_full[stage], STAGE_BYTES);
+        tma_load_3d(s_flow[stage], &map_flow, &s_full[stage], bx * TW, by * TH, b * 2);
+        tma_load_3d(s_filt[stage], &map_filt, &s_full[stage], bx * TW, by * TH, b * 16);
+    };
+
+    int tile = blockIdx.x;
+    if (tid == 0 && tile < num_tiles) issue(tile, 0);
+
+    for (int it = 0; tile < num_tiles; ++it, tile += gridDim.x) {
+        const int stage = it % STAGES;
+        const int next = tile + gridDim.x;
+        // the buffer of the next stage was last read in iteration it-1, which ended with __syncthreads()
+        if (tid == 0 && next < num_tiles) issue(next, (it + 1) % STAGES);
+
+        const int b = div_tiles_image.quot(tile), rem = tile - b * tiles_per_image;
+        const int by = div_tiles_x.quot(rem), bx = rem - by * tiles_x;
+        const int w_i = bx * TW + tx, h_i = by * TH + ty;
+        const size_t pix = (size_t)h_i * W + w_i;
+        const float *img = in1 + (size_t)b * C * HW;
+        float *o = out + (size_t)b * C * HW + pix;
+
+        mbar_wait(&s_full[stage], (uint32_t)((it / STAGES) & 1));
+
+        if (w_i < W && h_i < H) {
+            const float fx = s_flow[stage][sp], fy = s_flow[stage][TH * TW + sp];
+            const FiPix p = fi_pixel(w_i, h_i, fx, fy, W, H, 4);
+            if (!p.in_range) {   // :2814-2819 copies input1
+                for (int c = 0; c < C; ++c) st_stream(o + (size_t)c * HW, __ldg(img + (size_t)c * HW + pix));
+            } else {
+                float w[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) w[k] = s_filt[stage][k * (TH * TW) + sp];
+                const float qTL = (1 - p.alpha) * (1 - p.beta), qTR = p.alpha * (1 - p.beta);
+                const float qBL = (1 - p.alpha) * p.beta, qBR = p.alpha * p.beta;
+                if (p.L >= 0 && p.T >= 0 && p.L + 3 < W && p.T + 3 < H) {
+                    // interior window: no clamping, rows are contiguous -> immediate-offset loads
+                    const float *win = img + ((size_t)p.T * W + p.L);
+                    if (CT > 0) {
+                        float res[CT > 0 ? CT : 1];
+#pragma unroll
+                        for (int c = 0; c < CT; ++c) res[c] = fi_window_interior(win + (size_t)c * HW, W, w, qTL, qTR, qBL, qBR);
+#pragma unroll
+                        for (int c = 0; c < CT; ++c) st_stream(o + (size_t)c * HW, res[c]);
+                    } else {
+#pragma unroll 2
+                        for (int c = 0; c < C; ++c)
+                            st_stream(o + (size_t)c * HW, fi_window_interior(win + (size_t)c * HW, W, w, qTL, qTR, qBL, qBR));
+                    }
+                } else {
+                    // window touches the border: clamp every tap (:2751-2753)
+                    int ro[4], co[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        ro[j] = clampi(p.T + j, 0, H - 1) * W;
+                        co[j] = clampi(p.L + j, 0, W - 1);
+                    }
+                    for (int c = 0; c < C; ++c) {
+                        const float *pl = img + (size_t)c * HW;
+                        float Q[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                                Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)] += __ldg(pl + ro[j] + co[i]) * w[j * 4 + i];
+                        st_stream(o + (size_t)c * HW, qTL * Q[0] + qTR * Q[1] + qBL * Q[2] + qBR * Q[3]);
+                    }
+                }
+            }
+        }
+        __syncthreads();   // every thread is done with this stage's buffers before they are refilled
     }
 }
 
@@ -369,8 +526,33 @@ int launch_forward(const float *in1, const float *in2, const float *in3, const f
     if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
     dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
     if constexpr (V == V_ORI) {
-        if (F == 4) fi_forward_ori_kernel<4><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
-        else        fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
+        if (F == 4) {
+            // production path: TMA-streamed persistent kernel; needs 16-byte aligned rows for the tensor maps
+            if (W % 4 == 0 && aligned16(in2) && aligned16(in3) && !force_direct_path()) {
+                using namespace tmafwd;
+                CUtensorMap mflow, mfilt;
+                if (encode_tensor_map_3d(&mflow, in2, W, H, (uint64_t)B * 2, TW, TH, 2) &&
+                    encode_tensor_map_3d(&mfilt, in3, W, H, (uint64_t)B * 16, TW, TH, 16)) {
+                    const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
+                    const long long num_tiles = (long long)tiles_x * tiles_y * B;
+                    if (num_tiles < (1ll << 31)) {
+                        const int nblk = (int)std::min<long long>(num_tiles, (long long)sm_count() * 4);
+                        const FastDiv dx((unsigned)tiles_x), di((unsigned)(tiles_x * tiles_y));
+                        if (C == 3)
+                            fi_forward_ori_tma_kernel<3><<<nblk, NTHREADS, 0, s>>>(mflow, mfilt, in1, out, C, H, W, tiles_x,
+                                                                                  tiles_y, (int)num_tiles, dx, di);
+                        else
+                            fi_forward_ori_tma_kernel<0><<<nblk, NTHREADS, 0, s>>>(mflow, mfilt, in1, out, C, H, W, tiles_x,
+                                                                                  tiles_y, (int)num_tiles, dx, di);
+                        note_launch();
+                        return check_launch("filterinterpolation forward (tma)");
+                    }
+                }
+            }
+            fi_forward_ori_kernel<4><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
+        } else {
+            fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
+        }
     } else if (F == 4) {
         if (C == 3) fi_forward_dkr_kernel<V, 4, 3><<<grid, block, 0, s>>>(in1, in2, in3, in4, out, C, H, W, F);
         else        fi_forward_dkr_kernel<V, 4, 4><<<grid, block, 0, s>>>(in1, in2, in3, in4, out, C, H, W, F);
