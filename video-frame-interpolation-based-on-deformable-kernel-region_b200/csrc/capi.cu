@@ -58,34 +58,54 @@ static encode_tiled_fn resolve_encode()
 // Encoding a tensor map is a driver call; callers hit the same (base, shape, box) repeatedly (the allocator
 // recycles blocks), so a small thread-local direct-mapped cache removes it from the steady-state launch path.
 struct MapKey {
-    const float *base; uint64_t W, H, D; uint32_t bw, bh, bd;
+    const float *base; uint64_t d[4]; uint32_t b[4]; uint32_t rank;
     bool operator==(const MapKey &o) const
-    { return base == o.base && W == o.W && H == o.H && D == o.D && bw == o.bw && bh == o.bh && bd == o.bd; }
+    {
+        return base == o.base && rank == o.rank && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && d[3] == o.d[3] &&
+               b[0] == o.b[0] && b[1] == o.b[1] && b[2] == o.b[2] && b[3] == o.b[3];
+    }
 };
 struct MapSlot { MapKey key; CUtensorMap map; bool valid; };
 
-bool encode_tensor_map_3d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t D,
-                          uint32_t boxW, uint32_t boxH, uint32_t boxD)
+static bool encode_cached(CUtensorMap *map, const MapKey &key)
 {
     constexpr int SLOTS = 64;
     static thread_local MapSlot cache[SLOTS];
-    const MapKey key{base, W, H, D, boxW, boxH, boxD};
-    const uint64_t h = (reinterpret_cast<uintptr_t>(base) >> 8) * 0x9E3779B97F4A7C15ull ^ (W * 31 + H * 17 + D * 7 + boxD);
+    uint64_t h = (reinterpret_cast<uintptr_t>(key.base) >> 8) * 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < 4; ++i) h ^= (key.d[i] * 0x100000001B3ull + key.b[i]) << (7 * i);
     MapSlot &slot = cache[(h >> 32) % SLOTS];
     if (slot.valid && slot.key == key) { *map = slot.map; return true; }
 
     encode_tiled_fn enc = resolve_encode();
     if (!enc) return false;
-    const cuuint64_t dims[3] = {W, H, D};
-    const cuuint64_t strides[2] = {W * sizeof(float), W * H * sizeof(float)};   // byte strides of dims 1 and 2
-    const cuuint32_t box[3] = {boxW, boxH, boxD};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base), dims, strides, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    cuuint64_t dims[4], strides[3];
+    cuuint32_t box[4], estr[4];
+    uint64_t pitch = sizeof(float);
+    for (uint32_t i = 0; i < key.rank; ++i) {
+        dims[i] = key.d[i]; box[i] = key.b[i]; estr[i] = 1;
+        pitch *= key.d[i];
+        if (i + 1 < key.rank) strides[i] = pitch;   // byte stride of dimension i+1
+    }
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, key.rank, const_cast<float *>(key.base), dims, strides, box,
+                           estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return false;
     slot.key = key; slot.map = *map; slot.valid = true;
     return true;
+}
+
+bool encode_tensor_map_3d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t D,
+                          uint32_t boxW, uint32_t boxH, uint32_t boxD)
+{
+    const MapKey key{base, {W, H, D, 1}, {boxW, boxH, boxD, 1}, 3};
+    return encode_cached(map, key);
+}
+
+bool encode_tensor_map_4d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t C, uint64_t N,
+                          uint32_t boxW, uint32_t boxH, uint32_t boxC)
+{
+    const MapKey key{base, {W, H, C, N}, {boxW, boxH, boxC, 1}, 4};
+    return encode_cached(map, key);
 }
 
 }  // namespace vfidkr

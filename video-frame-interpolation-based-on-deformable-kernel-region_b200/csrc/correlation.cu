@@ -4,17 +4,22 @@
 // shape rules of correlation_cuda.cc:23-36.  What is different:
 //   * NCHW is read directly with zero padding applied on the fly -- the reference's channels_first
 //     repack into padded NHWC scratch tensors (two extra passes + two fill_ kernels) is gone;
-//   * fast path for the only configuration VFIDKR uses (kernel_size 1, stride1 = stride2 = 1,
-//     PWCNet.py:72): shared-memory tiles of both feature maps, each thread owns 4 adjacent pixels x
-//     9 horizontal displacements of one vertical displacement, so every f2 value fetched from shared
-//     memory feeds up to 4 FMAs (the reference runs 81 serial warp reductions per output pixel);
+//   * fast path for the only configuration VFIDKR uses (kernel_size 1, stride1 = stride2 = 1, md = 4,
+//     PWCNet.py:72): a persistent kernel with TMA-streamed shared-memory tiles of both feature maps; each
+//     thread owns 4 adjacent pixels x 9 horizontal x 3 vertical displacements (108 accumulators), so a
+//     float4 fetched from shared memory feeds ~11 FMAs (the reference runs 81 serial warp reductions per
+//     output pixel over a padded NHWC copy);
 //   * backward for the fast path keeps the 81 upstream gradients of a pixel in registers and reuses
 //     them for every channel, one launch for the whole batch (the reference launches per batch item);
 //   * a generic path restates the reference formulas for any (kernel_size, stride1, stride2).
 // fp32 FMA throughput, not HBM, bounds this op on SIMT (162*C flop vs 4*(2C+81) bytes per pixel);
 // tcgen05 is not used: the 9-wide band of the (T+8)-wide product wastes >= 89% of a GEMM tile and
 // 1e-5 parity needs a 3xTF32 split, which costs more tensor time than the SIMT kernel.
+#include <algorithm>
+#include <cstring>
+
 #include "common.cuh"
+#include "tma.cuh"
 
 namespace vfidkr {
 namespace {
@@ -74,103 +79,242 @@ corr_forward_generic_kernel(const float *__restrict__ in1, const float *__restri
 }
 
 // ---------------------------------------------------------------------------------------------
-// fast forward: kernel_size 1, stride1 = stride2 = 1, displacement radius DR (9 x 9 for DR = 4).
-// Block = TY x TX output pixels; threads = (TX/4 pixel quads) x (2*DR+1 vertical displacements) x TY.
+// fast forward: kernel_size 1, stride1 = stride2 = 1, max_displacement 4 (9 x 9 displacements) -- the only
+// configuration VFIDKR uses (PWCNet.py:72).
+//
+// A persistent CTA walks output tiles of TY x TX pixels and, per tile, the channel dimension in chunks of
+// CK.  Each (tile, chunk) item needs an f1 tile [CK][TY][TX] and an f2 tile [CK][TY+8][TX+8]; they are
+// streamed into a two-stage shared-memory ring by TMA box loads (cp.async.bulk.tensor.4d over [N][C][H][W]).
+// TMA's out-of-bounds zero fill IS the op's zero padding (negative / past-the-edge coordinates, and channels
+// past C), so the reference's padded NHWC repack (correlation_cuda_kernel.cu:47-70) needs no counterpart.
+// Thread tile: 4 adjacent pixels x 9 horizontal x 3 vertical displacements = 108 fp32 accumulators;
+// per channel it reads 1 + 3*3 float4 from shared memory (conflict-free, 16 B lane stride) for 108 FMAs.
+// When W % 4 != 0 (TMA needs 16-byte row pitch) the same kernel stages the tiles with plain loads.
 // ---------------------------------------------------------------------------------------------
-template <int DR>
-struct FastCfg {
-    static constexpr int D = 2 * DR + 1;
-    static constexpr int TX = 32, TY = 8, CK = 8;
-    static constexpr int F2W = TX + 2 * DR, F2H = TY + 2 * DR;
-    static constexpr int F2P = (F2W + 3) / 4 * 4;   // row pitch in floats (16-byte rows for LDS.128)
-    static constexpr int THREADS = (TX / 4) * D * TY;
-    static constexpr int SMEM_F1 = CK * TY * TX, SMEM_F2 = CK * F2H * F2P;
-};
+namespace cfast {
+constexpr int DR = 4, D = 2 * DR + 1;
+constexpr int TX = 32, TY = 8, CK = 8, PX = 4, TJ = 3;
+constexpr int F2W = TX + 2 * DR, F2H = TY + 2 * DR;
+constexpr int NTHREADS = (TX / PX) * (D / TJ) * TY;          // 8 * 3 * 8 = 192
+constexpr int F1_FLOATS = CK * TY * TX, F2_FLOATS = CK * F2H * F2W;
+constexpr uint32_t STAGE_BYTES = (F1_FLOATS + F2_FLOATS) * sizeof(float);
+// ring depth: 3 stages with two CTAs per SM for large maps; when there are fewer tiles than SMs (the coarse
+// PWC levels) a CTA has the SM to itself and a 7-deep ring hides the load latency of its long channel loop
+constexpr int STAGES_LARGE = 3, STAGES_SMALL = 7;
+constexpr size_t smem_bytes(int stages) { return (size_t)stages * STAGE_BYTES + 128; }
+static_assert(D % TJ == 0 && TX % PX == 0, "tile shape");
+}  // namespace cfast
 
-template <int DR>
-__global__ void __launch_bounds__(FastCfg<DR>::THREADS)
-corr_forward_fast_kernel(const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
-                         int C, int H, int W, int shift, int oh, int ow)
+template <bool TMA, int STAGES>
+__global__ void __launch_bounds__(cfast::NTHREADS, STAGES <= 3 ? 2 : 1)
+corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                          const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
+                          int C, int H, int W, int shift, int oh, int ow, int tiles_x, int tiles_y, int num_tiles,
+                          const FastDiv div_tiles_x, const FastDiv div_tiles_image)
 {
-    using K = FastCfg<DR>;
-    constexpr int D = K::D;
-    __shared__ __align__(16) float s1[K::SMEM_F1];
-    __shared__ __align__(16) float s2[K::SMEM_F2];
-
-    const int n = blockIdx.z;
-    const int ox0 = blockIdx.x * K::TX, oy0 = blockIdx.y * K::TY;   // output tile origin
-    const int ix0 = ox0 + shift, iy0 = oy0 + shift;                 // same pixel in image coordinates
-    const size_t HW = (size_t)H * W;
-    const float *f1 = in1 + (size_t)n * C * HW, *f2 = in2 + (size_t)n * C * HW;
+    using namespace cfast;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *s1 = reinterpret_cast<float *>(smem_raw);                     // [STAGES][F1_FLOATS]
+    float *s2 = s1 + STAGES * F1_FLOATS;                                  // [STAGES][F2_FLOATS]
+    uint64_t *s_full = reinterpret_cast<uint64_t *>(s2 + STAGES * F2_FLOATS);
 
     const int tid = threadIdx.x;
-    const int g = tid % (K::TX / 4);             // pixel quad inside the row
-    const int tj = (tid / (K::TX / 4)) % D;      // vertical displacement index 0..D-1  (tj - DR)
-    const int ry = tid / ((K::TX / 4) * D);      // row inside the tile
+    const int g = tid % (TX / PX);
+    const int tjg = (tid / (TX / PX)) % (D / TJ);
+    const int ry = tid / ((TX / PX) * (D / TJ));
+    const int nchunks = (C + CK - 1) / CK;
+    const int tiles_per_image = tiles_x * tiles_y;
+    const size_t HW = (size_t)H * W;
 
-    float acc[4][D];
-#pragma unroll
-    for (int p = 0; p < 4; ++p)
-#pragma unroll
-        for (int t = 0; t < D; ++t) acc[p][t] = 0.0f;
-
-    for (int c0 = 0; c0 < C; c0 += K::CK) {
-        // ---- stage CK channels of both maps (zero outside the image) ----
-        for (int idx = tid; idx < K::SMEM_F1; idx += K::THREADS) {
-            const int x = idx % K::TX, y = (idx / K::TX) % K::TY, c = idx / (K::TX * K::TY);
-            const int gy = iy0 + y, gx = ix0 + x;
-            float v = 0.0f;
-            if (c0 + c < C && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(f1 + (size_t)(c0 + c) * HW + (size_t)gy * W + gx);
-            s1[idx] = v;
-        }
-        for (int idx = tid; idx < K::CK * K::F2H * K::F2W; idx += K::THREADS) {
-            const int x = idx % K::F2W, y = (idx / K::F2W) % K::F2H, c = idx / (K::F2W * K::F2H);
-            const int gy = iy0 - DR + y, gx = ix0 - DR + x;
-            float v = 0.0f;
-            if (c0 + c < C && gy >= 0 && gy < H && gx >= 0 && gx < W) v = __ldg(f2 + (size_t)(c0 + c) * HW + (size_t)gy * W + gx);
-            s2[(c * K::F2H + y) * K::F2P + x] = v;
-        }
-        __syncthreads();
-        // ---- 4 pixels x D horizontal displacements per thread ----
-#pragma unroll
-        for (int c = 0; c < K::CK; ++c) {
-            const float4 a = *reinterpret_cast<const float4 *>(&s1[(c * K::TY + ry) * K::TX + 4 * g]);
-            const float *row = &s2[(c * K::F2H + ry + tj) * K::F2P + 4 * g];
-            float bv[4 + 2 * DR + 2];   // 12 for DR = 4 (three LDS.128)
-#pragma unroll
-            for (int q = 0; q < (4 + 2 * DR + 3) / 4; ++q) {
-                const float4 t = *reinterpret_cast<const float4 *>(row + 4 * q);
-                bv[4 * q + 0] = t.x; bv[4 * q + 1] = t.y; bv[4 * q + 2] = t.z; bv[4 * q + 3] = t.w;
-            }
-            const float av[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int p = 0; p < 4; ++p)
-#pragma unroll
-                for (int t = 0; t < D; ++t) acc[p][t] = fmaf(av[p], bv[p + t], acc[p][t]);
-        }
-        __syncthreads();
+    if (TMA && tid == 0) {
+        prefetch_tensormap(&map1);
+        prefetch_tensormap(&map2);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
+        fence_mbar_init();
     }
-    // ---- write: channel (tj, ti), row oy0+ry, pixels ox0+4g .. +3 ----
-    const int oy = oy0 + ry, ox = ox0 + 4 * g;
-    if (oy >= oh) return;
-    const float inv = 1.0f / (float)C;   // nelems = kernel_size^2 * C (:104); the division is applied as acc / nelems
-    const float nel = (float)C;
-    (void)inv;
-    const size_t plane = (size_t)oh * ow;
-    float *o = out + ((size_t)n * D * D + (size_t)tj * D) * plane + (size_t)oy * ow + ox;
-    const bool vec = (ox + 3 < ow) && ((((size_t)oy * ow + ox) & 3) == 0) && ((plane & 3) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    __syncthreads();
+
+    auto decode = [&](int tile, int &n, int &by, int &bx) {
+        n = div_tiles_image.quot(tile);
+        const int rem = tile - n * tiles_per_image;
+        by = div_tiles_x.quot(rem);
+        bx = rem - by * tiles_x;
+    };
+    auto issue = [&](int tile, int chunk, int stage) {   // thread 0 only (TMA path)
+        int n, by, bx;
+        decode(tile, n, by, bx);
+        const int ix0 = bx * TX + shift, iy0 = by * TY + shift;
+        mbar_arrive_expect_tx(&s_full[stage], STAGE_BYTES);
+        tma_load_4d(s1 + stage * F1_FLOATS, &map1, &s_full[stage], ix0, iy0, chunk * CK, n);
+        tma_load_4d(s2 + stage * F2_FLOATS, &map2, &s_full[stage], ix0 - DR, iy0 - DR, chunk * CK, n);
+    };
+
+    // cp.async staging of one (tile, chunk) item by all threads: one warp per tile row, lanes along x;
+    // zero fill outside the image and past C.  Used when the TMA pitch requirement does not hold.
+    auto stage_async = [&](int tile, int chunk, int stage) {
+        int n, by, bx;
+        decode(tile, n, by, bx);
+        const int ix0 = bx * TX + shift, iy0 = by * TY + shift;
+        const int warp = tid >> 5, lane = tid & 31, nwarps = NTHREADS / 32;
+        const float *f1 = in1 + (size_t)n * C * HW, *f2 = in2 + (size_t)n * C * HW;
+        float *d1 = s1 + stage * F1_FLOATS, *d2 = s2 + stage * F2_FLOATS;
+        for (int row = warp; row < CK * TY; row += nwarps) {
+            const int c = row / TY, y = row % TY, gy = iy0 + y, cc = chunk * CK + c, gx = ix0 + lane;
+            const bool ok = cc < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            cp_async_4(d1 + row * TX + lane, ok ? f1 + (size_t)cc * HW + (size_t)gy * W + gx : f1, ok);
+        }
+        for (int row = warp; row < CK * F2H; row += nwarps) {
+            const int c = row / F2H, y = row % F2H, gy = iy0 - DR + y, cc = chunk * CK + c;
+            const bool rowok = cc < C && gy >= 0 && gy < H;
+            const float *src = f2 + (rowok ? (size_t)cc * HW + (size_t)gy * W : 0);
+            for (int x = lane; x < F2W; x += 32) {
+                const int gx = ix0 - DR + x;
+                const bool ok = rowok && gx >= 0 && gx < W;
+                cp_async_4(d2 + row * F2W + x, ok ? src + gx : f2, ok);
+            }
+        }
+        cp_async_commit();
+    };
+
+    // flat item stream of this CTA: item k = (tile blockIdx.x + (k / nchunks) * gridDim.x, chunk k % nchunks)
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int total_items = my_tiles * nchunks;
+    auto produce = [&](int k) {   // start the loads of item k into stage k % STAGES (a no-op past the end)
+        if (k < total_items) {
+            const int t = k / nchunks, c = k - t * nchunks;
+            const int tl = blockIdx.x + t * gridDim.x;
+            if (TMA) { if (tid == 0) issue(tl, c, k % STAGES); }
+            else stage_async(tl, c, k % STAGES);
+        } else if (!TMA) {
+            cp_async_commit();   // empty group keeps the wait count uniform
+        }
+    };
+#pragma unroll 1
+    for (int k = 0; k < STAGES - 1; ++k) produce(k);
+
+    int it = 0;   // running item index (selects stage and mbarrier phase)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int n, by, bx;
+        decode(tile, n, by, bx);
+        const int ox0 = bx * TX, oy0 = by * TY;
+
+        float acc[TJ][PX][D];
+#pragma unroll
+        for (int t = 0; t < TJ; ++t)
+#pragma unroll
+            for (int p = 0; p < PX; ++p)
+#pragma unroll
+                for (int d = 0; d < D; ++d) acc[t][p][d] = 0.0f;
+
+        for (int ch = 0; ch < nchunks; ++ch, ++it) {
+            const int stage = it % STAGES;
+            // keep STAGES-1 items in flight; the stage being refilled was last read in item it-1, which ended
+            // with __syncthreads()
+            produce(it + STAGES - 1);
+            if (TMA) {
+                mbar_wait(&s_full[stage], (uint32_t)((it / STAGES) & 1));
+            } else {
+                cp_async_wait<STAGES - 1>();   // all but the STAGES-1 most recent groups have landed
+                __syncthreads();
+            }
+            const float *p1 = s1 + stage * F1_FLOATS + ry * TX + PX * g;
+            const float *p2 = s2 + stage * F2_FLOATS + (ry + TJ * tjg) * F2W + PX * g;
+#pragma unroll 2
+            for (int c = 0; c < CK; ++c) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(p1 + c * (TY * TX));
+                const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                for (int t = 0; t < TJ; ++t) {
+                    const float *row = p2 + (c * F2H + t) * F2W;
+                    const float4 b0 = *reinterpret_cast<const float4 *>(row);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(row + 4);
+                    const float4 b2 = *reinterpret_cast<const float4 *>(row + 8);
+                    const float bv[12] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w};
+#pragma unroll
+                    for (int p = 0; p < PX; ++p)
+#pragma unroll
+                        for (int d = 0; d < D; ++d) acc[t][p][d] = fmaf(av[p], bv[p + d], acc[t][p][d]);
+                }
+            }
+            __syncthreads();   // all reads of this stage are done before it is refilled
+        }
+
+        // ---- write the 27 displacement channels of this thread: out[n, (tj, ti), oy, ox .. ox+3] ----
+        const int oy = oy0 + ry, ox = ox0 + PX * g;
+        if (oy < oh && ox < ow) {
+            // nelems = kernel_size^2 * C (:104); the reference divides (:143), here it is one reciprocal and a
+            // multiply per output (<= 1 ulp apart, far inside the 1e-5 parity bound; an IEEE division costs ~10
+            // instructions x 108 outputs per thread)
+            const float inv = 1.0f / (float)C;
+            const size_t plane = (size_t)oh * ow;
+            float *o = out + ((size_t)n * D * D + (size_t)(TJ * tjg) * D) * plane + (size_t)oy * ow + ox;
+            const bool vec = (ow % 4 == 0) && (ox + 3 < ow) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+            for (int t = 0; t < TJ; ++t)
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    float *ot = o + (size_t)(t * D + d) * plane;
+                    if (vec) {
+                        st_stream4(ot, make_float4(acc[t][0][d] * inv, acc[t][1][d] * inv, acc[t][2][d] * inv, acc[t][3][d] * inv));
+                    } else {
+#pragma unroll
+                        for (int p = 0; p < PX; ++p)
+                            if (ox + p < ow) ot[p] = acc[t][p][d] * inv;
+                    }
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// direct forward for SMALL maps (kernel_size 1, strides 1, md 4): the coarse PWC levels (18x31, 36x62 at
+// 1080p) have too few tiles to fill 148 SMs with the tiled kernel and are issue-bound on a handful of
+// warps.  Here one thread owns (pixel, vertical displacement) and 9 horizontal displacements; warps run
+// along x so the 9 shifted f2 reads of a warp overlap in L1.  No shared memory, no staging, 9x more CTAs.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32 * 9)
+corr_forward_direct_kernel(const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
+                           int C, int H, int W, int shift, int oh, int ow)
+{
+    constexpr int DR = 4, D = 9;
+    const int ox = blockIdx.x * 32 + threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
+    const int tj = (int)threadIdx.y;   // 0..8  <->  displacement tj - 4
+    if (ox >= ow) return;
+    const size_t HW = (size_t)H * W;
+    const int x = ox + shift, y = oy + shift;            // same pixel in image coordinates
+    const int y2 = y + tj - DR;
+    const bool ok1 = x >= 0 && x < W && y >= 0 && y < H;
+    const bool row2 = y2 >= 0 && y2 < H;
+    const float *p1 = in1 + (size_t)n * C * HW + (ok1 ? (size_t)y * W + x : 0);
+    const float *p2 = in2 + (size_t)n * C * HW + (row2 ? (size_t)y2 * W : 0);
+    bool ok2[D];
+    int off2[D];
 #pragma unroll
     for (int t = 0; t < D; ++t) {
-        float *ot = o + (size_t)t * plane;
-        if (vec) {
-            st_stream4(ot, make_float4(acc[0][t] / nel, acc[1][t] / nel, acc[2][t] / nel, acc[3][t] / nel));
-        } else {
+        const int xx = x + t - DR;
+        ok2[t] = ok1 && row2 && xx >= 0 && xx < W;
+        off2[t] = ok2[t] ? xx : 0;
+    }
+    float acc[D];
 #pragma unroll
-            for (int p = 0; p < 4; ++p)
-                if (ox + p < ow) ot[p] = acc[p][t] / nel;
+    for (int t = 0; t < D; ++t) acc[t] = 0.0f;
+    if (ok1 && row2) {
+#pragma unroll 4
+        for (int c = 0; c < C; ++c) {
+            const float a = __ldg(p1 + (size_t)c * HW);
+            const float *r = p2 + (size_t)c * HW;
+#pragma unroll
+            for (int t = 0; t < D; ++t) {
+                const float b = ok2[t] ? __ldg(r + off2[t]) : 0.0f;
+                acc[t] = fmaf(a, b, acc[t]);
+            }
         }
     }
+    const float inv = 1.0f / (float)C;
+    const size_t plane = (size_t)oh * ow;
+    float *o = out + ((size_t)n * D * D + (size_t)tj * D) * plane + (size_t)oy * ow + ox;
+#pragma unroll
+    for (int t = 0; t < D; ++t) o[(size_t)t * plane] = acc[t] * inv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -297,9 +441,41 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
     if (cs.oh <= 0 || cs.ow <= 0) return VFIDKR_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     if (k == 1 && s1 == 1 && s2 == 1 && md == 4) {
-        using K = FastCfg<4>;
-        dim3 grid(ceil_div(cs.ow, K::TX), ceil_div(cs.oh, K::TY), B);
-        corr_forward_fast_kernel<4><<<grid, K::THREADS, 0, s>>>(input1, input2, output, C, H, W, md - pad, cs.oh, cs.ow);
+        using namespace cfast;
+        const int tiles_x = ceil_div(cs.ow, TX), tiles_y = ceil_div(cs.oh, TY);
+        const long long num_tiles = (long long)tiles_x * tiles_y * B;
+        if (num_tiles >= (1ll << 31)) return VFIDKR_ERR_ARG;
+        const FastDiv dx((unsigned)tiles_x), di((unsigned)(tiles_x * tiles_y));
+        CUtensorMap m1, m2;
+        const bool tma = (W % 4 == 0) && aligned16(input1) && aligned16(input2) &&
+                         encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
+                         encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK);
+        if (!tma) { memset(&m1, 0, sizeof m1); memset(&m2, 0, sizeof m2); }
+        if (num_tiles * 4 <= (long long)sm_count()) {
+            // far too few tiles to fill the machine (the coarsest PWC level): one thread per (pixel, vertical
+            // displacement) instead -- measured 66 us vs 142 us for 8x196x18x31
+            dim3 block(32, 9), grid(ceil_div(cs.ow, 32), cs.oh, B);
+            if (cs.oh > 65535) return VFIDKR_ERR_ARG;
+            corr_forward_direct_kernel<<<grid, block, 0, s>>>(input1, input2, output, C, H, W, md - pad, cs.oh, cs.ow);
+            note_launch();
+            return check_launch("correlation forward (direct)");
+        }
+        const bool small = num_tiles <= sm_count();
+        auto launch = [&](auto kernel, int stages, int ctas_per_sm) {
+            // raising the dynamic shared memory limit is idempotent and cheap; do it on every launch so the
+            // attribute is set on whichever device is current
+            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(stages));
+            const int nblk = (int)std::min<long long>(num_tiles, (long long)sm_count() * ctas_per_sm);
+            kernel<<<nblk, NTHREADS, smem_bytes(stages), s>>>(m1, m2, input1, input2, output, C, H, W, md - pad, cs.oh, cs.ow,
+                                                              tiles_x, tiles_y, (int)num_tiles, dx, di);
+        };
+        if (tma) {
+            if (small) launch(corr_forward_tiled_kernel<true, STAGES_SMALL>, STAGES_SMALL, 1);
+            else       launch(corr_forward_tiled_kernel<true, STAGES_LARGE>, STAGES_LARGE, 2);
+        } else {
+            if (small) launch(corr_forward_tiled_kernel<false, STAGES_SMALL>, STAGES_SMALL, 1);
+            else       launch(corr_forward_tiled_kernel<false, STAGES_LARGE>, STAGES_LARGE, 2);
+        }
     } else {
         dim3 block(32, 8), grid(ceil_div(cs.ow, 32), ceil_div(cs.oh, 8), B);
         corr_forward_generic_kernel<<<grid, block, 0, s>>>(input1, input2, output, C, H, W, pad, k, md, s1, s2, cs);

@@ -16,6 +16,10 @@ namespace vfidkr {
 // boxW * 4 a multiple of 16.  Returns false if the driver entry point is unavailable or rejects the map.
 bool encode_tensor_map_3d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t D,
                           uint32_t boxW, uint32_t boxH, uint32_t boxD);
+// Rank-4 variant over a contiguous [N][C][H][W] array: a box that runs past C (or H, W) is zero-filled
+// instead of running into the next batch item.
+bool encode_tensor_map_4d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t C, uint64_t N,
+                          uint32_t boxW, uint32_t boxH, uint32_t boxC);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -57,6 +61,14 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
 }
+// 4-D tiled load (x, y, channel, batch)
+__device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int c, int n)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(c), "r"(n)
+        : "memory");
+}
 // same with an L2 cache-policy hint (createpolicy-generated 64-bit policy)
 __device__ __forceinline__ void tma_load_3d_hint(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y,
                                                  int z, uint64_t policy)
@@ -78,6 +90,21 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
     return p;
 }
+// Ampere-style asynchronous 4-byte copy global -> shared with zero fill (src_bytes = 0 writes 0.0f and
+// reads nothing); used where TMA's 16-byte pitch requirement does not hold.  SASS: LDGSTS.
+__device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src, bool valid)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 4u : 0u)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap *map)
 {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
