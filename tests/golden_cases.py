@@ -1,0 +1,137 @@
+"""Definitions of the golden cases under tests/golden/ (one .npz per case).
+
+Each fixture holds the seeded INPUTS and the OUTPUTS of the reference's own, unmodified CUDA extension
+(built by oracle/build_ref.py, run on a B200 by oracle/make_golden.py).  The same definitions are used by
+the generator and by the tests, so a fixture can be regenerated and checked against its recipe.
+
+Reference undefined behaviour and how the cases treat it
+  * DKR families read `Bottom = Top + 1` / `Right = Left + 1` without clamping
+    (filterinterpolation_cuda_kernel.cu:102-111): a tap on the last row/column with a non-negative offset reads
+    one row/column past the plane.  Cases tagged `neg_offsets` draw every offset from U(-amp, -0.01), which keeps
+    the reference inside the plane for every pixel; cases with symmetric offsets carry a `contract_mask`
+    (pixels whose window stays at least one row/column away from the bottom/right border) and are compared
+    under that mask only.
+  * the reference's atomics make summation order non-deterministic: fixtures of atomically accumulated
+    tensors are compared at the 1e-4 tolerance, everything else at 1e-5 (BASELINE.json north_star).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+import util as U
+
+CASES = {
+    # FilterInterpolation "_ori"
+    "fi_ori_gauss": dict(op="fi_ori", B=2, C=3, H=18, W=28, flow="gauss", filt="softmax", seed=7001),
+    "fi_ori_stress": dict(op="fi_ori", B=1, C=5, H=15, W=21, flow="stress", filt="uniform", seed=7002),
+    "fi_ori_unit": dict(op="fi_ori", B=1, C=3, H=16, W=24, flow="unit", filt="uniform", seed=7003),
+    # 4-input DKR (static quadrants), _deforconv (data-dependent quadrants), _nofilterwithdeforconv
+    "fi_dkr_neg": dict(op="fi_dkr", B=2, C=3, H=16, W=24, flow="unit", filt="softmax", seed=7011, neg_offsets=True),
+    "fi_dkr_sym": dict(op="fi_dkr", B=1, C=3, H=18, W=26, flow="gauss", filt="uniform", seed=7012, neg_offsets=False),
+    "fi_deforconv_neg": dict(op="fi_deforconv", B=2, C=3, H=16, W=24, flow="unit", filt="softmax", seed=7021, neg_offsets=True),
+    "fi_deforconv_sym": dict(op="fi_deforconv", B=1, C=4, H=18, W=26, flow="gauss", filt="uniform", seed=7022, neg_offsets=False),
+    "fi_nofilter_neg": dict(op="fi_nofilter", B=2, C=3, H=16, W=24, flow="unit", seed=7031, neg_offsets=True),
+    "fi_nofilter_sym": dict(op="fi_nofilter", B=1, C=3, H=18, W=26, flow="gauss", seed=7032, neg_offsets=False),
+    # projections
+    "flowproj_gauss": dict(op="flowproj", B=2, H=20, W=30, flow="gauss", seed=7041),
+    "flowproj_stress": dict(op="flowproj", B=1, H=17, W=23, flow="stress", seed=7042),
+    "depthflowproj_gauss": dict(op="depthflowproj", B=2, H=20, W=30, flow="gauss", seed=7051),
+    "depthflowproj_unit": dict(op="depthflowproj", B=1, H=16, W=24, flow="unit", seed=7052),
+    # bilinear warps
+    "interp_gauss": dict(op="interp", B=2, C=3, H=18, W=28, flow="gauss", seed=7061),
+    "interp_stress": dict(op="interp", B=1, C=3, H=15, W=21, flow="stress", seed=7062),
+    "interpch_gauss": dict(op="interpch", B=1, C=5, H=16, W=24, flow="gauss", seed=7063),
+    # separable convolutions
+    "sepconv_f5": dict(op="sepconv", B=2, H=14, W=19, F=5, seed=7071),
+    "sepconvflow_f5": dict(op="sepconvflow", B=2, Ho=10, Wo=15, F=5, seed=7072),
+    # cost volume
+    "corr_pwc": dict(op="corr", B=2, C=8, H=12, W=20, pad=4, k=1, md=4, s1=1, s2=1, seed=7081),
+    "corr_pwc_c196": dict(op="corr", B=1, C=196, H=6, W=9, pad=4, k=1, md=4, s1=1, s2=1, seed=7082),
+    # pad >= md + kernel_radius keeps the reference inside its padded scratch (with less padding it indexes
+    # rInput2 at negative rows/columns, correlation_cuda_kernel.cu:112-121 -- undefined, so not a fixture)
+    "corr_generic": dict(op="corr", B=1, C=4, H=14, W=18, pad=7, k=3, md=6, s1=1, s2=2, seed=7083),
+    "corr_stride2": dict(op="corr", B=1, C=5, H=13, W=17, pad=8, k=1, md=8, s1=2, s2=2, seed=7085, bwd=False),
+    "corr_md2": dict(op="corr", B=1, C=6, H=10, W=13, pad=2, k=1, md=2, s1=1, s2=1, seed=7084),
+}
+
+# outputs accumulated with atomics in the reference (order-dependent rounding) -> 1e-4
+ATOMIC_OUTPUTS = {
+    "fi_ori": {"gi1", "gi3"}, "fi_dkr": {"gi1", "gi3", "gi4"}, "fi_deforconv": {"gi1", "gi3", "gi4"},
+    "fi_nofilter": {"gi1", "gi3"},
+    "flowproj": {"out", "out_fill", "gi1"}, "depthflowproj": {"out", "out_fill", "count", "gi1", "gi2"},
+    "interp": {"gi1"}, "interpch": {"gi1"}, "sepconv": {"gi1", "gi2", "gi3"}, "sepconvflow": set(), "corr": set(),
+}
+# exact-integer outputs (bit-exact)
+EXACT_OUTPUTS = {"flowproj": {"count"}}
+
+
+def offsets(r, B, F, H, W, neg, amp=0.45):
+    if neg:
+        return (-(0.01 + (amp - 0.01) * r.random((B, 2 * F * F, H, W), dtype=np.float32))).astype(np.float32)
+    return U.offsets(r, B, F, H, W, amp)
+
+
+def contract_mask(flow, H, W, F=4):
+    """[B,1,H,W] bool: the pixel's F x F window (before clamping) stays inside rows/cols [0, H-2] x [0, W-2], so
+    no deformed tap of the reference reads past the plane (|offset| < 1)."""
+    fx, fy = flow[:, 0], flow[:, 1]
+    x2 = np.arange(W, dtype=np.float32)[None, None, :] + fx
+    y2 = np.arange(H, dtype=np.float32)[None, :, None] + fy
+    ix, iy = np.trunc(x2).astype(np.int64), np.trunc(y2).astype(np.int64)
+    L, T = ix + 1 - F // 2, iy + 1 - F // 2
+    ok = (L >= 1) & (T >= 1) & (L + F - 1 <= W - 2) & (T + F - 1 <= H - 2)
+    return ok[:, None]
+
+
+def build_inputs(name: str) -> dict:
+    c = CASES[name]
+    r = U.rng(c["seed"])
+    op = c["op"]
+    d = {}
+    if op.startswith("fi_"):
+        B, C, H, W = c["B"], c["C"], c["H"], c["W"]
+        d["input1"] = U.image(r, B, C, H, W)
+        d["input2"] = U.flow(r, B, H, W, c["flow"])
+        if op == "fi_nofilter":
+            d["input3"] = offsets(r, B, 4, H, W, c["neg_offsets"])
+        else:
+            d["input3"] = U.filt(r, B, 4, H, W, c["filt"])
+        if op in ("fi_dkr", "fi_deforconv"):
+            d["input4"] = offsets(r, B, 4, H, W, c["neg_offsets"])
+        d["gradoutput"] = U.image(r, B, C, H, W, "normal")
+    elif op in ("flowproj", "depthflowproj"):
+        B, H, W = c["B"], c["H"], c["W"]
+        d["input1"] = U.flow(r, B, H, W, c["flow"])
+        if op == "depthflowproj":
+            d["input2"] = U.depth_inv(r, B, H, W)
+        d["gradoutput"] = r.standard_normal((B, 2, H, W)).astype(np.float32)
+    elif op in ("interp", "interpch"):
+        B, C, H, W = c["B"], c["C"], c["H"], c["W"]
+        d["input1"] = U.image(r, B, C, H, W)
+        d["input2"] = U.flow(r, B, H, W, c["flow"])
+        d["gradoutput"] = U.image(r, B, C, H, W, "normal")
+    elif op == "sepconv":
+        B, H, W, F = c["B"], c["H"], c["W"], c["F"]
+        d["input1"] = U.image(r, B, 3, H, W)
+        d["input2"] = r.random((B, F, H - F + 1, W - F + 1), dtype=np.float32)
+        d["input3"] = r.random((B, F, H - F + 1, W - F + 1), dtype=np.float32)
+        d["gradoutput"] = r.standard_normal((B, 3, H - F + 1, W - F + 1)).astype(np.float32)
+    elif op == "sepconvflow":
+        B, Ho, Wo, F = c["B"], c["Ho"], c["Wo"], c["F"]
+        d["input1"] = U.image(r, B, 3, Ho + F - 1, Wo + F - 1)
+        d["input2"] = r.random((B, F, Ho, Wo), dtype=np.float32)
+        d["input3"] = r.random((B, F, Ho, Wo), dtype=np.float32)
+        d["input2"][0, :, 0, 0] = 0.0   # the |sum| == 0 -> -2000 branch (separableconvflow_cuda_kernel.cu:66-89)
+        d["gradoutput"] = r.standard_normal((B, 2, Ho, Wo)).astype(np.float32)
+    elif op == "corr":
+        B, C, H, W = c["B"], c["C"], c["H"], c["W"]
+        d["input1"] = U.image(r, B, C, H, W, "normal")
+        d["input2"] = U.image(r, B, C, H, W, "normal")
+        # gradoutput is shaped by the op; drawn by the generator / the test from the same stream
+    else:
+        raise KeyError(op)
+    return d
+
+
+def corr_gradoutput(name: str, shape) -> np.ndarray:
+    return U.rng(CASES[name]["seed"] + 500).standard_normal(shape).astype(np.float32)

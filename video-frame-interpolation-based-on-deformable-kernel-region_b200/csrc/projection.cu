@@ -5,11 +5,14 @@
 // my_package/DepthFlowProjection/depthflowprojection_cuda_kernel.cu:29-341.  One templated kernel
 // family serves both (DEPTH = false -> weight 1).  Atomics are kept exactly where the reference
 // splats (the four corners of (x+fx, y+fy), three planes each); what changes:
-//   * horizontally adjacent corner pairs that land on the same address (a clamped right/bottom
-//     corner) are merged into one RED of twice the value -- same sum, fewer atomics;
+//   * the 2 x 2 splat is split into an atomic vertical half (rows T, Bm at column L: 6 REDs per pixel
+//     instead of 12) and a dense, atomic-free horizontal half fused with the averaging pass -- same sums,
+//     half the atomics, which is what bounds this op (the L2 retires ~1 fp32 RED per clock per slice);
 //   * the accumulation planes are cleared by the library on the stream (no caller zero-fill);
 //   * the backward is a pure gather with register accumulation and a single store per output
 //     (the reference does eight / sixteen read-modify-writes of its own pixel).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vfidkr {
@@ -33,6 +36,13 @@ __device__ __forceinline__ Corners corners(int w_i, int h_i, float fx, float fy,
     return c;
 }
 
+// Splat, restructured.  Every in-range pixel adds the SAME triple (-d*fx, -d*fy, d) to the 2 x 2 block of
+// cells {T, Bm} x {L, R} (:75-88).  The L2 atomic units retire about one fp32 RED per clock per slice, so the
+// splat is bound by the NUMBER of atomics (12 per pixel in the reference).  Here only the left column of the
+// block is splatted -- rows T and Bm at column L, 6 atomics per pixel, 3 when the border clamp makes Bm == T --
+// and the right column is produced by the dense pass below:  A[y][x] = S[y][x] + S[y][x-1],
+// with the reference's border behaviour (R = min(L+1, W-1), so a pixel with L == W-1 hits column W-1 twice):
+//   A[y][W-1] = 2*S[y][W-1] + S[y][W-2].
 template <bool DEPTH>
 __global__ void __launch_bounds__(BX *BY)
 projection_splat_kernel(const float *__restrict__ flow, const float *__restrict__ depth,
@@ -49,33 +59,48 @@ projection_splat_kernel(const float *__restrict__ flow, const float *__restrict_
     const float d = DEPTH ? ld_stream(depth + (size_t)b * HW + pix) : 1.0f;
     const float vx = DEPTH ? -d * fx : -fx, vy = DEPTH ? -d * fy : -fy;   // :75-88 / depth :77-92
     float *ou = out + ((size_t)b * 2 + 0) * HW, *ov = ou + HW, *cn = count + (size_t)b * HW;
-    // rows T and Bm, columns L and R; merge duplicates created by the border clamp
-    const int rows = (c.Bm == c.T) ? 1 : 2, cols = (c.R == c.L) ? 1 : 2;
-    const float mul = (rows == 1 ? 2.0f : 1.0f) * (cols == 1 ? 2.0f : 1.0f);
-    for (int r = 0; r < rows; ++r) {
-        const size_t ro = (size_t)(r == 0 ? c.T : c.Bm) * W;
-        for (int q = 0; q < cols; ++q) {
-            const size_t a = ro + (q == 0 ? c.L : c.R);
-            red_add(ou + a, vx * mul);
-            red_add(ov + a, vy * mul);
-            red_add(cn + a, d * mul);
-        }
+    const size_t a0 = (size_t)c.T * W + c.L;
+    if (c.Bm == c.T) {   // bottom row clamped onto the top row: the cell is hit twice
+        red_add(ou + a0, 2.0f * vx);
+        red_add(ov + a0, 2.0f * vy);
+        red_add(cn + a0, 2.0f * d);
+    } else {
+        const size_t a1 = a0 + W;
+        red_add(ou + a0, vx); red_add(ou + a1, vx);
+        red_add(ov + a0, vy); red_add(ov + a1, vy);
+        red_add(cn + a0, d);  red_add(cn + a1, d);
     }
 }
 
-// averaging (:128-135) -- one pass, in place
-__global__ void __launch_bounds__(256)
-projection_average_kernel(const float *__restrict__ count, float *__restrict__ out, size_t HW, size_t total)
+// Dense pass: completes the horizontal half of the 2 x 2 splat (see above) and averages (:128-135), in place.
+// One CTA owns whole rows and walks each row right to left in segments, so a cell is always read before the
+// thread that rewrites it runs: no scratch buffer is needed and there is no dependence between CTAs.
+constexpr int ROW_THREADS = 256;
+
+__global__ void __launch_bounds__(ROW_THREADS)
+projection_finish_kernel(float *__restrict__ count, float *__restrict__ out, int H, int W, int rows_total)
 {
-    // total = B*HW pixels; out has two planes per batch item
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        const float t = __ldg(count + idx);
-        if (t > 0.0f) {
-            const size_t b = idx / HW, pix = idx - b * HW;
-            float *ou = out + (b * 2) * HW + pix;
-            ou[0] = ou[0] / t;
-            ou[HW] = ou[HW] / t;
+    const size_t HW = (size_t)H * W;
+    for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
+        const int b = row / H, y = row - b * H;
+        float *ou = out + ((size_t)b * 2 + 0) * HW + (size_t)y * W, *ov = ou + HW;
+        float *cn = count + (size_t)b * HW + (size_t)y * W;
+        const int nseg = (W + ROW_THREADS - 1) / ROW_THREADS;
+        for (int seg = nseg - 1; seg >= 0; --seg) {
+            const int x = seg * ROW_THREADS + (int)threadIdx.x;
+            float su = 0.f, sv = 0.f, sc = 0.f;
+            if (x < W) {
+                const float w0 = (x == W - 1) ? 2.0f : 1.0f;   // clamped right corner lands on column W-1 again
+                su = w0 * ou[x]; sv = w0 * ov[x]; sc = w0 * cn[x];
+                if (x > 0) { su += ou[x - 1]; sv += ov[x - 1]; sc += cn[x - 1]; }
+            }
+            __syncthreads();   // every read of this segment (and of the cell left of it) precedes the writes
+            if (x < W) {
+                cn[x] = sc;
+                if (sc > 0.0f) { su = su / sc; sv = sv / sc; }   // :130-134
+                ou[x] = su; ov[x] = sv;
+            }
+            // the next segment (to the left) only reads cells this segment did not write
         }
     }
 }
@@ -167,9 +192,10 @@ int projection_forward(const float *flow, const float *depth, float *count, floa
     if (e) return e;
     dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
     projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(flow, depth, count, out, H, W);
-    const size_t total = (size_t)B * HW;
-    const unsigned nb = (unsigned)min((size_t)sm_count() * 8, (total + 255) / 256);
-    projection_average_kernel<<<nb, 256, 0, s>>>(count, out, HW, total);
+    const long long rows_total = (long long)B * H;
+    if (rows_total >= (1ll << 31)) return VFIDKR_ERR_ARG;
+    const unsigned nb = (unsigned)std::min<long long>(rows_total, (long long)sm_count() * 8);
+    projection_finish_kernel<<<nb, ROW_THREADS, 0, s>>>(count, out, H, W, (int)rows_total);
     note_launch(2);
     if (fillhole) {
         projection_fillhole_kernel<<<grid, block, 0, s>>>(count, out, H, W);
