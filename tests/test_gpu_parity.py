@@ -404,3 +404,74 @@ def test_fi_ori_tma_and_direct_paths_agree(lib, oracle, monkeypatch):
     view.copy_(cu(ft))
     out = lib.FilterInterpolationModule()(cu(I), cu(fl), view)
     U.assert_close(host(out), oracle.fi_forward("ori", I, fl, ft), U.RTOL_FWD, "unaligned filter tensor")
+
+
+# ------------------------------------------------------------------------------ strip kernel (rolling window)
+def big_flow(r, B, H, W, kind):
+    """Flows that exercise the rolling shared-memory window of fi_strip.cu."""
+    if kind == "uniform_motion":      # large constant motion: the window must be re-based away from the strip
+        f = np.zeros((B, 2, H, W), np.float32)
+        f[:, 0] = 37.3
+        f[:, 1] = -21.6
+        f += 0.3 * r.standard_normal((B, 2, H, W)).astype(np.float32)
+    elif kind == "shear":             # x-displacement grows with y: periodic re-basing inside a strip
+        yy = np.arange(H, dtype=np.float32)[None, :, None]
+        f = np.zeros((B, 2, H, W), np.float32)
+        f[:, 0] = 0.35 * yy - 20
+        f[:, 1] = 6 * np.sin(yy / 9.0)
+    elif kind == "wild":              # +-40 px i.i.d.: most tiles do not fit the window (global fallback)
+        f = np.clip(r.standard_normal((B, 2, H, W)) * 25.0, -60, 60).astype(np.float32)
+    elif kind == "jump_back":         # y-flow that jumps up by a block every 16 rows: window rows must be re-loaded
+        yy = np.arange(H)[None, :, None]
+        f = np.zeros((B, 2, H, W), np.float32)
+        f[:, 1] = np.where((yy // 16) % 2 == 0, 18.0, -18.0)
+        f[:, 0] = 2.5
+    else:
+        raise KeyError(kind)
+    return np.ascontiguousarray(f, dtype=np.float32)
+
+
+STRIP_CASES = [  # B, C, H, W, flow
+    (1, 3, 256, 448, "gauss"),            # BASELINE config 1
+    (2, 3, 131, 200, "stress"),           # ragged: W % 64 != 0, H % 4 != 0, out-of-range pixels
+    (1, 3, 96, 256, "smooth"),
+    (1, 3, 180, 192, "uniform_motion"),
+    (1, 3, 200, 160, "shear"),
+    (1, 3, 120, 224, "wild"),
+    (1, 3, 160, 128, "jump_back"),
+    (2, 1, 64, 96, "gauss"),              # narrowest width the path accepts
+    (1, 2, 70, 132, "unit"),
+    (1, 4, 90, 164, "gauss"),
+    (3, 3, 8, 640, "gauss"),              # very short strips: many strip changes per CTA
+]
+
+
+@pytest.mark.parametrize("B,C,H,W,fk", STRIP_CASES)
+def test_fi_ori_strip_kernel(lib, oracle, monkeypatch, B, C, H, W, fk):
+    """fi_strip.cu (rolling shared-memory window fed by TMA) against the oracle and against the direct kernel."""
+    r = U.rng(2100 + H + W)
+    I = U.image(r, B, C, H, W)
+    fl = big_flow(r, B, H, W, fk) if fk in ("uniform_motion", "shear", "wild", "jump_back") else U.flow(r, B, H, W, fk)
+    ft = U.filt(r, B, 4, H, W, "uniform")
+    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "strip")
+    a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
+    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    b = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
+    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    ref = oracle.fi_forward("ori", I, fl, ft)
+    U.assert_close(host(a), ref, U.RTOL_FWD, f"strip kernel vs oracle ({fk})")
+    U.assert_close(host(b), ref, U.RTOL_FWD, f"direct kernel vs oracle ({fk})")
+    assert U.max_err(host(a), host(b).astype(np.float64)) < 2e-6
+
+
+def test_fi_ori_strip_kernel_repeated_launches_are_deterministic(lib):
+    """The forward has no atomics: two launches must agree bit for bit (also shakes out pipeline races)."""
+    B, C, H, W = 4, 3, 512, 960
+    g = torch.Generator(device="cuda").manual_seed(5)
+    I = torch.rand(B, C, H, W, device="cuda", generator=g)
+    lo = (torch.randn(B, 2, H // 4, W // 4, device="cuda", generator=g) * 4).clamp_(-20, 20)
+    fl = torch.nn.functional.interpolate(lo, scale_factor=4, mode="bilinear", align_corners=False).contiguous()
+    ft = torch.softmax(torch.randn(B, 16, H, W, device="cuda", generator=g), 1)
+    first = lib.FilterInterpolationModule()(I, fl, ft).clone()
+    for _ in range(5):
+        assert torch.equal(lib.FilterInterpolationModule()(I, fl, ft), first)

@@ -53,6 +53,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
     while (!mbar_try_wait(bar, parity)) {}
 }
 
+// plain arrival (consumer -> producer "slot free" signalling)
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Wait with a watchdog: a protocol error traps (the launch fails with an error) instead of hanging the GPU.
+// try_wait suspends the thread for a hardware-defined time slice per poll, so the bound is far above any
+// legitimate wait (seconds) yet finite.
+__device__ __forceinline__ void mbar_wait_guarded(uint64_t *bar, uint32_t parity)
+{
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 24)) __trap();
+}
+
 // 3-D tiled load global -> shared, completion signalled on `bar` (complete_tx::bytes)
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
 {
