@@ -6,20 +6,25 @@
 // is what bounds the straightforward kernels (L1 tag/sector throughput and 1.8 cycles per LDG of LSU issue),
 // so here the gathers are served from SHARED memory:
 //
-//   * a persistent CTA owns a contiguous run of 64 x 4 pixel tiles, walked DOWN a 64-column strip of one frame;
-//   * a producer warp streams the flow + filter planes of the next tiles into a 3-stage ring with TMA
-//     (cp.async.bulk.tensor), computes the bounding box of the tile's clamped gather windows from the flow
-//     as soon as it lands, and tops up a ROLLING WINDOW of image rows -- a ring of 12 chunks x 4 rows x 96
-//     columns x C channels, also filled by TMA -- with just the rows the next tile adds (about 4 per tile, so
-//     the image is fetched from L2 ~1.5x instead of the ~4-6x of per-tile halos);
-//   * 8 compute warps (one pixel per thread, warps along x) read flow, taps and the 16 x C window values
-//     with conflict-free LDS and write the result with streaming stores;
-//   * producer/consumer hand-off is mbarrier based (full/empty per stage; image loads complete_tx on their own
-//     barrier); the window is re-based (new x origin, refilled) when the flow leaves it, and a tile whose box
-//     does not fit at all falls back to clamped global gathers -- correctness never depends on the flow.
+//   * one persistent CTA per SM walks 128 x 4 pixel tiles DOWN a 128-column strip segment of one frame; segments
+//     are dealt to CTAs so that neighbouring CTAs work on neighbouring strips at the same rows at the same
+//     time (their overlapping window columns then hit in L2 instead of being fetched from HBM twice);
+//   * 16 compute warps, one pixel per thread, warps along x.  A thread loads the flow of ITS pixel for the tile
+//     LEAD (= 3) tiles ahead straight into registers, derives the clamped extent of that pixel's gather window
+//     and folds it into the tile's bounding box (warp min/max reduction + 4 shared-memory atomics per warp);
+//   * a producer warp (a) streams the 16 filter planes of the next tiles into a 4-stage ring with TMA
+//     (cp.async.bulk.tensor, ~100 KB in flight per SM = HBM latency x bandwidth), and (b) as soon as a tile's
+//     bounding box is complete tops up a ROLLING WINDOW of image rows -- a ring of 48 rows x C channels x 160
+//     columns, row y living in slot y % 48, also filled by TMA -- with just the rows the tile adds (about 4 per
+//     tile, so the image is fetched from L2 ~1.3x instead of the ~4-6x of per-tile halos), three tiles ahead;
+//   * the compute warps then read taps and the 16 x C window values with LDS (conflict-free when the flow is
+//     locally smooth) and write the result with streaming stores;
+//   * hand-off is mbarrier based (filter full / tile done / bbox done / image full).  The window is re-based
+//     (new x origin, refilled) when the flow leaves it, and a tile whose box does not fit at all falls back to
+//     clamped global gathers -- correctness never depends on the flow.
 //
 // Preconditions for this path (checked by the launcher, which otherwise reports "not applicable" and the
-// caller uses the generic kernels): F == 4, 1 <= C <= 4, W % 4 == 0, W >= 96, 16-byte aligned bases.
+// caller uses the generic kernels): F == 4, 1 <= C <= 4, W % 4 == 0, W >= 160, 16-byte aligned bases.
 #include <algorithm>
 #include <climits>
 
@@ -30,29 +35,32 @@
 namespace vfidkr {
 namespace strip {
 
-constexpr int TW = 64, TH = 4, NPIX = TW * TH;     // tile = 256 pixels, one per compute thread
-constexpr int NCOMP_WARPS = NPIX / 32;             // 8 compute warps
+constexpr int TW = 128, TH = 4, NPIX = TW * TH;    // tile = 512 pixels, one per compute thread
+constexpr int NCOMP_WARPS = NPIX / 32;             // 16 compute warps
 constexpr int NTHREADS = NPIX + 32;                // + 1 producer warp
-constexpr int S = 3;                               // flow+filter pipeline depth
-constexpr int WB = 96;                             // columns held by the rolling window
-constexpr int RCH = 12;                            // window ring: 12 chunks x 4 rows = 48 rows
-constexpr int CROWS = 4;
-constexpr int FF_PLANES = 18;                      // 2 flow + 16 taps
-constexpr int FF_FLOATS = FF_PLANES * NPIX;
-constexpr uint32_t FF_BYTES = FF_FLOATS * sizeof(float);
+constexpr int LEAD = 3;                            // flow / bounding box / image window run this many tiles ahead
+constexpr int NB = 8;                              // ring of bounding boxes and tile descriptors (> LEAD)
+constexpr int WB = 160;                            // columns held by the rolling window (tile + 16 either side)
+constexpr int RROWS = 48;                          // rows held by the rolling window (a ring indexed by y % RROWS)
+constexpr int FILT_FLOATS = 16 * NPIX;
+constexpr uint32_t FILT_BYTES = FILT_FLOATS * sizeof(float);
 enum { MODE_NONE = 0, MODE_SMEM = 1, MODE_GLOBAL = 2 };
 
-template <int CG> __host__ __device__ constexpr int chunk_floats() { return CG * CROWS * WB; }
+template <int CG> __host__ __device__ constexpr int row_floats() { return CG * WB; }   // one window row: [C][WB]
+// filter pipeline depth: as deep as shared memory allows next to the window ring
+template <int CG> __host__ __device__ constexpr int stages() { return CG <= 3 ? 4 : 3; }
 template <int CG> __host__ __device__ constexpr size_t smem_bytes()
 {
-    return (size_t)S * FF_BYTES + (size_t)RCH * chunk_floats<CG>() * sizeof(float) + 256;
+    return (size_t)stages<CG>() * FILT_BYTES + (size_t)RROWS * row_floats<CG>() * sizeof(float) + 512;
 }
 
 struct TileMeta { int mode, xorg; };
+struct Box { int xmin, xmax, ymin, ymax; };
 
-// window values of one channel plane from the rolling window; rb[j] = float offset of the (clamped) row j
-template <bool INTERIOR_X>
-__device__ __forceinline__ float window_from_smem(const float *__restrict__ ring, const int (&rb)[4], const int (&co)[4],
+// 16 taps x one channel from the rolling window.  off[j] = float offset of (row j of the window, first column);
+// INTERIOR: the four columns are consecutive (no border clamp), so every LDS carries an immediate offset.
+template <bool INTERIOR>
+__device__ __forceinline__ float window_from_smem(const float *__restrict__ ring, const int (&off)[4], const int (&co)[4],
                                                   const float (&w)[16], float qTL, float qTR, float qBL, float qBR)
 {
     float Q[4] = {0.f, 0.f, 0.f, 0.f};
@@ -60,201 +68,312 @@ __device__ __forceinline__ float window_from_smem(const float *__restrict__ ring
     for (int j = 0; j < 4; ++j)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float v = INTERIOR_X ? ring[rb[j] + co[0] + i] : ring[rb[j] + co[i]];
+            const float v = INTERIOR ? ring[off[j] + i] : ring[off[j] + co[i]];
             Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)] = fmaf(v, w[j * 4 + i], Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)]);
         }
     return qTL * Q[0] + qTR * Q[1] + qBL * Q[2] + qBR * Q[3];
 }
 
+// Position of one thread in the CTA's sequence of pipeline slots (tiles of its items, back to back), advanced
+// incrementally: the per-item decode (two divisions) runs once per item, not once per tile.
+struct Cursor {
+    int item_no;    // index into this CTA's items
+    int left;       // tiles left in the current item, including the current one
+    int b;          // batch item
+    int w_i, h_i;   // pixel of this thread; h_i >= H marks "no pixel" (null slot / past the end)
+    unsigned pix;   // h_i * W + w_i
+};
+
 template <int CG>
-__global__ void __launch_bounds__(NTHREADS, 2)
-fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_flow, const __grid_constant__ CUtensorMap map_filt,
-                            const __grid_constant__ CUtensorMap map_img,
-                            const float *__restrict__ in1, float *__restrict__ out,
-                            int H, int W, int tiles_x, int tiles_y, int total_tiles,
-                            const FastDiv div_tiles_y, const FastDiv div_tiles_x)
+__global__ void __launch_bounds__(NTHREADS, 1)
+fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const __grid_constant__ CUtensorMap map_img,
+                            const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
+                            int H, int W, int tiles_x, int tiles_y, int nseg, int segt, int num_items,
+                            const FastDiv div_tiles_x, const FastDiv div_nseg)
 {
+    constexpr int SF = stages<CG>();
+    constexpr int ROWF = row_floats<CG>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    float *s_ff = reinterpret_cast<float *>(smem_raw);                               // [S][18][TH][TW]
-    float *s_ring = s_ff + S * FF_FLOATS;                                             // [RCH][CG][4][WB]
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + RCH * chunk_floats<CG>());
-    uint64_t *ff_full = s_bar, *ff_empty = s_bar + S, *img_full = s_bar + 2 * S;
-    TileMeta *s_meta = reinterpret_cast<TileMeta *>(s_bar + 3 * S);                   // [S]
-    int *s_cmin = reinterpret_cast<int *>(s_meta + S);                                // [S], producer private
+    float *s_filt = reinterpret_cast<float *>(smem_raw);                              // [SF][16][TH][TW]
+    float *s_ring = s_filt + SF * FILT_FLOATS;                                         // [RROWS][CG][WB]
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + RROWS * ROWF);
+    uint64_t *filt_full = s_bar, *tile_done = s_bar + SF, *bbox_done = s_bar + 2 * SF, *img_full = bbox_done + NB;
+    Box *s_box = reinterpret_cast<Box *>(img_full + NB);                              // [NB]
+    TileMeta *s_meta = reinterpret_cast<TileMeta *>(s_box + NB);                      // [NB]
+    int *s_ymin = reinterpret_cast<int *>(s_meta + NB);                               // [SF], producer private
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t HW = (size_t)H * W;
 
-    // contiguous, balanced run of tiles for this CTA (tile index = (b * tiles_x + bx) * tiles_y + ty)
-    const long long t_begin = (long long)total_tiles * blockIdx.x / gridDim.x;
-    const long long t_end = (long long)total_tiles * (blockIdx.x + 1) / gridDim.x;
-    const int n = (int)(t_end - t_begin);
+    // Work items are strip segments (b, seg, bx) -- `segt` tiles walked downwards -- numbered with bx fastest and
+    // dealt round-robin, so CTAs k and k+1 hold neighbouring strips of the same rows at the same time.
+    // This CTA's pipeline slots are the tiles of its items back to back; slots past the end of a ragged last
+    // segment are "null" (no loads, no pixels) so that stage and phase accounting stays uniform.
+    const int my_items = (int)blockIdx.x < num_items ? (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+    const int n = my_items * segt;
 
     if (tid == 0) {
-        prefetch_tensormap(&map_flow);
         prefetch_tensormap(&map_filt);
         prefetch_tensormap(&map_img);
-        for (int s = 0; s < S; ++s) {
-            mbar_init(&ff_full[s], 1);
-            mbar_init(&ff_empty[s], NCOMP_WARPS);
+        for (int s = 0; s < SF; ++s) {
+            mbar_init(&filt_full[s], 1);
+            mbar_init(&tile_done[s], NCOMP_WARPS);
+        }
+        for (int s = 0; s < NB; ++s) {
+            mbar_init(&bbox_done[s], NCOMP_WARPS);
             mbar_init(&img_full[s], 1);
+            s_box[s] = Box{INT_MAX, INT_MIN, INT_MAX, INT_MIN};
         }
         fence_mbar_init();
     }
     __syncthreads();
 
-    auto decode = [&](int t, int &b, int &bx, int &ty, int &strip_id) {
-        strip_id = div_tiles_y.quot(t);
-        ty = t - strip_id * tiles_y;
-        b = div_tiles_x.quot(strip_id);
-        bx = strip_id - b * tiles_x;
+    // item number (of this CTA) -> batch item, column block, first tile row
+    auto decode_item = [&](int item_no, int &b, int &bx, int &ty0) {
+        const int item = (int)blockIdx.x + item_no * (int)gridDim.x;
+        const int bs = div_tiles_x.quot(item);   // b * nseg + seg
+        bx = item - bs * tiles_x;
+        b = div_nseg.quot(bs);
+        ty0 = (bs - b * nseg) * segt;
     };
 
     if (warp == NCOMP_WARPS) {
         // ================================ producer warp ================================
-        int cur_strip = -1, xorg = 0, base = 0, hi = 0;   // window state: chunks [max(base, hi - RCH), hi) are resident
-        for (int i = 0; i <= n; ++i) {
-            if (i < n) {
-                const int stage = i % S;
-                if (i >= S) mbar_wait_guarded(&ff_empty[stage], (uint32_t)(((i / S) - 1) & 1));
+        // Two independent streams: the filter planes run as far ahead as the SF-deep ring allows (they only wait
+        // for "tile done"), the image window follows the bounding boxes.  The filter stream is advanced from
+        // inside every wait of the image stream, so a window re-base never stalls the HBM prefetch.
+        int f_t = 0, f_b = 0, f_bx = 0, f_ty = 0, f_left = 0, f_item = -1;   // filter stream position
+        auto pump_filters = [&]() {
+            while (f_t < n && (f_t < SF || mbar_test(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1)))) {
+                if (f_left == 0) { ++f_item; decode_item(f_item, f_b, f_bx, f_ty); f_left = segt; }
+                else ++f_ty;
+                --f_left;
                 if (lane == 0) {
-                    int b, bx, ty, sid;
-                    decode((int)t_begin + i, b, bx, ty, sid);
-                    float *dst = s_ff + stage * FF_FLOATS;
-                    mbar_arrive_expect_tx(&ff_full[stage], FF_BYTES);
-                    tma_load_3d(dst, &map_flow, &ff_full[stage], bx * TW, ty * TH, b * 2);
-                    tma_load_3d(dst + 2 * NPIX, &map_filt, &ff_full[stage], bx * TW, ty * TH, b * 16);
-                }
-            }
-            if (i == 0) continue;
-            // ---- image stage of tile j = i - 1 (its flow was requested one iteration ago) ----
-            const int j = i - 1, sj = j % S;
-            int b, bx, ty, sid;
-            decode((int)t_begin + j, b, bx, ty, sid);
-            mbar_wait_guarded(&ff_full[sj], (uint32_t)((j / S) & 1));
-            const float *fl = s_ff + sj * FF_FLOATS;
-            int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
-#pragma unroll
-            for (int k = 0; k < NPIX / 32; ++k) {
-                const int sp = lane + 32 * k;
-                const int w_i = bx * TW + (sp % TW), h_i = ty * TH + (sp / TW);
-                if (w_i < W && h_i < H) {
-                    const FiPix p = fi_pixel(w_i, h_i, fl[sp], fl[NPIX + sp], W, H, 4);
-                    if (p.in_range) {
-                        xmin = min(xmin, max(p.L, 0));
-                        xmax = max(xmax, min(p.L + 3, W - 1));
-                        ymin = min(ymin, max(p.T, 0));
-                        ymax = max(ymax, min(p.T + 3, H - 1));
+                    const int sf = f_t % SF;
+                    if (f_ty < tiles_y) {
+                        mbar_arrive_expect_tx(&filt_full[sf], FILT_BYTES);
+                        tma_load_3d(s_filt + sf * FILT_FLOATS, &map_filt, &filt_full[sf], f_bx * TW, f_ty * TH, f_b * 16);
+                    } else {
+                        mbar_arrive(&filt_full[sf]);   // null slot
                     }
                 }
+                ++f_t;
             }
+        };
+        // wait for a barrier phase while keeping the filter stream going; traps instead of hanging on a protocol error
+        auto wait_pumping = [&](uint64_t *bar, uint32_t parity) {
+            for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 400u); ++spins) {
+                pump_filters();
+                if (spins > (1u << 24)) __trap();
+            }
+        };
+
+        int xorg = 0, base = 0, hi = 0;   // window state: rows [max(base, hi - RROWS), hi) are resident
+        int b = 0, bx = 0, ty = 0, left = 0, item_no = -1;
+        for (int t = 0; t < n; ++t) {
+            bool new_item = false;
+            if (left == 0) { ++item_no; decode_item(item_no, b, bx, ty); left = segt; new_item = true; }
+            else ++ty;
+            --left;
+            const int sb = t % NB;
+            pump_filters();
+            // ---- image window of tile t, as soon as the compute warps have folded its bounding box ----
+            wait_pumping(&bbox_done[sb], (uint32_t)((t / NB) & 1));
+            const Box bb = s_box[sb];
+            __syncwarp();
+            if (lane == 0) s_box[sb] = Box{INT_MAX, INT_MIN, INT_MAX, INT_MIN};   // ready for tile t + NB
+
+            int mode = MODE_NONE, my_ymin = INT_MAX;
+            int load_lo = 0, load_hi = -1;
+            if (bb.xmax >= bb.xmin) {
+                const int width = bb.xmax - bb.xmin + 1, slack = WB - width;
+                if (bb.ymax - bb.ymin + 1 > RROWS || slack < 7) {
+                    mode = MODE_GLOBAL;   // the tile's box does not fit the window at all
+                } else {
+                    mode = MODE_SMEM;
+                    const bool rebase = new_item || bb.xmin < xorg || bb.xmax >= xorg + WB || bb.ymin < max(base, hi - RROWS);
+                    // bbox_done(t) means every compute warp has started tile t - LEAD: older tiles are consumed.  (Only
+                    // these last LEAD tiles may be waited on: their tile_done phase is the barrier's current one.)
+                    int oldest = max(0, t - LEAD);
+                    if (rebase) {
+                        // everything in flight may still read the window: drain, then restart it around this tile
+                        for (; oldest < t; ++oldest) wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1));
+                        xorg = (bb.xmin - (slack >= 14 ? slack / 2 : 0)) & ~7;   // sector-aligned, box centred when it can be
+                        base = hi = bb.ymin;
+                    }
+                    if (bb.ymin > hi) base = hi = bb.ymin;   // jumped ahead: nothing older is needed any more
+                    // loading row y reuses the slot of row y - RROWS: every tile still in flight must be past it
+                    for (;;) {
+                        int need_lo = bb.ymin;
+                        for (int q = oldest; q < t; ++q) need_lo = min(need_lo, s_ymin[q % NB]);
+                        if (bb.ymax - need_lo + 1 <= RROWS) break;
+                        wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1));   // oldest < t here
+                        ++oldest;
+                    }
+                    load_lo = max(hi, bb.ymin);
+                    load_hi = bb.ymax;
+                    hi = max(hi, bb.ymax + 1);
+                    my_ymin = bb.ymin;
+                }
+            }
+            if (lane == 0) {
+                s_ymin[sb] = my_ymin;
+                s_meta[sb].mode = mode;
+                s_meta[sb].xorg = xorg;
+                const int nrows = max(load_hi - load_lo + 1, 0);
+                mbar_arrive_expect_tx(&img_full[sb], (uint32_t)nrows * ROWF * (uint32_t)sizeof(float));   // release: publishes the descriptor
+                int slot = load_lo % RROWS;
+                for (int y = load_lo; y <= load_hi; ++y) {
+                    tma_load_4d(s_ring + slot * ROWF, &map_img, &img_full[sb], xorg, y, 0, b);
+                    slot = slot + 1 == RROWS ? 0 : slot + 1;
+                }
+            }
+            __syncwarp();
+        }
+        while (f_t < n) {   // filter planes of the last tiles whose ring slots were still busy
+            if (f_t >= SF) mbar_wait_sleepy(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1));
+            pump_filters();
+        }
+    } else {
+        // ================================ compute warps ================================
+        const int tx = tid % TW, tyy = tid / TW;   // position inside the tile
+        const unsigned tile_step = (unsigned)(TH * W);
+
+        auto start_item = [&](Cursor &c) {
+            if (c.item_no >= my_items) { c.left = INT_MAX; c.b = 0; c.w_i = 0; c.h_i = INT_MAX / 2; c.pix = 0; return; }
+            int bx, ty0;
+            decode_item(c.item_no, c.b, bx, ty0);
+            c.left = segt;
+            c.w_i = bx * TW + tx;
+            c.h_i = ty0 * TH + tyy;   // rows past the frame (ragged last segment) are >= H by construction
+            c.pix = (unsigned)(c.h_i * W + c.w_i);
+        };
+        auto advance = [&](Cursor &c) {
+            if (--c.left == 0) { ++c.item_no; start_item(c); }
+            else { c.h_i += TH; c.pix += tile_step; }
+        };
+        auto has_pixel = [&](const Cursor &c) { return c.w_i < W && c.h_i < H; };
+
+        // three cursors over the same sequence: the tile being computed, the tile whose box is folded (LEAD ahead)
+        // and the tile whose flow is requested (LEAD + 1 ahead)
+        Cursor cur{0, 0, 0, 0, 0, 0};
+        start_item(cur);
+        Cursor fold = cur, req = cur;
+
+        auto request_flow = [&](const Cursor &c, float &fx, float &fy) {
+            fx = 0.0f; fy = 0.0f;
+            if (has_pixel(c)) {
+                const float *f = in2 + (size_t)c.b * 2 * HW + c.pix;
+                fx = ld_stream(f);
+                fy = ld_stream(f + HW);
+            }
+        };
+        // Turns the flow of the cursor's pixel into (x2, y2) -- x2 = -1 marks "out of range" (:2735-2736), which is
+        // all the tile computation needs later -- and folds the clamped gather window into the slot's bounding box.
+        auto fold_box = [&](const Cursor &c, int slot, float &fx_x2, float &fy_y2) {
+            int xmin = INT_MAX, xmax = INT_MIN, ymin = INT_MAX, ymax = INT_MIN;
+            float x2 = -1.0f, y2 = 0.0f;
+            if (has_pixel(c)) {
+                const FiPix p = fi_pixel(c.w_i, c.h_i, fx_x2, fy_y2, W, H, 4);
+                if (p.in_range) {
+                    x2 = p.x2; y2 = p.y2;
+                    xmin = max(p.L, 0); xmax = min(p.L + 3, W - 1);
+                    ymin = max(p.T, 0); ymax = min(p.T + 3, H - 1);
+                }
+            }
+            fx_x2 = x2; fy_y2 = y2;
+            if (slot >= n) return;
             xmin = __reduce_min_sync(0xffffffffu, xmin);
             xmax = __reduce_max_sync(0xffffffffu, xmax);
             ymin = __reduce_min_sync(0xffffffffu, ymin);
             ymax = __reduce_max_sync(0xffffffffu, ymax);
-
-            int mode = MODE_NONE, my_cmin = INT_MAX;
-            uint32_t bytes = 0;
-            int load_lo = 0, load_hi = -1;
-            if (xmax >= xmin) {
-                const int cmin = ymin >> 2, cmax = ymax >> 2;
-                const int width = xmax - xmin + 1, slack = WB - width;
-                if (cmax - cmin + 1 > RCH || slack < 7) {
-                    mode = MODE_GLOBAL;   // the tile's box does not fit the window at all
-                } else {
-                    mode = MODE_SMEM;
-                    const bool rebase = sid != cur_strip || xmin < xorg || xmax >= xorg + WB || cmin < max(base, hi - RCH);
-                    int oldest = max(0, j - S + 1);   // tiles before this one are known to be consumed
-                    if (rebase) {
-                        // everything in flight may still read the window: drain, then restart it around this tile
-                        for (; oldest < j; ++oldest) mbar_wait_guarded(&ff_empty[oldest % S], (uint32_t)((oldest / S) & 1));
-                        cur_strip = sid;
-                        xorg = (xmin - (slack >= 14 ? slack / 2 : 0)) & ~7;   // sector-aligned, box centred when it can be
-                        base = hi = cmin;
-                    }
-                    if (cmin > hi) base = hi = cmin;   // jumped ahead: nothing older is needed any more
-                    // loading chunk c reuses the slot of chunk c - RCH: every tile still in flight must be past it
-                    for (;;) {
-                        int need_lo = cmin;
-                        for (int q = oldest; q < j; ++q) need_lo = min(need_lo, s_cmin[q % S]);
-                        if (cmax - need_lo + 1 <= RCH) break;
-                        mbar_wait_guarded(&ff_empty[oldest % S], (uint32_t)((oldest / S) & 1));   // oldest < j here
-                        ++oldest;
-                    }
-                    load_lo = max(hi, cmin);
-                    load_hi = cmax;
-                    if (load_hi >= load_lo) bytes = (uint32_t)(load_hi - load_lo + 1) * chunk_floats<CG>() * sizeof(float);
-                    hi = max(hi, cmax + 1);
-                    my_cmin = cmin;
-                }
-            }
             if (lane == 0) {
-                s_cmin[sj] = my_cmin;
-                s_meta[sj].mode = mode;
-                s_meta[sj].xorg = xorg;
-                mbar_arrive_expect_tx(&img_full[sj], bytes);   // release: publishes the meta words as well
-                for (int c = load_lo; c <= load_hi; ++c)
-                    tma_load_4d(s_ring + (c % RCH) * chunk_floats<CG>(), &map_img, &img_full[sj], xorg, c * CROWS, 0, b);
+                Box *bx_ = &s_box[slot % NB];
+                if (xmax >= xmin) {
+                    atomicMin(&bx_->xmin, xmin); atomicMax(&bx_->xmax, xmax);
+                    atomicMin(&bx_->ymin, ymin); atomicMax(&bx_->ymax, ymax);
+                }
+                mbar_arrive(&bbox_done[slot % NB]);   // release: the atomics above are visible to the producer
             }
-            __syncwarp();
-        }
-    } else {
-        // ================================ compute warps ================================
-        const int sp = tid;                       // position inside the tile
-        const int tx = sp % TW, tyy = sp / TW;
-        for (int j = 0; j < n; ++j) {
-            const int sj = j % S;
-            const uint32_t ph = (uint32_t)((j / S) & 1);
-            int b, bx, ty, sid;
-            decode((int)t_begin + j, b, bx, ty, sid);
-            const int w_i = bx * TW + tx, h_i = ty * TH + tyy;
-            const size_t pix = (size_t)h_i * W + w_i;
-            const float *img = in1 + (size_t)b * CG * HW;
-            float *o = out + (size_t)b * CG * HW + pix;
-            const float *ff = s_ff + sj * FF_FLOATS;
+        };
 
-            mbar_wait_guarded(&ff_full[sj], ph);
-            mbar_wait_guarded(&img_full[sj], ph);
-            const int mode = s_meta[sj].mode, xorg = s_meta[sj].xorg;
-
-            if (w_i < W && h_i < H) {
-                const FiPix p = fi_pixel(w_i, h_i, ff[sp], ff[NPIX + sp], W, H, 4);
-                if (!p.in_range) {   // :2814-2819 copies input1
+        // prologue: (x2, y2) and boxes of the first LEAD slots, and the flow request for slot LEAD in flight
+        float qx[LEAD + 1], qy[LEAD + 1], nx, ny;
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, __ldg(img + (size_t)c * HW + pix));
+        for (int k = 0; k < LEAD; ++k) {
+            request_flow(req, qx[k], qy[k]);
+            advance(req);
+        }
+        request_flow(req, nx, ny);
+        advance(req);
+#pragma unroll
+        for (int k = 0; k < LEAD; ++k) {
+            fold_box(fold, k, qx[k], qy[k]);
+            advance(fold);
+        }
+
+        for (int j = 0; j < n; ++j) {
+            // box of slot j + LEAD from the flow requested one tile ago; then request the flow of slot j + LEAD + 1
+            qx[LEAD] = nx; qy[LEAD] = ny;
+            fold_box(fold, j + LEAD, qx[LEAD], qy[LEAD]);
+            advance(fold);
+            request_flow(req, nx, ny);
+            advance(req);
+
+            const int sf = j % SF, sb = j % NB;
+            const float *ft = s_filt + sf * FILT_FLOATS + tid;
+
+            mbar_wait_sleepy(&img_full[sb], (uint32_t)((j / NB) & 1));
+            const int mode = s_meta[sb].mode, xorg = s_meta[sb].xorg;
+            mbar_wait_sleepy(&filt_full[sf], (uint32_t)((j / SF) & 1));
+
+            if (has_pixel(cur)) {
+                float *o = out + (size_t)cur.b * CG * HW + cur.pix;
+                const float x2 = qx[0], y2 = qy[0];
+                if (x2 < 0.0f) {   // out of range: :2814-2819 copies input1
+                    const float *img = in1 + (size_t)cur.b * CG * HW + cur.pix;
+#pragma unroll
+                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, __ldg(img + (size_t)c * HW));
                 } else {
+                    const int ix = (int)x2, iy = (int)y2;
+                    const int L = ix - 1, T = iy - 1;                       // window origin for F = 4 (:2745-2748)
+                    const float alpha = __fsub_rn(x2, (float)ix), beta = __fsub_rn(y2, (float)iy);
                     float w[16];
 #pragma unroll
-                    for (int k = 0; k < 16; ++k) w[k] = ff[(2 + k) * NPIX + sp];
-                    const float qTL = (1 - p.alpha) * (1 - p.beta), qTR = p.alpha * (1 - p.beta);
-                    const float qBL = (1 - p.alpha) * p.beta, qBR = p.alpha * p.beta;
+                    for (int k = 0; k < 16; ++k) w[k] = ft[k * NPIX];
+                    const float qTL = (1 - alpha) * (1 - beta), qTR = alpha * (1 - beta);
+                    const float qBL = (1 - alpha) * beta, qBR = alpha * beta;
                     float res[CG];
                     if (mode == MODE_SMEM) {
-                        int rb[4], co[4];
+                        int off[4], co[4];
+                        if (L >= 0 && T >= 0 && L + 3 < W && T + 3 < H) {
+                            // interior window: rows T..T+3 are consecutive ring slots (mod RROWS), columns are contiguous
+                            const int r0 = (int)((unsigned)T % RROWS);
+                            const int o0 = r0 * ROWF + (L - xorg);
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int yy = clampi(p.T + r, 0, H - 1);   // :2751
-                            rb[r] = (int)((unsigned)(yy >> 2) % RCH) * chunk_floats<CG>() + (yy & 3) * WB;
-                        }
-                        if (p.L >= 0 && p.L + 3 < W) {
-                            co[0] = p.L - xorg; co[1] = co[2] = co[3] = 0;
+                            for (int r = 0; r < 4; ++r) off[r] = o0 + r * ROWF - (r0 + r >= RROWS ? RROWS * ROWF : 0);
+                            co[0] = co[1] = co[2] = co[3] = 0;
 #pragma unroll
                             for (int c = 0; c < CG; ++c)
-                                res[c] = window_from_smem<true>(s_ring + c * (CROWS * WB), rb, co, w, qTL, qTR, qBL, qBR);
+                                res[c] = window_from_smem<true>(s_ring + c * WB, off, co, w, qTL, qTR, qBL, qBR);
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 4; ++i) co[i] = clampi(p.L + i, 0, W - 1) - xorg;   // :2753
+                            for (int r = 0; r < 4; ++r) {
+                                off[r] = (int)((unsigned)clampi(T + r, 0, H - 1) % RROWS) * ROWF - xorg;   // :2751
+                                co[r] = clampi(L + r, 0, W - 1);                                           // :2753
+                            }
 #pragma unroll
                             for (int c = 0; c < CG; ++c)
-                                res[c] = window_from_smem<false>(s_ring + c * (CROWS * WB), rb, co, w, qTL, qTR, qBL, qBR);
+                                res[c] = window_from_smem<false>(s_ring + c * WB, off, co, w, qTL, qTR, qBL, qBR);
                         }
                     } else {
                         // the tile's windows do not fit the rolling window: clamped gathers from global memory
+                        const float *img = in1 + (size_t)cur.b * CG * HW;
                         int ro[4], co[4];
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
-                            ro[r] = clampi(p.T + r, 0, H - 1) * W;
-                            co[r] = clampi(p.L + r, 0, W - 1);
+                            ro[r] = clampi(T + r, 0, H - 1) * W;
+                            co[r] = clampi(L + r, 0, W - 1);
                         }
 #pragma unroll
                         for (int c = 0; c < CG; ++c) {
@@ -273,26 +392,41 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_flow, const 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&ff_empty[sj]);   // this warp is done with stage sj and with the window rows of tile j
+            if (lane == 0) mbar_arrive(&tile_done[sf]);   // this warp is done with filter stage sf and the window rows of tile j
+            advance(cur);
+#pragma unroll
+            for (int k = 0; k < LEAD; ++k) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; }
         }
     }
 }
 
 template <int CG>
-static int launch(const CUtensorMap &mflow, const CUtensorMap &mfilt, const float *in1, float *out, int B, int H, int W,
+static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, float *out, int B, int H, int W,
                   cudaStream_t s)
 {
     CUtensorMap mimg;
-    if (!encode_tensor_map_4d(&mimg, in1, W, H, CG, B, WB, CROWS, CG)) return -1;
+    if (!encode_tensor_map_4d(&mimg, in1, W, H, CG, B, WB, 1, CG)) return -1;
+    if ((long long)CG * H * W >= (1ll << 31)) return -1;   // 32-bit pixel offsets inside one batch item
     const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
-    const long long total = (long long)tiles_x * tiles_y * B;
-    if (total >= (1ll << 31)) return -1;
+    if ((long long)tiles_x * tiles_y * B >= (1ll << 28)) return -1;
+    // Split every strip into `nseg` segments so that the items fill whole rounds of one CTA per SM.  Cost model:
+    // rounds x (tiles per segment + ~3 tiles' worth of window refill at each segment start).
+    const int sms = sm_count();
+    int best_nseg = 1;
+    long long best_cost = LLONG_MAX;
+    for (int ns = 1; ns <= std::min(tiles_y, 64); ++ns) {
+        const long long items = (long long)B * tiles_x * ns;
+        const long long rounds = (items + sms - 1) / sms;
+        const long long cost = rounds * ((tiles_y + ns - 1) / ns + 3);
+        if (cost < best_cost) { best_cost = cost; best_nseg = ns; }
+    }
+    const int nseg = best_nseg, segt = (tiles_y + nseg - 1) / nseg;
+    const long long items = (long long)B * tiles_x * nseg;
     auto kernel = fi_forward_ori_strip_kernel<CG>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<CG>());
-    // two CTAs per SM; never more CTAs than tiles, and keep runs long enough that the window pays off
-    const int nblk = (int)std::max<long long>(1, std::min<long long>((long long)sm_count() * 2, total / 8 + 1));
-    kernel<<<nblk, NTHREADS, smem_bytes<CG>(), s>>>(mflow, mfilt, mimg, in1, out, H, W, tiles_x, tiles_y, (int)total,
-                                                   FastDiv((unsigned)tiles_y), FastDiv((unsigned)tiles_x));
+    const int nblk = (int)std::min<long long>(sms, items);
+    kernel<<<nblk, NTHREADS, smem_bytes<CG>(), s>>>(mfilt, mimg, in1, in2, out, H, W, tiles_x, tiles_y, nseg, segt, (int)items,
+                                                   FastDiv((unsigned)tiles_x), FastDiv((unsigned)nseg));
     note_launch();
     return check_launch("filterinterpolation forward (strip)");
 }
@@ -304,17 +438,15 @@ int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, f
                          int B, int C, int H, int W, cudaStream_t s)
 {
     using namespace strip;
-    if (C < 1 || C > 4 || W % 4 != 0 || W < WB || H < CROWS) return -1;
-    if (!aligned16(in1) || !aligned16(in2) || !aligned16(in3)) return -1;
-    CUtensorMap mflow, mfilt;
-    if (!encode_tensor_map_3d(&mflow, in2, W, H, (uint64_t)B * 2, TW, TH, 2) ||
-        !encode_tensor_map_3d(&mfilt, in3, W, H, (uint64_t)B * 16, TW, TH, 16))
-        return -1;
+    if (C < 1 || C > 4 || W % 4 != 0 || W < WB) return -1;
+    if (!aligned16(in1) || !aligned16(in3)) return -1;
+    CUtensorMap mfilt;
+    if (!encode_tensor_map_3d(&mfilt, in3, W, H, (uint64_t)B * 16, TW, TH, 16)) return -1;
     switch (C) {
-    case 1: return launch<1>(mflow, mfilt, in1, out, B, H, W, s);
-    case 2: return launch<2>(mflow, mfilt, in1, out, B, H, W, s);
-    case 3: return launch<3>(mflow, mfilt, in1, out, B, H, W, s);
-    default: return launch<4>(mflow, mfilt, in1, out, B, H, W, s);
+    case 1: return launch<1>(mfilt, in1, in2, out, B, H, W, s);
+    case 2: return launch<2>(mfilt, in1, in2, out, B, H, W, s);
+    case 3: return launch<3>(mfilt, in1, in2, out, B, H, W, s);
+    default: return launch<4>(mfilt, in1, in2, out, B, H, W, s);
     }
 }
 
