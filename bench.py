@@ -18,8 +18,11 @@ collective on the data path; NCCL only reduces the timing / unit counts.
            of every input and the device -> host read of the interpolated frames are inside the timed region.
 `roofline` FilterInterpolation "_ori" forward kernel: algorithmic bytes (96 B/pixel) / its
            average duration measured with CUDA events inside the timed region, against the measured HBM copy peak.
-`cpu_baseline` / `--impl reference`: the float64 CPU oracle (a port; the reference has no CPU implementation
-           and its CUDA extensions do not build in this image) on the host cores, on a bounded sample (one pair).
+`cpu_baseline`  the float64 CPU oracle (a port: the reference has no CPU implementation of this path) on the
+           host cores, on a bounded sample (one pair).
+`--impl reference`  the reference's OWN CUDA kernels -- oracle/_ref/*.so, the unmodified reference sources built
+           for sm_100a by oracle/build_ref.py -- through the same step, called as the reference's Python layers call
+           them (caller zero-fills every output).  If those modules or a GPU are absent: the CPU oracle port.
 """
 from __future__ import annotations
 
@@ -293,7 +296,7 @@ def bench_ours(args):
                    "pairs_per_gpu": PAIRS_PER_GPU, "frame": "1920x1080 padded to 1152x1984",
                    "parallelism": f"pair-sharded x{world}, no data-path collective",
                    "l2": "inputs_exceed_l2 (one step streams > 4 GB, L2 is 126 MB)"},
-        "roofline": {"bound": "hbm", "kernel": "fi_forward_ori_kernel<4>", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "fi_forward_ori_strip_kernel<3>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": FI_BYTES_PER_PIXEL * n_px,
                      "avg_launch_ms": fi_avg_ms},
@@ -349,10 +352,112 @@ def cpu_reference_arm(steps=1, warmup=0):
             "seconds": dt, "steps": steps}
 
 
+def _reference_modules():
+    """The reference's own extension modules (oracle/_ref), or None when they / a GPU are not available."""
+    try:
+        import torch
+        if not torch.cuda.is_available():
+            return None
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("vfidkr_build_ref", str(ROOT / "oracle" / "build_ref.py"))
+        build_ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(build_ref)
+        return {n: build_ref.load(n) for n in ("correlation_cuda", "depthflowprojection_cuda", "filterinterpolation_cuda")}
+    except Exception as e:   # missing .so, ABI mismatch, ...
+        print(f"[bench] reference CUDA modules unavailable ({e}); using the CPU oracle port", file=sys.stderr)
+        return None
+
+
+def bench_reference_cuda(args, mods):
+    """The same step on the reference's unmodified CUDA kernels, driven the way its Python layers drive them."""
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    corr_m, dproj_m, fi_m = mods["correlation_cuda"], mods["depthflowprojection_cuda"], mods["filterinterpolation_cuda"]
+    B, H, W = PAIRS_PER_GPU, PAD_H, PAD_W
+
+    def step(d):
+        for lvl in range(len(PWC_LEVELS)):
+            a, b = d[f"feat{lvl}_0"], d[f"feat{lvl}_1"]
+            for x, y in ((a, b), (b, a)):   # correlation.py:24-31
+                rb1, rb2, o = x.new_empty(0), y.new_empty(0), x.new_empty(0)
+                corr_m.forward(x, y, rb1, rb2, o, 4, 1, 4, 1, 1, 1)
+        for k in (0, 1):                    # DepthFlowProjectionLayer.py:33-35
+            cnt = torch.zeros(B, 1, H, W, device=device)
+            po = torch.zeros(B, 2, H, W, device=device)
+            dproj_m.DepthFlowProjectionLayer_gpu_forward(d[f"rawflow{k}"], d["depth"], cnt, po, 1)
+        warped = []
+        for k in (0, 1):                    # FilterInterpolationLayer.py:34-35
+            out = torch.zeros_like(d[f"frame{k}"])
+            fi_m.FilterInterpolationLayer_gpu_forward_ori(d[f"frame{k}"], d[f"flow{k}"], d[f"filter{k}"], out)
+            warped.append(out)
+        return warped
+
+    steps, warm = max(1, args.steps), max(args.warmup, 3)
+    d = build_inputs(torch, device, seed=1004 + rank)
+    with torch.no_grad():
+        for _ in range(warm):
+            step(d)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(steps):
+            step(d)
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1)
+        value = steps * PAIRS_PER_GPU * FRAME_PIXELS / (ms * 1e-3) / 1e6
+        del d
+        torch.cuda.empty_cache()
+        # end to end from pinned host buffers, as in our arm
+        hd = build_inputs(torch, device, seed=2004 + rank, pinned_host=True)
+        h2d = sum(t.numel() * 4 for t in hd.values())
+        host_out = torch.empty((2, PAIRS_PER_GPU, 3, PAD_H, PAD_W), dtype=torch.float32, pin_memory=True)
+        e_steps = min(steps, args.e2e_steps)
+
+        def e2e_step():
+            dd = {k: t.to(device, non_blocking=True) for k, t in hd.items()}
+            warped = step(dd)
+            host_out[0].copy_(warped[0], non_blocking=True)
+            host_out[1].copy_(warped[1], non_blocking=True)
+        e2e_step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(e_steps):
+            e2e_step()
+        e1.record()
+        torch.cuda.synchronize()
+        e2e_value = e_steps * PAIRS_PER_GPU * FRAME_PIXELS / (e0.elapsed_time(e1) * 1e-3) / 1e6
+    line = {
+        "impl": "reference", "metric": "interpolated Mpixel/s (1080p)", "value": value, "unit": "Mpixel/s",
+        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "1080p_pair_inference_b8: 10x correlation fwd + 2x DepthFlowProjection fwd (fillhole) + "
+                               "2x FilterInterpolation_ori fwd (C=3,F=4)", "pairs_per_gpu": PAIRS_PER_GPU,
+                   "frame": "1920x1080 padded to 1152x1984",
+                   "note": "reference = its own CUDA kernels, unmodified sources compiled for sm_100a (oracle/_ref), on the same "
+                           "GPU; it has no CPU implementation of this path. Rank 0 only."},
+        "reference_kind": "reference CUDA extensions (oracle/_ref)",
+        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": host_out.numel() * 4, "steps": e_steps},
+        "gpu_launches": 0,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_arm(steps=3, warmup=1)
+    print(json.dumps(line), flush=True)
+
+
 def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    mods = None if args.reference_cpu else _reference_modules()
+    if mods is not None:
+        return bench_reference_cuda(args, mods)
     res = cpu_reference_arm(steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
     world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
@@ -362,8 +467,9 @@ def bench_reference(args):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "1080p_pair_inference_b8 (bounded sample: 1 pair per step)", "pairs_per_gpu": PAIRS_PER_GPU,
                    "frame": "1920x1080 padded to 1152x1984",
-                   "note": "the reference has no CPU implementation of this path and its CUDA extensions do not build "
-                           "here; this arm is the float64 CPU oracle port on the host cores"},
+                   "note": "the reference has no CPU implementation of this path and its CUDA modules (oracle/_ref) were not "
+                           "available; this arm is the float64 CPU oracle port on the host cores"},
+        "reference_kind": "CPU oracle port",
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -408,6 +514,10 @@ def op_table(torch, V, device, path):
     with torch.no_grad():
         add("FI_ori_fwd_C3", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl, ft)), 96, px)
         add("FI_ori_fwd_C3_iidflow", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl_iid, ft)), 96, px)
+        yy, xx = torch.meshgrid(torch.linspace(0, 6, H, device=device), torch.linspace(0, 6, W, device=device), indexing="ij")
+        fl_smooth = torch.stack([6 * torch.sin(xx) + 3 * torch.cos(yy), 5 * torch.cos(0.7 * xx) - 3 * torch.sin(yy)], 0)[None].repeat(B, 1, 1, 1).contiguous()
+        add("FI_ori_fwd_C3_smoothflow", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl_smooth, ft)), 96, px)
+        del fl_smooth, yy, xx
         add("FI_dkr_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDKR.apply(I, fl, ft, off)), 224, px)
         add("FI_deforconv_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDeforConv.apply(I, fl, ft, off)), 224, px)
         add("FI_nofilter_fwd_C3", timeit(lambda: V.FilterInterpolationLayerNoFilterWithDeforConv.apply(I, fl, off)), 160, px)
@@ -466,6 +576,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=5, help="cap on the (PCIe-bound) end-to-end steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reference-cpu", action="store_true", help="--impl reference: force the CPU oracle port")
     ap.add_argument("--table", default=None, help="also write the per-operator timing table (JSON lines) here")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -33,10 +33,14 @@ __device__ __forceinline__ Bilin bilin(int w_i, int h_i, float fx, float fy, int
     return r;
 }
 
-__global__ void __launch_bounds__(BX *BY)
+// CT > 0: compile-time channel count -- the 4 * CT gathers of a pixel are independent and all in flight together;
+// CT == 0: run-time C, one channel at a time (keeps the register count low enough for full occupancy either way).
+template <int CT>
+__global__ void __launch_bounds__(BX *BY, 8)
 interp_forward_kernel(const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
-                      int C, int H, int W)
+                      int Crt, int H, int W)
 {
+    const int C = CT > 0 ? CT : Crt;
     const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
     if (w_i >= W || h_i >= H) return;
     const int b = blockIdx.z;
@@ -52,11 +56,22 @@ interp_forward_kernel(const float *__restrict__ in1, const float *__restrict__ i
     }
     const float wTL = (1 - g.alpha) * (1 - g.beta), wTR = g.alpha * (1 - g.beta);
     const float wBL = (1 - g.alpha) * g.beta, wBR = g.alpha * g.beta;
-#pragma unroll 4
-    for (int c = 0; c < C; ++c) {
-        const float *pl = img + (size_t)c * HW;
-        st_stream(o + (size_t)c * HW,
-                  wTL * __ldg(pl + g.aTL) + wTR * __ldg(pl + g.aTR) + wBL * __ldg(pl + g.aBL) + wBR * __ldg(pl + g.aBR));  // :85-86
+    if (CT > 0) {
+        float r[CT > 0 ? CT : 1];
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+            const float *pl = img + (size_t)c * HW;
+            r[c] = wTL * __ldg(pl + g.aTL) + wTR * __ldg(pl + g.aTR) + wBL * __ldg(pl + g.aBL) + wBR * __ldg(pl + g.aBR);   // :85-86
+        }
+#pragma unroll
+        for (int c = 0; c < CT; ++c) st_stream(o + (size_t)c * HW, r[c]);
+    } else {
+#pragma unroll 1
+        for (int c = 0; c < C; ++c) {
+            const float *pl = img + (size_t)c * HW;
+            st_stream(o + (size_t)c * HW,
+                      wTL * __ldg(pl + g.aTL) + wTR * __ldg(pl + g.aTR) + wBL * __ldg(pl + g.aBL) + wBR * __ldg(pl + g.aBR));
+        }
     }
 }
 
@@ -120,7 +135,8 @@ VFIDKR_API int vfidkr_interpolation_forward(const float *input1, const float *in
     if (require_c3 && C != 3) return VFIDKR_ERR_ARG;   // interpolation_cuda.cc:19
     if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
     dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
-    interp_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(input1, input2, output, C, H, W);
+    if (C == 3) interp_forward_kernel<3><<<grid, block, 0, (cudaStream_t)stream>>>(input1, input2, output, C, H, W);
+    else        interp_forward_kernel<0><<<grid, block, 0, (cudaStream_t)stream>>>(input1, input2, output, C, H, W);
     note_launch();
     return check_launch("interpolation forward");
 }

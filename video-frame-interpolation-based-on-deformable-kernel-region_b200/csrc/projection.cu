@@ -5,9 +5,13 @@
 // my_package/DepthFlowProjection/depthflowprojection_cuda_kernel.cu:29-341.  One templated kernel
 // family serves both (DEPTH = false -> weight 1).  Atomics are kept exactly where the reference
 // splats (the four corners of (x+fx, y+fy), three planes each); what changes:
-//   * the 2 x 2 splat is split into an atomic vertical half (rows T, Bm at column L: 6 REDs per pixel
-//     instead of 12) and a dense, atomic-free horizontal half fused with the averaging pass -- same sums,
-//     half the atomics, which is what bounds this op (the L2 retires ~1 fp32 RED per clock per slice);
+//   * every source pixel adds the SAME triple (-d*fx, -d*fy, d) to the 2 x 2 block {T, Bm} x {L, R}, so the splat
+//     is split: ONE 128-bit vector RED per pixel (REDG.E.ADD.F32x4) deposits the triple at the block's top-left
+//     cell of an interleaved scratch image, and a dense, atomic-free 2 x 2 box pass (fused with the averaging)
+//     spreads it -- same sums, 1 atomic instead of 12, which is what bounds this op (the L2 retires roughly
+//     one RED request per clock per slice, whatever its width);
+//   * the scratch image (16 B per pixel) is stream-ordered memory from the device's default pool
+//     (cudaMallocAsync: no synchronisation, cached after the first call);
 //   * the accumulation planes are cleared by the library on the stream (no caller zero-fill);
 //   * the backward is a pure gather with register accumulation and a single store per output
 //     (the reference does eight / sixteen read-modify-writes of its own pixel).
@@ -37,16 +41,14 @@ __device__ __forceinline__ Corners corners(int w_i, int h_i, float fx, float fy,
 }
 
 // Splat, restructured.  Every in-range pixel adds the SAME triple (-d*fx, -d*fy, d) to the 2 x 2 block of
-// cells {T, Bm} x {L, R} (:75-88).  The L2 atomic units retire about one fp32 RED per clock per slice, so the
-// splat is bound by the NUMBER of atomics (12 per pixel in the reference).  Here only the left column of the
-// block is splatted -- rows T and Bm at column L, 6 atomics per pixel, 3 when the border clamp makes Bm == T --
-// and the right column is produced by the dense pass below:  A[y][x] = S[y][x] + S[y][x-1],
-// with the reference's border behaviour (R = min(L+1, W-1), so a pixel with L == W-1 hits column W-1 twice):
-//   A[y][W-1] = 2*S[y][W-1] + S[y][W-2].
+// cells {T, Bm} x {L, R} (:75-88).  Here the triple goes, with one vector RED, to cell (T, L) of the scratch image
+// S; the box pass below then forms, with the reference's border behaviour (R = min(L+1, W-1), Bm = min(T+1, H-1):
+// a block on the last column / row hits that column / row twice),
+//   A[y][x] = sum_{dy,dx in {0,1}} wy(y,dy) * wx(x,dx) * S[y-dy][x-dx],   w(.,1) = 1,  wx(x,0) = (x == W-1 ? 2 : 1), wy alike.
 template <bool DEPTH>
 __global__ void __launch_bounds__(BX *BY)
-projection_splat_kernel(const float *__restrict__ flow, const float *__restrict__ depth,
-                        float *__restrict__ count, float *__restrict__ out, int H, int W)
+projection_splat_kernel(const float *__restrict__ flow, const float *__restrict__ depth, float4 *__restrict__ S,
+                        int H, int W)
 {
     const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
     if (w_i >= W || h_i >= H) return;
@@ -58,49 +60,67 @@ projection_splat_kernel(const float *__restrict__ flow, const float *__restrict_
     if (!c.in_range) return;
     const float d = DEPTH ? ld_stream(depth + (size_t)b * HW + pix) : 1.0f;
     const float vx = DEPTH ? -d * fx : -fx, vy = DEPTH ? -d * fy : -fy;   // :75-88 / depth :77-92
-    float *ou = out + ((size_t)b * 2 + 0) * HW, *ov = ou + HW, *cn = count + (size_t)b * HW;
-    const size_t a0 = (size_t)c.T * W + c.L;
-    if (c.Bm == c.T) {   // bottom row clamped onto the top row: the cell is hit twice
-        red_add(ou + a0, 2.0f * vx);
-        red_add(ov + a0, 2.0f * vy);
-        red_add(cn + a0, 2.0f * d);
-    } else {
-        const size_t a1 = a0 + W;
-        red_add(ou + a0, vx); red_add(ou + a1, vx);
-        red_add(ov + a0, vy); red_add(ov + a1, vy);
-        red_add(cn + a0, d);  red_add(cn + a1, d);
-    }
+    atomicAdd(S + (size_t)b * HW + (size_t)c.T * W + c.L, make_float4(vx, vy, d, 0.0f));   // result unused -> REDG.F32x4
 }
 
-// Dense pass: completes the horizontal half of the 2 x 2 splat (see above) and averages (:128-135), in place.
-// One CTA owns whole rows and walks each row right to left in segments, so a cell is always read before the
-// thread that rewrites it runs: no scratch buffer is needed and there is no dependence between CTAs.
-constexpr int ROW_THREADS = 256;
+// Box pass + averaging (:128-135).  One warp owns a 32-column block of a row segment and walks it downwards,
+// carrying the horizontally summed previous row in registers: S is read once (plus one halo row per segment and
+// one halo column per block), count and output are written once, planar.
+constexpr int FIN_ROWS = 32, FIN_WARPS = 4, FIN_UNROLL = 4;
 
-__global__ void __launch_bounds__(ROW_THREADS)
-projection_finish_kernel(float *__restrict__ count, float *__restrict__ out, int H, int W, int rows_total)
+// raw loads of one row: this lane's cell and (lane 0 only) the cell left of the block
+__device__ __forceinline__ void load_row(const float4 *__restrict__ Srow, int x, int W, int lane, bool valid,
+                                         float4 &cur, float4 &edge)
 {
+    cur = make_float4(0.f, 0.f, 0.f, 0.f);
+    edge = cur;
+    if (valid) {
+        if (x < W) cur = __ldcs(Srow + x);
+        if (lane == 0 && x > 0 && x < W) edge = __ldg(Srow + x - 1);
+    }
+}
+// horizontal half of the box: wx(x,0) * S[x] + S[x-1]
+__device__ __forceinline__ float4 hsum_row(const float4 &cur, const float4 &edge, int x, int W, int lane)
+{
+    float4 left;
+    left.x = __shfl_up_sync(0xffffffffu, cur.x, 1);
+    left.y = __shfl_up_sync(0xffffffffu, cur.y, 1);
+    left.z = __shfl_up_sync(0xffffffffu, cur.z, 1);
+    if (lane == 0) left = edge;
+    const float w0 = (x == W - 1) ? 2.0f : 1.0f;
+    return make_float4(w0 * cur.x + left.x, w0 * cur.y + left.y, w0 * cur.z + left.z, 0.f);
+}
+
+__global__ void __launch_bounds__(32 * FIN_WARPS)
+projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count, float *__restrict__ out, int H, int W)
+{
+    const int lane = threadIdx.x, x = (blockIdx.x * FIN_WARPS + threadIdx.y) * 32 + lane;
+    if ((blockIdx.x * FIN_WARPS + threadIdx.y) * 32 >= W) return;   // whole warp outside
+    const int b = blockIdx.z, y0 = blockIdx.y * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
     const size_t HW = (size_t)H * W;
-    for (int row = blockIdx.x; row < rows_total; row += gridDim.x) {
-        const int b = row / H, y = row - b * H;
-        float *ou = out + ((size_t)b * 2 + 0) * HW + (size_t)y * W, *ov = ou + HW;
-        float *cn = count + (size_t)b * HW + (size_t)y * W;
-        const int nseg = (W + ROW_THREADS - 1) / ROW_THREADS;
-        for (int seg = nseg - 1; seg >= 0; --seg) {
-            const int x = seg * ROW_THREADS + (int)threadIdx.x;
-            float su = 0.f, sv = 0.f, sc = 0.f;
-            if (x < W) {
-                const float w0 = (x == W - 1) ? 2.0f : 1.0f;   // clamped right corner lands on column W-1 again
-                su = w0 * ou[x]; sv = w0 * ov[x]; sc = w0 * cn[x];
-                if (x > 0) { su += ou[x - 1]; sv += ov[x - 1]; sc += cn[x - 1]; }
-            }
-            __syncthreads();   // every read of this segment (and of the cell left of it) precedes the writes
-            if (x < W) {
-                cn[x] = sc;
+    const float4 *Sb = S + (size_t)b * HW;
+    float *ou = out + ((size_t)b * 2 + 0) * HW, *ov = ou + HW, *cn = count + (size_t)b * HW;
+    float4 c0, e0;
+    load_row(Sb + (size_t)max(y0 - 1, 0) * W, x, W, lane, y0 > 0, c0, e0);
+    float4 prev = hsum_row(c0, e0, x, W, lane);
+    for (int yb = y0; yb < y1; yb += FIN_UNROLL) {
+        float4 cur[FIN_UNROLL], edge[FIN_UNROLL];
+#pragma unroll
+        for (int k = 0; k < FIN_UNROLL; ++k)   // all loads of the group are in flight before the first is used
+            load_row(Sb + (size_t)min(yb + k, H - 1) * W, x, W, lane, yb + k < y1, cur[k], edge[k]);
+#pragma unroll
+        for (int k = 0; k < FIN_UNROLL; ++k) {
+            const int y = yb + k;
+            const float4 h = hsum_row(cur[k], edge[k], x, W, lane);
+            const float w0 = (y == H - 1) ? 2.0f : 1.0f;
+            float su = w0 * h.x + prev.x, sv = w0 * h.y + prev.y;
+            const float sc = w0 * h.z + prev.z;
+            prev = h;
+            if (y < y1 && x < W) {
                 if (sc > 0.0f) { su = su / sc; sv = sv / sc; }   // :130-134
-                ou[x] = su; ov[x] = sv;
+                const size_t a = (size_t)y * W + x;
+                st_stream(cn + a, sc); st_stream(ou + a, su); st_stream(ov + a, sv);
             }
-            // the next segment (to the left) only reads cells this segment did not write
         }
     }
 }
@@ -179,29 +199,49 @@ projection_backward_kernel(const float *__restrict__ flow, const float *__restri
     if (DEPTH) st_stream(gi2 + (size_t)b * HW + pix, sd);
 }
 
+// stream-ordered scratch from the device's default memory pool; the pool keeps the block cached between calls
+static int scratch_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    static thread_local int configured_for = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev != configured_for) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;   // never trim: the same few sizes come back every step
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        (void)cudaGetLastError();
+        configured_for = dev;
+    }
+    return set_error(cudaMallocAsync(p, bytes, s), "projection scratch (cudaMallocAsync)");
+}
+
 template <bool DEPTH>
 int projection_forward(const float *flow, const float *depth, float *count, float *out,
                        int B, int H, int W, int fillhole, cudaStream_t s)
 {
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !flow || !count || !out || (DEPTH && !depth)) return VFIDKR_ERR_ARG;
-    if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
+    if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
-    int e = set_error(cudaMemsetAsync(count, 0, sizeof(float) * B * HW, s), "clear count");
+    void *scratch = nullptr;
+    int e = scratch_alloc(&scratch, sizeof(float4) * B * HW, s);
     if (e) return e;
-    e = set_error(cudaMemsetAsync(out, 0, sizeof(float) * 2 * B * HW, s), "clear output");
-    if (e) return e;
-    dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
-    projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(flow, depth, count, out, H, W);
-    const long long rows_total = (long long)B * H;
-    if (rows_total >= (1ll << 31)) return VFIDKR_ERR_ARG;
-    const unsigned nb = (unsigned)std::min<long long>(rows_total, (long long)sm_count() * 8);
-    projection_finish_kernel<<<nb, ROW_THREADS, 0, s>>>(count, out, H, W, (int)rows_total);
-    note_launch(2);
-    if (fillhole) {
-        projection_fillhole_kernel<<<grid, block, 0, s>>>(count, out, H, W);
-        note_launch();
+    float4 *S = static_cast<float4 *>(scratch);
+    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * B * HW, s), "clear projection scratch");
+    if (!e) {
+        dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
+        projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(flow, depth, S, H, W);
+        dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), B);
+        projection_finish_kernel<<<fgrid, fblock, 0, s>>>(S, count, out, H, W);
+        note_launch(2);
+        if (fillhole) {
+            projection_fillhole_kernel<<<grid, block, 0, s>>>(count, out, H, W);
+            note_launch();
+        }
+        e = check_launch("flow projection forward");
     }
-    return check_launch("flow projection forward");
+    const int e2 = set_error(cudaFreeAsync(scratch, s), "projection scratch (cudaFreeAsync)");
+    return e ? e : e2;
 }
 
 template <bool DEPTH>
