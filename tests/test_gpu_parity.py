@@ -475,3 +475,38 @@ def test_fi_ori_strip_kernel_repeated_launches_are_deterministic(lib):
     first = lib.FilterInterpolationModule()(I, fl, ft).clone()
     for _ in range(5):
         assert torch.equal(lib.FilterInterpolationModule()(I, fl, ft), first)
+
+
+DKR_STRIP_CASES = [  # B, C, H, W, flow kind, offset amplitude
+    (2, 3, 131, 200, "stress", 0.45),        # ragged, out-of-range pixels
+    (1, 3, 96, 256, "smooth", 0.95),         # offsets up to the edge of the in-contract domain
+    (1, 3, 180, 192, "uniform_motion", 0.45),
+    (1, 3, 120, 224, "wild", 0.45),          # most tiles without a window (global path)
+    (1, 3, 64, 160, "gauss", 3.0),           # wild offsets: per-tap global fallback next to window taps
+    (1, 1, 40, 164, "gauss", 0.45),
+    (1, 4, 50, 196, "unit", 0.45),
+    (2, 2, 8, 320, "gauss", 1.5),
+]
+
+
+@pytest.mark.parametrize("variant", ["dkr", "deforconv", "nofilterwithdeforconv"])
+@pytest.mark.parametrize("B,C,H,W,fk,amp", DKR_STRIP_CASES)
+def test_fi_dkr_strip_kernel(lib, oracle, monkeypatch, variant, B, C, H, W, fk, amp):
+    """fi_strip_dkr.cu (bilinear samples from the rolling window, tap-row sub-stages) against the oracle and the
+    direct kernel; amplitudes > 1 mix window taps with the clamp-to-plane global fallback."""
+    r = U.rng(2300 + H + W + len(variant))
+    I = U.image(r, B, C, H, W)
+    fl = big_flow(r, B, H, W, fk) if fk in ("uniform_motion", "shear", "wild", "jump_back") else U.flow(r, B, H, W, fk)
+    ft, off = U.filt(r, B, 4, H, W, "uniform"), U.offsets(r, B, 4, H, W, amp)
+    args = (I, fl, off) if variant == "nofilterwithdeforconv" else (I, fl, ft, off)
+    run = lambda: lib.FilterInterpolationModule(variant)(*map(cu, args))
+    a = run()
+    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    b = run()
+    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    ref = oracle.fi_forward(variant, *args)
+    # an offset of exactly +-amp can land a sample on a pixel boundary where the two paths round the fraction
+    # identically (same fp32 index arithmetic), so both must match the oracle at the forward tolerance
+    U.assert_close(host(a), ref, U.RTOL_FWD, f"{variant} strip kernel vs oracle")
+    U.assert_close(host(b), ref, U.RTOL_FWD, f"{variant} direct kernel vs oracle")
+    assert U.max_err(host(a), host(b).astype(np.float64)) < 3e-6

@@ -28,34 +28,19 @@
 #include <algorithm>
 #include <climits>
 
-#include "common.cuh"
-#include "fi_common.cuh"
-#include "tma.cuh"
+#include "fi_strip_common.cuh"
 
 namespace vfidkr {
 namespace strip {
 
-constexpr int TW = 128, TH = 4, NPIX = TW * TH;    // tile = 512 pixels, one per compute thread
-constexpr int NCOMP_WARPS = NPIX / 32;             // 16 compute warps
-constexpr int NTHREADS = NPIX + 32;                // + 1 producer warp
-constexpr int LEAD = 3;                            // flow / bounding box / image window run this many tiles ahead
-constexpr int NB = 8;                              // ring of bounding boxes and tile descriptors (> LEAD)
-constexpr int WB = 160;                            // columns held by the rolling window (tile + 16 either side)
-constexpr int RROWS = 48;                          // rows held by the rolling window (a ring indexed by y % RROWS)
 constexpr int FILT_FLOATS = 16 * NPIX;
 constexpr uint32_t FILT_BYTES = FILT_FLOATS * sizeof(float);
-enum { MODE_NONE = 0, MODE_SMEM = 1, MODE_GLOBAL = 2 };
-
-template <int CG> __host__ __device__ constexpr int row_floats() { return CG * WB; }   // one window row: [C][WB]
 // filter pipeline depth: as deep as shared memory allows next to the window ring
 template <int CG> __host__ __device__ constexpr int stages() { return CG <= 3 ? 4 : 3; }
 template <int CG> __host__ __device__ constexpr size_t smem_bytes()
 {
     return (size_t)stages<CG>() * FILT_BYTES + (size_t)RROWS * row_floats<CG>() * sizeof(float) + 512;
 }
-
-struct TileMeta { int mode, xorg; };
-struct Box { int xmin, xmax, ymin, ymax; };
 
 // 16 taps x one channel from the rolling window.  off[j] = float offset of (row j of the window, first column);
 // INTERIOR: the four columns are consecutive (no border clamp), so every LDS carries an immediate offset.
@@ -73,16 +58,6 @@ __device__ __forceinline__ float window_from_smem(const float *__restrict__ ring
         }
     return qTL * Q[0] + qTR * Q[1] + qBL * Q[2] + qBR * Q[3];
 }
-
-// Position of one thread in the CTA's sequence of pipeline slots (tiles of its items, back to back), advanced
-// incrementally: the per-item decode (two divisions) runs once per item, not once per tile.
-struct Cursor {
-    int item_no;    // index into this CTA's items
-    int left;       // tiles left in the current item, including the current one
-    int b;          // batch item
-    int w_i, h_i;   // pixel of this thread; h_i >= H marks "no pixel" (null slot / past the end)
-    unsigned pix;   // h_i * W + w_i
-};
 
 template <int CG>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -409,18 +384,8 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
     if ((long long)CG * H * W >= (1ll << 31)) return -1;   // 32-bit pixel offsets inside one batch item
     const int tiles_x = ceil_div(W, TW), tiles_y = ceil_div(H, TH);
     if ((long long)tiles_x * tiles_y * B >= (1ll << 28)) return -1;
-    // Split every strip into `nseg` segments so that the items fill whole rounds of one CTA per SM.  Cost model:
-    // rounds x (tiles per segment + ~3 tiles' worth of window refill at each segment start).
     const int sms = sm_count();
-    int best_nseg = 1;
-    long long best_cost = LLONG_MAX;
-    for (int ns = 1; ns <= std::min(tiles_y, 64); ++ns) {
-        const long long items = (long long)B * tiles_x * ns;
-        const long long rounds = (items + sms - 1) / sms;
-        const long long cost = rounds * ((tiles_y + ns - 1) / ns + 3);
-        if (cost < best_cost) { best_cost = cost; best_nseg = ns; }
-    }
-    const int nseg = best_nseg, segt = (tiles_y + nseg - 1) / nseg;
+    const int nseg = choose_segments(B, tiles_x, tiles_y, sms), segt = (tiles_y + nseg - 1) / nseg;
     const long long items = (long long)B * tiles_x * nseg;
     auto kernel = fi_forward_ori_strip_kernel<CG>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<CG>());

@@ -24,6 +24,8 @@ namespace vfidkr {
 
 int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
                          int B, int C, int H, int W, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
+int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
+                         int B, int C, int H, int W, cudaStream_t s);   // fi_strip_dkr.cu; -1 = not applicable
 
 namespace {
 
@@ -506,6 +508,12 @@ int launch_forward(const float *in1, const float *in2, const float *in3, const f
             fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
         }
     } else if (F == 4) {
+        if (forced_forward_path() != PATH_DIRECT) {
+            // production path: strip-walking kernel, bilinear samples from the rolling shared-memory window
+            const int e = (V == V_NOFILT) ? fi_strip_forward_dkr(V, in1, in2, nullptr, in3, out, B, C, H, W, s)
+                                          : fi_strip_forward_dkr(V, in1, in2, in3, in4, out, B, C, H, W, s);
+            if (e >= 0) return e;
+        }
         if (C == 3) fi_forward_dkr_kernel<V, 4, 3><<<grid, block, 0, s>>>(in1, in2, in3, in4, out, C, H, W, F);
         else        fi_forward_dkr_kernel<V, 4, 4><<<grid, block, 0, s>>>(in1, in2, in3, in4, out, C, H, W, F);
     } else {
