@@ -134,6 +134,35 @@ class ClockSampler(threading.Thread):
 
 
 # ----------------------------------------------------------------------------- the workload
+def scene_flow(torch, g, device, B, H, W):
+    """Synthetic optical flow with the statistics the warping ops see in the network: PWC-Net's flow lives at quarter
+    resolution and is upsampled 4x bilinearly (networks/DAIN.py:306-308), so it is smooth at the 4-pixel scale; at
+    larger scales a scene moves piecewise smoothly.  Quarter-resolution field = a smooth large-scale motion
+    (1/64-resolution N(0, 6^2) px, bicubic) + six independently moving rectangular "objects" per item (constant extra
+    motion N(0, 8^2) px, sharp motion boundaries) + N(0, 0.25^2) px estimation jitter; clipped to +-24 px; then x4
+    bilinear.  (The operator table also times the rougher `up4` field -- i.i.d. N(0, 4^2) at quarter resolution --
+    and a per-pixel i.i.d. field as stress cases.)"""
+    F = torch.nn.functional
+    h4, w4 = H // 4, W // 4
+    coarse = torch.randn((B, 2, max(H // 64, 2), max(W // 64, 2)), generator=g, device=device) * 6.0
+    lo = F.interpolate(coarse, size=(h4, w4), mode="bicubic", align_corners=False)
+    n_obj = 6
+    motion = torch.randn((B, n_obj, 2), generator=g, device=device) * 8.0
+    geom = torch.rand((B, n_obj, 4), generator=g, device=device)
+    yy = torch.arange(h4, device=device).view(1, h4, 1)
+    xx = torch.arange(w4, device=device).view(1, 1, w4)
+    for k in range(n_obj):
+        y0 = (geom[:, k, 0] * 0.8 * h4).view(B, 1, 1)
+        x0 = (geom[:, k, 1] * 0.8 * w4).view(B, 1, 1)
+        hh = ((0.08 + 0.25 * geom[:, k, 2]) * h4).view(B, 1, 1)
+        ww = ((0.08 + 0.25 * geom[:, k, 3]) * w4).view(B, 1, 1)
+        inside = ((yy >= y0) & (yy < y0 + hh) & (xx >= x0) & (xx < x0 + ww)).unsqueeze(1)   # [B,1,h4,w4]
+        lo = lo + inside * motion[:, k].view(B, 2, 1, 1)
+    lo = lo + torch.randn((B, 2, h4, w4), generator=g, device=device) * 0.25
+    lo = lo.clamp_(-24, 24)
+    return F.interpolate(lo, scale_factor=4, mode="bilinear", align_corners=False).contiguous()
+
+
 def build_inputs(torch, device, seed, pinned_host=False):
     """Synthetic inputs of one step.  Returns a dict of tensors; with pinned_host
     they live in pinned host memory, else on `device`."""
@@ -147,11 +176,7 @@ def build_inputs(torch, device, seed, pinned_host=False):
         if kind == "image":
             x = torch.rand(shape, generator=g, device=device)
         elif kind == "flow":
-            # the networks produce the flow at quarter resolution and upsample it 4x bilinearly
-            # (networks/DAIN.py:306-308); the synthetic flow follows the same recipe: N(0, 4^2) px clipped
-            # to +-20 px at H/4 x W/4, then bilinear x4
-            lo = (torch.randn((shape[0], shape[1], shape[2] // 4, shape[3] // 4), generator=g, device=device) * 4.0).clamp_(-20, 20)
-            x = torch.nn.functional.interpolate(lo, scale_factor=4, mode="bilinear", align_corners=False).contiguous()
+            x = scene_flow(torch, g, device, shape[0], shape[2], shape[3])
         elif kind == "filter":
             x = torch.softmax(torch.randn(shape, generator=g, device=device), dim=1)
         elif kind == "depth":
@@ -295,7 +320,8 @@ def bench_ours(args):
                                "2x DepthFlowProjection fwd (fillhole) + 2x FilterInterpolation_ori fwd (C=3,F=4)",
                    "pairs_per_gpu": PAIRS_PER_GPU, "frame": "1920x1080 padded to 1152x1984",
                    "parallelism": f"pair-sharded x{world}, no data-path collective",
-                   "l2": "inputs_exceed_l2 (one step streams > 4 GB, L2 is 126 MB)"},
+                   "l2": "inputs_exceed_l2 (one step streams > 4 GB, L2 is 126 MB)",
+                   "flow": "synthetic scene flow: quarter-res smooth field + 6 moving rectangles + 0.25 px jitter, x4 bilinear (bench.py: scene_flow)"},
         "roofline": {"bound": "hbm", "kernel": "fi_forward_ori_strip_kernel<3>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(),
                      "peak_source": peak_src, "algorithmic_bytes_per_launch": FI_BYTES_PER_PIXEL * n_px,
@@ -503,8 +529,11 @@ def op_table(torch, V, device, path):
 
     px = B * H * W
     I = torch.rand(B, 3, H, W, device=device)
-    fl = torch.nn.functional.interpolate((torch.randn(B, 2, H // 4, W // 4, device=device) * 4).clamp_(-20, 20),
-                                         scale_factor=4, mode="bilinear", align_corners=False).contiguous()
+    gen = torch.Generator(device=device)
+    gen.manual_seed(77)
+    fl = scene_flow(torch, gen, device, B, H, W)                             # the bench's flow model
+    fl_up4 = torch.nn.functional.interpolate((torch.randn(B, 2, H // 4, W // 4, device=device) * 4).clamp_(-20, 20),
+                                             scale_factor=4, mode="bilinear", align_corners=False).contiguous()   # rough stress field
     fl_iid = (torch.randn(B, 2, H, W, device=device) * 4).clamp_(-20, 20)   # per-pixel i.i.d. flow: worst case for the gathers
     ft = torch.softmax(torch.randn(B, 16, H, W, device=device), 1)
     off = (torch.rand(B, 32, H, W, device=device) - 0.5) * 0.9
@@ -513,6 +542,7 @@ def op_table(torch, V, device, path):
     g2 = torch.randn(B, 2, H, W, device=device)
     with torch.no_grad():
         add("FI_ori_fwd_C3", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl, ft)), 96, px)
+        add("FI_ori_fwd_C3_up4flow", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl_up4, ft)), 96, px)
         add("FI_ori_fwd_C3_iidflow", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl_iid, ft)), 96, px)
         yy, xx = torch.meshgrid(torch.linspace(0, 6, H, device=device), torch.linspace(0, 6, W, device=device), indexing="ij")
         fl_smooth = torch.stack([6 * torch.sin(xx) + 3 * torch.cos(yy), 5 * torch.cos(0.7 * xx) - 3 * torch.sin(yy)], 0)[None].repeat(B, 1, 1, 1).contiguous()
@@ -525,6 +555,8 @@ def op_table(torch, V, device, path):
         add("FlowProjection_fwd_fill", timeit(lambda: V.FlowProjectionLayer.apply(fl, False)), 20, px)
         add("FlowProjection_fwd", timeit(lambda: V.FlowProjectionLayer.apply(fl, True)), 20, px)
         add("DepthFlowProjection_fwd_fill", timeit(lambda: V.DepthFlowProjectionLayer.apply(fl, dep, False)), 24, px)
+        add("DepthFlowProjection_fwd_fill_up4flow", timeit(lambda: V.DepthFlowProjectionLayer.apply(fl_up4, dep, False)), 24, px)
+        add("FI_dkr_fwd_C3_up4flow", timeit(lambda: V.FilterInterpolationLayerDKR.apply(I, fl_up4, ft, off)), 224, px)
     # backward timings through the C ABI directly (no autograd bookkeeping in the timed region)
     from vfidkr_b200 import _lib
     from vfidkr_b200._common import ptr, stream_ptr

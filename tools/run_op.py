@@ -21,7 +21,7 @@ ap.add_argument("--B", type=int, default=8)
 ap.add_argument("--C", type=int, default=3)
 ap.add_argument("--H", type=int, default=1152)
 ap.add_argument("--W", type=int, default=1984)
-ap.add_argument("--flow", default="up4", help="up4 | gauss (iid per pixel) | smooth | zero")
+ap.add_argument("--flow", default="up4", help="scene (bench flow) | up4 | gauss (iid per pixel) | smooth | zero")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 B, C, H, W = a.B, a.C, a.H, a.W
@@ -30,6 +30,11 @@ I = torch.rand(B, C, H, W, device=dev)
 if a.flow == "up4":
     fl = torch.nn.functional.interpolate((torch.randn(B, 2, H // 4, W // 4, device=dev) * 4).clamp_(-20, 20),
                                          scale_factor=4, mode="bilinear", align_corners=False).contiguous()
+elif a.flow == "scene":
+    from bench import scene_flow
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77)
+    fl = scene_flow(torch, gen, dev, B, H, W)
 elif a.flow == "gauss":
     fl = (torch.randn(B, 2, H, W, device=dev) * 4).clamp_(-20, 20)
 elif a.flow == "smooth":

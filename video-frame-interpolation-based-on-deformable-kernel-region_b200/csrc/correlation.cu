@@ -268,22 +268,26 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
 
 // ---------------------------------------------------------------------------------------------
 // direct forward for SMALL maps (kernel_size 1, strides 1, md 4): the coarse PWC levels (18x31, 36x62 at
-// 1080p) have too few tiles to fill 148 SMs with the tiled kernel and are issue-bound on a handful of
-// warps.  Here one thread owns (pixel, vertical displacement) and 9 horizontal displacements; warps run
-// along x so the 9 shifted f2 reads of a warp overlap in L1.  No shared memory, no staging, 9x more CTAs.
+// 1080p) have too few tiles to fill 148 SMs with the tiled kernel and are latency-bound on a handful of
+// warps walking the channels serially.  Here a thread owns (pixel, vertical displacement, channel slice):
+// the channels are dealt round-robin to S = 4 adjacent lanes, each accumulates 9 horizontal displacements
+// over its quarter of the channels, and two shuffle steps add the slices -- 4 x 9 x more threads than output
+// pixels, no shared memory, no staging, no atomics.
 // ---------------------------------------------------------------------------------------------
+constexpr int CORR_SLICES = 4, CORR_DPX = 32 / CORR_SLICES;   // 8 pixels per warp
+
 __global__ void __launch_bounds__(32 * 9)
 corr_forward_direct_kernel(const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
                            int C, int H, int W, int shift, int oh, int ow)
 {
-    constexpr int DR = 4, D = 9;
-    const int ox = blockIdx.x * 32 + threadIdx.x, oy = blockIdx.y, n = blockIdx.z;
+    constexpr int DR = 4, D = 9, S = CORR_SLICES;
+    const int lane = threadIdx.x, slice = lane % S;
+    const int ox = blockIdx.x * CORR_DPX + lane / S, oy = blockIdx.y, n = blockIdx.z;
     const int tj = (int)threadIdx.y;   // 0..8  <->  displacement tj - 4
-    if (ox >= ow) return;
     const size_t HW = (size_t)H * W;
     const int x = ox + shift, y = oy + shift;            // same pixel in image coordinates
     const int y2 = y + tj - DR;
-    const bool ok1 = x >= 0 && x < W && y >= 0 && y < H;
+    const bool ok1 = ox < ow && x >= 0 && x < W && y >= 0 && y < H;
     const bool row2 = y2 >= 0 && y2 < H;
     const float *p1 = in1 + (size_t)n * C * HW + (ok1 ? (size_t)y * W + x : 0);
     const float *p2 = in2 + (size_t)n * C * HW + (row2 ? (size_t)y2 * W : 0);
@@ -299,8 +303,8 @@ corr_forward_direct_kernel(const float *__restrict__ in1, const float *__restric
 #pragma unroll
     for (int t = 0; t < D; ++t) acc[t] = 0.0f;
     if (ok1 && row2) {
-#pragma unroll 4
-        for (int c = 0; c < C; ++c) {
+#pragma unroll 2
+        for (int c = slice; c < C; c += S) {
             const float a = __ldg(p1 + (size_t)c * HW);
             const float *r = p2 + (size_t)c * HW;
 #pragma unroll
@@ -310,11 +314,20 @@ corr_forward_direct_kernel(const float *__restrict__ in1, const float *__restric
             }
         }
     }
+    // add the S channel slices (adjacent lanes); afterwards every lane of the group holds the full sums
+#pragma unroll
+    for (int t = 0; t < D; ++t) {
+        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 1);
+        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 2);
+    }
+    if (ox >= ow) return;
     const float inv = 1.0f / (float)C;
     const size_t plane = (size_t)oh * ow;
     float *o = out + ((size_t)n * D * D + (size_t)tj * D) * plane + (size_t)oy * ow + ox;
+    // the group's lanes share the 9 stores: lane `slice` writes displacements slice, slice + S, ...
 #pragma unroll
-    for (int t = 0; t < D; ++t) o[(size_t)t * plane] = acc[t] * inv;
+    for (int t = 0; t < D; ++t)
+        if (t % S == slice) o[(size_t)t * plane] = acc[t] * inv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -451,10 +464,10 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
                          encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
                          encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK);
         if (!tma) { memset(&m1, 0, sizeof m1); memset(&m2, 0, sizeof m2); }
-        if (num_tiles * 4 <= (long long)sm_count()) {
-            // far too few tiles to fill the machine (the coarsest PWC level): one thread per (pixel, vertical
-            // displacement) instead -- measured 66 us vs 142 us for 8x196x18x31
-            dim3 block(32, 9), grid(ceil_div(cs.ow, 32), cs.oh, B);
+        if (num_tiles <= (long long)sm_count()) {
+            // too few tiles to fill the machine (the two coarsest PWC levels at 1080p): one thread per (pixel,
+            // vertical displacement, channel slice) instead
+            dim3 block(32, 9), grid(ceil_div(cs.ow, CORR_DPX), cs.oh, B);
             if (cs.oh > 65535) return VFIDKR_ERR_ARG;
             corr_forward_direct_kernel<<<grid, block, 0, s>>>(input1, input2, output, C, H, W, md - pad, cs.oh, cs.ow);
             note_launch();

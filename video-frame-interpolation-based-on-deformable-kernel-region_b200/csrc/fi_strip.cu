@@ -118,6 +118,19 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         // for "tile done"), the image window follows the bounding boxes.  The filter stream is advanced from
         // inside every wait of the image stream, so a window re-base never stalls the HBM prefetch.
         int f_t = 0, f_b = 0, f_bx = 0, f_ty = 0, f_left = 0, f_item = -1;   // filter stream position
+        // Optional L2 prefetch stream, PF tiles ahead of the filter stream (cp.async.bulk.prefetch.tensor).  Measured:
+        // PF = 8 is 6 % SLOWER than PF = 0 at 1080p x 8 -- the ring is not HBM-latency bound -- so it is off.
+        constexpr int PF = 0;
+        int p_t = 0, p_b = 0, p_bx = 0, p_ty = 0, p_left = 0, p_item = -1;
+        auto prefetch_next = [&]() {
+            if (PF == 0 || p_t >= n) return;
+            if (p_left == 0) { ++p_item; decode_item(p_item, p_b, p_bx, p_ty); p_left = segt; }
+            else ++p_ty;
+            --p_left;
+            if (lane == 0 && p_ty < tiles_y) tma_prefetch_3d(&map_filt, p_bx * TW, p_ty * TH, p_b * 16);
+            ++p_t;
+        };
+        for (int k = 0; k < PF; ++k) prefetch_next();
         auto pump_filters = [&]() {
             while (f_t < n && (f_t < SF || mbar_test(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1)))) {
                 if (f_left == 0) { ++f_item; decode_item(f_item, f_b, f_bx, f_ty); f_left = segt; }
@@ -133,6 +146,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                     }
                 }
                 ++f_t;
+                prefetch_next();
             }
         };
         // wait for a barrier phase while keeping the filter stream going; traps instead of hanging on a protocol error
@@ -213,6 +227,9 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         // ================================ compute warps ================================
         const int tx = tid % TW, tyy = tid / TW;   // position inside the tile
         const unsigned tile_step = (unsigned)(TH * W);
+        // 32-bit shared addresses of the barrier / box rings, computed once
+        const uint32_t a_filt_full = smem_u32(filt_full), a_tile_done = smem_u32(tile_done);
+        const uint32_t a_bbox_done = smem_u32(bbox_done), a_img_full = smem_u32(img_full), a_box = smem_u32(s_box);
 
         auto start_item = [&](Cursor &c) {
             if (c.item_no >= my_items) { c.left = INT_MAX; c.b = 0; c.w_i = 0; c.h_i = INT_MAX / 2; c.pix = 0; return; }
@@ -238,7 +255,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         auto request_flow = [&](const Cursor &c, float &fx, float &fy) {
             fx = 0.0f; fy = 0.0f;
             if (has_pixel(c)) {
-                const float *f = in2 + (size_t)c.b * 2 * HW + c.pix;
+                const float *f = in2 + ((size_t)c.b * 2 * HW + c.pix);
                 fx = ld_stream(f);
                 fy = ld_stream(f + HW);
             }
@@ -263,12 +280,13 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             ymin = __reduce_min_sync(0xffffffffu, ymin);
             ymax = __reduce_max_sync(0xffffffffu, ymax);
             if (lane == 0) {
-                Box *bx_ = &s_box[slot % NB];
+                const uint32_t sl = (uint32_t)(slot % NB);
                 if (xmax >= xmin) {
-                    atomicMin(&bx_->xmin, xmin); atomicMax(&bx_->xmax, xmax);
-                    atomicMin(&bx_->ymin, ymin); atomicMax(&bx_->ymax, ymax);
+                    const uint32_t ab = a_box + sl * (uint32_t)sizeof(Box);
+                    red_shared_min_a(ab, xmin); red_shared_max_a(ab + 4, xmax);
+                    red_shared_min_a(ab + 8, ymin); red_shared_max_a(ab + 12, ymax);
                 }
-                mbar_arrive(&bbox_done[slot % NB]);   // release: the atomics above are visible to the producer
+                mbar_arrive_a(a_bbox_done + sl * 8);   // release: the reductions above are visible to the producer
             }
         };
 
@@ -298,9 +316,9 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             const int sf = j % SF, sb = j % NB;
             const float *ft = s_filt + sf * FILT_FLOATS + tid;
 
-            mbar_wait_sleepy(&img_full[sb], (uint32_t)((j / NB) & 1));
+            mbar_wait_backoff_a(a_img_full + sb * 8, (uint32_t)((j / NB) & 1));
             const int mode = s_meta[sb].mode, xorg = s_meta[sb].xorg;
-            mbar_wait_sleepy(&filt_full[sf], (uint32_t)((j / SF) & 1));
+            mbar_wait_backoff_a(a_filt_full + sf * 8, (uint32_t)((j / SF) & 1));
 
             if (has_pixel(cur)) {
                 float *o = out + (size_t)cur.b * CG * HW + cur.pix;
@@ -367,7 +385,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tile_done[sf]);   // this warp is done with filter stage sf and the window rows of tile j
+            if (lane == 0) mbar_arrive_a(a_tile_done + sf * 8);   // this warp is done with filter stage sf and the window rows of tile j
             advance(cur);
 #pragma unroll
             for (int k = 0; k < LEAD; ++k) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; }

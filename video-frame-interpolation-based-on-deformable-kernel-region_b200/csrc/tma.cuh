@@ -101,6 +101,44 @@ __device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, uint32_t parity)
         if (spins > (1u << 22)) __trap();
 }
 
+// ---- the same primitives on precomputed 32-bit shared addresses (hot loops: no address conversion per call) ----
+__device__ __forceinline__ bool mbar_try_wait_a(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Wait of a compute warp: a failed probe is followed by a real sleep, so a warp that is ahead of its data does not
+// burn the issue slots of the warps it is waiting for.  Traps instead of hanging on a protocol error.
+__device__ __forceinline__ void mbar_wait_backoff_a(uint32_t bar, uint32_t parity)
+{
+    if (mbar_try_wait_a(bar, parity)) return;
+    for (uint32_t spins = 0;; ++spins) {
+        __nanosleep(128);
+        if (mbar_try_wait_a(bar, parity)) return;
+        if (spins > (1u << 24)) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// shared-memory min / max without the compiler's warp-aggregation wrapper (the caller is a single elected lane)
+__device__ __forceinline__ void red_shared_min_a(uint32_t addr, int v)
+{
+    asm volatile("red.shared::cta.min.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_shared_max_a(uint32_t addr, int v)
+{
+    asm volatile("red.shared::cta.max.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
 // 3-D tiled load global -> shared, completion signalled on `bar` (complete_tx::bytes)
 __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int z)
 {
@@ -108,6 +146,13 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
+}
+// L2 prefetch of a 3-D box: brings the bytes from HBM into L2 without occupying shared memory, so a later
+// tma_load_3d of the same box pays L2 latency only (decouples HBM latency from the depth of the smem ring)
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int x, int y, int z)
+{
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z)
+                 : "memory");
 }
 // 4-D tiled load (x, y, channel, batch)
 __device__ __forceinline__ void tma_load_4d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int x, int y, int c, int n)
