@@ -64,6 +64,12 @@ ops = {
     "proj_fwd": lambda: V.FlowProjectionLayer.apply(fl, False),
     "dproj_fwd": lambda: V.DepthFlowProjectionLayer.apply(fl, dep, False),
 }
+if a.op == "fi_bench":
+    # the FilterInterpolation calls of bench.py, on bench.py's own inputs (both directions)
+    import bench
+    d = bench.build_inputs(torch, dev, seed=1004)
+    fi = V.FilterInterpolationModule()
+    ops["fi_bench"] = lambda: (fi(d["frame0"], d["flow0"], d["filter0"]), fi(d["frame1"], d["flow1"], d["filter1"]))
 if a.op.startswith("corr"):
     Cc, s = {"corr_l2": (32, 4), "corr_l3": (64, 8), "corr_l4": (96, 16), "corr_l5": (128, 32), "corr_l6": (196, 64)}[a.op]
     f1 = torch.randn(B, Cc, H // s, W // s, device=dev)
