@@ -15,6 +15,8 @@ void note_launch(int n = 1);              // relaxed launch counter (capi.cu)
 int  check_launch(const char *what);      // cudaGetLastError -> VFIDKR_OK / VFIDKR_ERR_CUDA
 int  set_error(cudaError_t e, const char *what);
 int  sm_count();                          // cached multiprocessor count of the current device
+// stream-ordered scratch memory from the device's default pool (projection.cu): no synchronisation, cached by the pool
+int  stream_scratch_alloc(void **p, size_t bytes, cudaStream_t s);
 
 static inline unsigned ceil_div(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

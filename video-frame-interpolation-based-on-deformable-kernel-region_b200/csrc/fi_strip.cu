@@ -39,7 +39,7 @@ constexpr uint32_t FILT_BYTES = FILT_FLOATS * sizeof(float);
 template <int CG> __host__ __device__ constexpr int stages() { return CG <= 3 ? 4 : 3; }
 template <int CG> __host__ __device__ constexpr size_t smem_bytes()
 {
-    return (size_t)stages<CG>() * FILT_BYTES + (size_t)RROWS * row_floats<CG>() * sizeof(float) + 512;
+    return (size_t)stages<CG>() * FILT_BYTES + (size_t)RROWS * row_floats<CG>() * sizeof(float) + 1024;
 }
 
 // 16 taps x one channel from the rolling window.  off[j] = float offset of (row j of the window, first column);
@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const __grid_constant__ CUtensorMap map_img,
                             const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
                             int H, int W, int tiles_x, int tiles_y, int nseg, int segt, int num_items,
-                            const FastDiv div_tiles_x, const FastDiv div_nseg)
+                            const FastDiv div_tiles_x, const FastDiv div_nseg, int *__restrict__ work_counter)
 {
     constexpr int SF = stages<CG>();
     constexpr int ROWF = row_floats<CG>();
@@ -75,17 +75,11 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
     uint64_t *filt_full = s_bar, *tile_done = s_bar + SF, *bbox_done = s_bar + 2 * SF, *img_full = bbox_done + NB;
     Box *s_box = reinterpret_cast<Box *>(img_full + NB);                              // [NB]
     TileMeta *s_meta = reinterpret_cast<TileMeta *>(s_box + NB);                      // [NB]
-    int *s_ymin = reinterpret_cast<int *>(s_meta + NB);                               // [SF], producer private
+    int *s_ymin = reinterpret_cast<int *>(s_meta + NB);                               // [NB], producer private
+    ItemQueue *s_queue = reinterpret_cast<ItemQueue *>(s_ymin + NB);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const size_t HW = (size_t)H * W;
-
-    // Work items are strip segments (b, seg, bx) -- `segt` tiles walked downwards -- numbered with bx fastest and
-    // dealt round-robin, so CTAs k and k+1 hold neighbouring strips of the same rows at the same time.
-    // This CTA's pipeline slots are the tiles of its items back to back; slots past the end of a ragged last
-    // segment are "null" (no loads, no pixels) so that stage and phase accounting stays uniform.
-    const int my_items = (int)blockIdx.x < num_items ? (num_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
-    const int n = my_items * segt;
 
     if (tid == 0) {
         prefetch_tensormap(&map_filt);
@@ -99,42 +93,52 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             mbar_init(&img_full[s], 1);
             s_box[s] = Box{INT_MAX, INT_MIN, INT_MAX, INT_MIN};
         }
+        s_queue->fetched = 0;
+        s_queue->wanted = 0;
         fence_mbar_init();
     }
     __syncthreads();
 
-    // item number (of this CTA) -> batch item, column block, first tile row
-    auto decode_item = [&](int item_no, int &b, int &bx, int &ty0) {
-        const int item = (int)blockIdx.x + item_no * (int)gridDim.x;
+    // k-th item of this CTA -> batch item, column block, first tile row; false when the work is exhausted.
+    // The CTA's pipeline slots are the tiles of its items back to back; slots past the end of a ragged last segment
+    // of a strip are "null" (no loads, no pixels) so that stage and phase accounting stays uniform.
+    auto decode_item = [&](int item_no, int &b, int &bx, int &ty0) -> bool {
+        // every lane reads the same entry; the redux hands it to the compiler as a warp-UNIFORM value, so the tile
+        // bookkeeping derived from it (loop trip counts, item boundaries) stays on the uniform datapath
+        const int item = __reduce_max_sync(0xffffffffu, queue_get(s_queue, item_no));
+        if (item < 0) return false;
         const int bs = div_tiles_x.quot(item);   // b * nseg + seg
         bx = item - bs * tiles_x;
         b = div_nseg.quot(bs);
         ty0 = (bs - b * nseg) * segt;
+        return true;
     };
 
     if (warp == NCOMP_WARPS) {
         // ================================ producer warp ================================
         // Two independent streams: the filter planes run as far ahead as the SF-deep ring allows (they only wait
         // for "tile done"), the image window follows the bounding boxes.  The filter stream is advanced from
-        // inside every wait of the image stream, so a window re-base never stalls the HBM prefetch.
-        int f_t = 0, f_b = 0, f_bx = 0, f_ty = 0, f_left = 0, f_item = -1;   // filter stream position
-        // Optional L2 prefetch stream, PF tiles ahead of the filter stream (cp.async.bulk.prefetch.tensor).  Measured:
-        // PF = 8 is 6 % SLOWER than PF = 0 at 1080p x 8 -- the ring is not HBM-latency bound -- so it is off.
-        constexpr int PF = 0;
-        int p_t = 0, p_b = 0, p_bx = 0, p_ty = 0, p_left = 0, p_item = -1;
-        auto prefetch_next = [&]() {
-            if (PF == 0 || p_t >= n) return;
-            if (p_left == 0) { ++p_item; decode_item(p_item, p_b, p_bx, p_ty); p_left = segt; }
-            else ++p_ty;
-            --p_left;
-            if (lane == 0 && p_ty < tiles_y) tma_prefetch_3d(&map_filt, p_bx * TW, p_ty * TH, p_b * 16);
-            ++p_t;
+        // inside every wait of the image stream, so a window re-base never stalls the HBM prefetch.  The same pump
+        // serves the compute warps' requests for the next work item.
+        bool exhausted = false;
+        int item_no = -1;                                                   // image stream: current item
+        auto draw_items = [&](int upto) {
+            if (lane == 0) queue_fill(s_queue, work_counter, num_items, upto, exhausted);
+            __syncwarp();
         };
-        for (int k = 0; k < PF; ++k) prefetch_next();
+        int f_t = 0, f_b = 0, f_bx = 0, f_ty = 0, f_left = 0, f_item = -1;   // filter stream position
+        bool f_end = false;
         auto pump_filters = [&]() {
-            while (f_t < n && (f_t < SF || mbar_test(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1)))) {
-                if (f_left == 0) { ++f_item; decode_item(f_item, f_b, f_bx, f_ty); f_left = segt; }
-                else ++f_ty;
+            draw_items(*(volatile int *)&s_queue->wanted);
+            while (!f_end && (f_t < SF || mbar_test(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1)))) {
+                if (f_left == 0) {
+                    ++f_item;
+                    draw_items(f_item + 1);
+                    if (!decode_item(f_item, f_b, f_bx, f_ty)) { f_end = true; break; }
+                    f_left = segt;
+                } else {
+                    ++f_ty;
+                }
                 --f_left;
                 if (lane == 0) {
                     const int sf = f_t % SF;
@@ -146,7 +150,6 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                     }
                 }
                 ++f_t;
-                prefetch_next();
             }
         };
         // wait for a barrier phase while keeping the filter stream going; traps instead of hanging on a protocol error
@@ -158,11 +161,18 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         };
 
         int xorg = 0, base = 0, hi = 0;   // window state: rows [max(base, hi - RROWS), hi) are resident
-        int b = 0, bx = 0, ty = 0, left = 0, item_no = -1;
-        for (int t = 0; t < n; ++t) {
+        int b = 0, bx = 0, ty = 0, left = 0;
+        for (int t = 0;; ++t) {
             bool new_item = false;
-            if (left == 0) { ++item_no; decode_item(item_no, b, bx, ty); left = segt; new_item = true; }
-            else ++ty;
+            if (left == 0) {
+                ++item_no;
+                draw_items(item_no + 1);
+                if (!decode_item(item_no, b, bx, ty)) break;
+                left = segt;
+                new_item = true;
+            } else {
+                ++ty;
+            }
             --left;
             const int sb = t % NB;
             pump_filters();
@@ -219,7 +229,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             }
             __syncwarp();
         }
-        while (f_t < n) {   // filter planes of the last tiles whose ring slots were still busy
+        while (!f_end) {   // filter planes of the last tiles whose ring slots were still busy
             if (f_t >= SF) mbar_wait_sleepy(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1));
             pump_filters();
         }
@@ -231,16 +241,17 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         const uint32_t a_filt_full = smem_u32(filt_full), a_tile_done = smem_u32(tile_done);
         const uint32_t a_bbox_done = smem_u32(bbox_done), a_img_full = smem_u32(img_full), a_box = smem_u32(s_box);
 
+        // left == 0 marks the end of the work: the cursor stays there (no pixel, no further queue reads)
         auto start_item = [&](Cursor &c) {
-            if (c.item_no >= my_items) { c.left = INT_MAX; c.b = 0; c.w_i = 0; c.h_i = INT_MAX / 2; c.pix = 0; return; }
             int bx, ty0;
-            decode_item(c.item_no, c.b, bx, ty0);
+            if (!decode_item(c.item_no, c.b, bx, ty0)) { c.left = 0; c.b = 0; c.w_i = 0; c.h_i = INT_MAX / 2; c.pix = 0; return; }
             c.left = segt;
             c.w_i = bx * TW + tx;
             c.h_i = ty0 * TH + tyy;   // rows past the frame (ragged last segment) are >= H by construction
             c.pix = (unsigned)(c.h_i * W + c.w_i);
         };
         auto advance = [&](Cursor &c) {
+            if (c.left == 0) return;
             if (--c.left == 0) { ++c.item_no; start_item(c); }
             else { c.h_i += TH; c.pix += tile_step; }
         };
@@ -274,7 +285,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 }
             }
             fx_x2 = x2; fy_y2 = y2;
-            if (slot >= n) return;
+            if (c.left == 0) return;   // past the end of the work: no such slot
             xmin = __reduce_min_sync(0xffffffffu, xmin);
             xmax = __reduce_max_sync(0xffffffffu, xmax);
             ymin = __reduce_min_sync(0xffffffffu, ymin);
@@ -305,7 +316,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             advance(fold);
         }
 
-        for (int j = 0; j < n; ++j) {
+        for (int j = 0; cur.left != 0; ++j) {
             // box of slot j + LEAD from the flow requested one tile ago; then request the flow of slot j + LEAD + 1
             qx[LEAD] = nx; qy[LEAD] = ny;
             fold_box(fold, j + LEAD, qx[LEAD], qy[LEAD]);
@@ -408,10 +419,18 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
     auto kernel = fi_forward_ori_strip_kernel<CG>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<CG>());
     const int nblk = (int)std::min<long long>(sms, items);
-    kernel<<<nblk, NTHREADS, smem_bytes<CG>(), s>>>(mfilt, mimg, in1, in2, out, H, W, tiles_x, tiles_y, nseg, segt, (int)items,
-                                                   FastDiv((unsigned)tiles_x), FastDiv((unsigned)nseg));
-    note_launch();
-    return check_launch("filterinterpolation forward (strip)");
+    void *counter = nullptr;   // the global work counter: 4 bytes of stream-ordered scratch, zeroed on the stream
+    int e = stream_scratch_alloc(&counter, sizeof(int), s);
+    if (e) return e;
+    e = set_error(cudaMemsetAsync(counter, 0, sizeof(int), s), "clear work counter");
+    if (!e) {
+        kernel<<<nblk, NTHREADS, smem_bytes<CG>(), s>>>(mfilt, mimg, in1, in2, out, H, W, tiles_x, tiles_y, nseg, segt, (int)items,
+                                                       FastDiv((unsigned)tiles_x), FastDiv((unsigned)nseg), static_cast<int *>(counter));
+        note_launch();
+        e = check_launch("filterinterpolation forward (strip)");
+    }
+    const int e2 = set_error(cudaFreeAsync(counter, s), "free work counter");
+    return e ? e : e2;
 }
 
 }  // namespace strip

@@ -29,15 +29,61 @@ struct Box { int xmin, xmax, ymin, ymax; };
 // Position of one thread in the CTA's sequence of pipeline slots (tiles of its items, back to back), advanced
 // incrementally: the per-item decode (two divisions) runs once per item, not once per tile.
 struct Cursor {
-    int item_no;    // index into this CTA's items
-    int left;       // tiles left in the current item, including the current one
+    int item_no;    // index into this CTA's item sequence
+    int left;       // tiles left in the current item, including the current one (0 once the work is exhausted)
     int b;          // batch item
     int w_i, h_i;   // pixel of this thread; h_i >= H marks "no pixel" (null slot / past the end)
     unsigned pix;   // h_i * W + w_i
 };
 
-// Split every strip into `nseg` segments so that the items (b, seg, bx) fill whole rounds of one CTA per SM.
-// Cost model: rounds x (tiles per segment + ~3 tiles' worth of window refill at each segment start).
+// ---- dynamic work distribution ----------------------------------------------------------------------------------
+// Work items are strip segments (b, seg, bx), numbered with bx fastest.  CTAs draw them from a global counter, so a
+// CTA that meets expensive tiles (re-bases, bank conflicts, fallbacks) simply draws fewer: measured with static
+// round-robin dealing the slowest SM ran 1.15x - 1.5x longer than the average one.  Drawing in item order keeps
+// neighbouring SMs on neighbouring strips of the same rows (their window columns overlap and hit in L2).
+// Inside a CTA several parties walk the SAME item sequence at different distances ahead (filter stream, image
+// stream, three cursors per compute thread), so the drawn ids go through a small shared-memory queue: entry k is
+// the k-th item of this CTA, -1 = no more work.  Only lane 0 of the producer warp draws; everybody else reads.
+// Items are drawn LAZILY -- entry k only when some party first asks for it (a few tiles before the CTA finishes item
+// k-1) -- because every item drawn early is an item another SM cannot take.
+constexpr int ITEM_QUEUE = 32;      // ring of item ids (>> the distance between the most and least advanced party)
+
+struct ItemQueue {
+    int ids[ITEM_QUEUE];
+    int fetched;                    // number of entries published so far
+    int wanted;                     // highest entry count any compute thread is waiting for
+};
+
+// k-th item of this CTA; -1 when the work is exhausted.  If it has not been drawn yet the caller posts its wish and
+// waits for the producer warp (which polls `wanted` from its pump loop, at most ~0.4 us apart).
+__device__ __forceinline__ int queue_get(ItemQueue *q, int k)
+{
+    volatile int *nf = &q->fetched;
+    if (*nf <= k) {
+        atomicMax(&q->wanted, k + 1);
+        while (*nf <= k) __nanosleep(64);
+    }
+    __threadfence_block();
+    return *(volatile int *)&q->ids[k % ITEM_QUEUE];
+}
+// producer lane 0: draw until entries [0, upto) exist or the work is exhausted
+__device__ __forceinline__ void queue_fill(ItemQueue *q, int *counter, int num_items, int upto, bool &exhausted)
+{
+    int nf = q->fetched;
+    while (nf < upto && !exhausted) {
+        int id = atomicAdd(counter, 1);
+        if (id >= num_items) { id = -1; exhausted = true; }
+        q->ids[nf % ITEM_QUEUE] = id;
+        __threadfence_block();
+        ++nf;
+        *(volatile int *)&q->fetched = nf;
+    }
+}
+
+// Segments per strip.  With uniform tiles the makespan is rounds x item length, rounds = ceil(items / SMs), so the
+// split is chosen to fill whole rounds (e.g. 128 strips x 8 segments = 1024 items = 6.9 -> 7 rounds on 148 SMs)
+// while keeping segments long: each segment start costs ~3 tiles' worth of window refill.  Dynamic drawing then
+// absorbs the non-uniformity of real tiles inside that schedule.
 inline int choose_segments(int B, int tiles_x, int tiles_y, int sms)
 {
     int best_nseg = 1;

@@ -199,8 +199,10 @@ projection_backward_kernel(const float *__restrict__ flow, const float *__restri
     if (DEPTH) st_stream(gi2 + (size_t)b * HW + pix, sd);
 }
 
+}  // namespace
+
 // stream-ordered scratch from the device's default memory pool; the pool keeps the block cached between calls
-static int scratch_alloc(void **p, size_t bytes, cudaStream_t s)
+int stream_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
 {
     static thread_local int configured_for = -1;
     int dev = 0;
@@ -213,8 +215,10 @@ static int scratch_alloc(void **p, size_t bytes, cudaStream_t s)
         (void)cudaGetLastError();
         configured_for = dev;
     }
-    return set_error(cudaMallocAsync(p, bytes, s), "projection scratch (cudaMallocAsync)");
+    return set_error(cudaMallocAsync(p, bytes, s), "scratch (cudaMallocAsync)");
 }
+
+namespace {
 
 template <bool DEPTH>
 int projection_forward(const float *flow, const float *depth, float *count, float *out,
@@ -224,7 +228,7 @@ int projection_forward(const float *flow, const float *depth, float *count, floa
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
     void *scratch = nullptr;
-    int e = scratch_alloc(&scratch, sizeof(float4) * B * HW, s);
+    int e = stream_scratch_alloc(&scratch, sizeof(float4) * B * HW, s);
     if (e) return e;
     float4 *S = static_cast<float4 *>(scratch);
     e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * B * HW, s), "clear projection scratch");
