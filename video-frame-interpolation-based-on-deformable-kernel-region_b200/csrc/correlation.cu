@@ -100,7 +100,7 @@ constexpr int F1_FLOATS = CK * TY * TX, F2_FLOATS = CK * F2H * F2W;
 constexpr uint32_t STAGE_BYTES = (F1_FLOATS + F2_FLOATS) * sizeof(float);
 // ring depth: 3 stages with two CTAs per SM for large maps; when there are fewer tiles than SMs (the coarse
 // PWC levels) a CTA has the SM to itself and a 7-deep ring hides the load latency of its long channel loop
-constexpr int STAGES_LARGE = 3, STAGES_SMALL = 7;
+constexpr int STAGES_LARGE = 3;
 constexpr size_t smem_bytes(int stages) { return (size_t)stages * STAGE_BYTES + 128; }
 static_assert(D % TJ == 0 && TX % PX == 0, "tile shape");
 }  // namespace cfast
@@ -110,8 +110,13 @@ __global__ void __launch_bounds__(cfast::NTHREADS, STAGES <= 3 ? 2 : 1)
 corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
                           const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
                           int C, int H, int W, int shift, int oh, int ow, int tiles_x, int tiles_y, int num_tiles,
-                          const FastDiv div_tiles_x, const FastDiv div_tiles_image)
+                          const FastDiv div_tiles_x, const FastDiv div_tiles_image,
+                          int ksplit, int cps, const FastDiv div_ksplit, float *__restrict__ partial, size_t part_stride)
 {
+    // Split-K for maps with too few tiles to fill the machine: a work item is (tile, channel slice); every slice
+    // walks `cps` chunks of CK channels (chunks past C are zero-filled by the loader) and, when ksplit > 1, writes
+    // its UNSCALED partial sums to `partial`[slice]; corr_reduce_kernel adds the slices.  num_tiles counts
+    // (tile, slice) items.  No atomics: the result does not depend on the order the slices finish in.
     using namespace cfast;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s1 = reinterpret_cast<float *>(smem_raw);                     // [STAGES][F1_FLOATS]
@@ -122,7 +127,7 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
     const int g = tid % (TX / PX);
     const int tjg = (tid / (TX / PX)) % (D / TJ);
     const int ry = tid / ((TX / PX) * (D / TJ));
-    const int nchunks = (C + CK - 1) / CK;
+    const int nchunks = cps;
     const int tiles_per_image = tiles_x * tiles_y;
     const size_t HW = (size_t)H * W;
 
@@ -134,7 +139,8 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
     }
     __syncthreads();
 
-    auto decode = [&](int tile, int &n, int &by, int &bx) {
+    auto decode = [&](int vt, int &n, int &by, int &bx) {
+        const int tile = div_ksplit.quot(vt);
         n = div_tiles_image.quot(tile);
         const int rem = tile - n * tiles_per_image;
         by = div_tiles_x.quot(rem);
@@ -143,6 +149,7 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
     auto issue = [&](int tile, int chunk, int stage) {   // thread 0 only (TMA path)
         int n, by, bx;
         decode(tile, n, by, bx);
+        chunk += (tile - div_ksplit.quot(tile) * ksplit) * cps;   // first chunk of this item's channel slice
         const int ix0 = bx * TX + shift, iy0 = by * TY + shift;
         mbar_arrive_expect_tx(&s_full[stage], STAGE_BYTES);
         tma_load_4d(s1 + stage * F1_FLOATS, &map1, &s_full[stage], ix0, iy0, chunk * CK, n);
@@ -154,6 +161,7 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
     auto stage_async = [&](int tile, int chunk, int stage) {
         int n, by, bx;
         decode(tile, n, by, bx);
+        chunk += (tile - div_ksplit.quot(tile) * ksplit) * cps;   // first chunk of this item's channel slice
         const int ix0 = bx * TX + shift, iy0 = by * TY + shift;
         const int warp = tid >> 5, lane = tid & 31, nwarps = NTHREADS / 32;
         const float *f1 = in1 + (size_t)n * C * HW, *f2 = in2 + (size_t)n * C * HW;
@@ -245,10 +253,12 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
             // nelems = kernel_size^2 * C (:104); the reference divides (:143), here it is one reciprocal and a
             // multiply per output (<= 1 ulp apart, far inside the 1e-5 parity bound; an IEEE division costs ~10
             // instructions x 108 outputs per thread)
-            const float inv = 1.0f / (float)C;
+            const float inv = ksplit > 1 ? 1.0f : 1.0f / (float)C;
             const size_t plane = (size_t)oh * ow;
-            float *o = out + ((size_t)n * D * D + (size_t)(TJ * tjg) * D) * plane + (size_t)oy * ow + ox;
-            const bool vec = (ow % 4 == 0) && (ox + 3 < ow) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+            float *dst = out;
+            if (ksplit > 1) dst = partial + (size_t)(tile - div_ksplit.quot(tile) * ksplit) * part_stride;
+            float *o = dst + ((size_t)n * D * D + (size_t)(TJ * tjg) * D) * plane + (size_t)oy * ow + ox;
+            const bool vec = (ow % 4 == 0) && (ox + 3 < ow) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll
             for (int t = 0; t < TJ; ++t)
 #pragma unroll
@@ -266,68 +276,15 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
     }
 }
 
-// ---------------------------------------------------------------------------------------------
-// direct forward for SMALL maps (kernel_size 1, strides 1, md 4): the coarse PWC levels (18x31, 36x62 at
-// 1080p) have too few tiles to fill 148 SMs with the tiled kernel and are latency-bound on a handful of
-// warps walking the channels serially.  Here a thread owns (pixel, vertical displacement, channel slice):
-// the channels are dealt round-robin to S = 4 adjacent lanes, each accumulates 9 horizontal displacements
-// over its quarter of the channels, and two shuffle steps add the slices -- 4 x 9 x more threads than output
-// pixels, no shared memory, no staging, no atomics.
-// ---------------------------------------------------------------------------------------------
-constexpr int CORR_SLICES = 4, CORR_DPX = 32 / CORR_SLICES;   // 8 pixels per warp
-
-__global__ void __launch_bounds__(32 * 9)
-corr_forward_direct_kernel(const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
-                           int C, int H, int W, int shift, int oh, int ow)
+// adds the ksplit partial cost volumes and applies the 1 / (kernel_size^2 * C) scaling (:104, :143)
+__global__ void __launch_bounds__(256)
+corr_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, size_t n, int ksplit, float inv)
 {
-    constexpr int DR = 4, D = 9, S = CORR_SLICES;
-    const int lane = threadIdx.x, slice = lane % S;
-    const int ox = blockIdx.x * CORR_DPX + lane / S, oy = blockIdx.y, n = blockIdx.z;
-    const int tj = (int)threadIdx.y;   // 0..8  <->  displacement tj - 4
-    const size_t HW = (size_t)H * W;
-    const int x = ox + shift, y = oy + shift;            // same pixel in image coordinates
-    const int y2 = y + tj - DR;
-    const bool ok1 = ox < ow && x >= 0 && x < W && y >= 0 && y < H;
-    const bool row2 = y2 >= 0 && y2 < H;
-    const float *p1 = in1 + (size_t)n * C * HW + (ok1 ? (size_t)y * W + x : 0);
-    const float *p2 = in2 + (size_t)n * C * HW + (row2 ? (size_t)y2 * W : 0);
-    bool ok2[D];
-    int off2[D];
-#pragma unroll
-    for (int t = 0; t < D; ++t) {
-        const int xx = x + t - DR;
-        ok2[t] = ok1 && row2 && xx >= 0 && xx < W;
-        off2[t] = ok2[t] ? xx : 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float acc = 0.0f;
+        for (int s = 0; s < ksplit; ++s) acc += __ldcs(partial + (size_t)s * n + i);
+        out[i] = acc * inv;
     }
-    float acc[D];
-#pragma unroll
-    for (int t = 0; t < D; ++t) acc[t] = 0.0f;
-    if (ok1 && row2) {
-#pragma unroll 2
-        for (int c = slice; c < C; c += S) {
-            const float a = __ldg(p1 + (size_t)c * HW);
-            const float *r = p2 + (size_t)c * HW;
-#pragma unroll
-            for (int t = 0; t < D; ++t) {
-                const float b = ok2[t] ? __ldg(r + off2[t]) : 0.0f;
-                acc[t] = fmaf(a, b, acc[t]);
-            }
-        }
-    }
-    // add the S channel slices (adjacent lanes); afterwards every lane of the group holds the full sums
-#pragma unroll
-    for (int t = 0; t < D; ++t) {
-        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 1);
-        acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 2);
-    }
-    if (ox >= ow) return;
-    const float inv = 1.0f / (float)C;
-    const size_t plane = (size_t)oh * ow;
-    float *o = out + ((size_t)n * D * D + (size_t)tj * D) * plane + (size_t)oy * ow + ox;
-    // the group's lanes share the 9 stores: lane `slice` writes displacements slice, slice + S, ...
-#pragma unroll
-    for (int t = 0; t < D; ++t)
-        if (t % S == slice) o[(size_t)t * plane] = acc[t] * inv;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -464,30 +421,43 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
                          encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
                          encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK);
         if (!tma) { memset(&m1, 0, sizeof m1); memset(&m2, 0, sizeof m2); }
-        if (num_tiles <= (long long)sm_count()) {
-            // too few tiles to fill the machine (the two coarsest PWC levels at 1080p): one thread per (pixel,
-            // vertical displacement, channel slice) instead
-            dim3 block(32, 9), grid(ceil_div(cs.ow, CORR_DPX), cs.oh, B);
-            if (cs.oh > 65535) return VFIDKR_ERR_ARG;
-            corr_forward_direct_kernel<<<grid, block, 0, s>>>(input1, input2, output, C, H, W, md - pad, cs.oh, cs.ow);
-            note_launch();
-            return check_launch("correlation forward (direct)");
+        // Too few tiles to fill the machine (the two coarsest PWC levels at 1080p): split the channels over
+        // ksplit work items per tile and add the partial volumes in a second, tiny kernel.
+        const int nchunks = (C + CK - 1) / CK;
+        int ksplit = 1;
+        if (num_tiles <= (long long)sm_count())
+            ksplit = (int)std::min<long long>(nchunks, (2ll * sm_count() + num_tiles - 1) / num_tiles);
+        const int cps = (nchunks + ksplit - 1) / ksplit;
+        ksplit = (nchunks + cps - 1) / cps;   // drop slices that would be empty
+        const long long num_items = num_tiles * ksplit;
+        const size_t out_elems = (size_t)B * D * D * cs.oh * cs.ow;
+        void *partial = nullptr;
+        if (ksplit > 1) {
+            const int e = stream_scratch_alloc(&partial, sizeof(float) * out_elems * ksplit, s);
+            if (e) return e;
         }
-        const bool small = num_tiles <= sm_count();
         auto launch = [&](auto kernel, int stages, int ctas_per_sm) {
             // raising the dynamic shared memory limit is idempotent and cheap; do it on every launch so the
             // attribute is set on whichever device is current
             cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(stages));
-            const int nblk = (int)std::min<long long>(num_tiles, (long long)sm_count() * ctas_per_sm);
+            const int nblk = (int)std::min<long long>(num_items, (long long)sm_count() * ctas_per_sm);
             kernel<<<nblk, NTHREADS, smem_bytes(stages), s>>>(m1, m2, input1, input2, output, C, H, W, md - pad, cs.oh, cs.ow,
-                                                              tiles_x, tiles_y, (int)num_tiles, dx, di);
+                                                              tiles_x, tiles_y, (int)num_items, dx, di, ksplit, cps,
+                                                              FastDiv((unsigned)ksplit), static_cast<float *>(partial), out_elems);
         };
-        if (tma) {
-            if (small) launch(corr_forward_tiled_kernel<true, STAGES_SMALL>, STAGES_SMALL, 1);
-            else       launch(corr_forward_tiled_kernel<true, STAGES_LARGE>, STAGES_LARGE, 2);
-        } else {
-            if (small) launch(corr_forward_tiled_kernel<false, STAGES_SMALL>, STAGES_SMALL, 1);
-            else       launch(corr_forward_tiled_kernel<false, STAGES_LARGE>, STAGES_LARGE, 2);
+        if (tma) launch(corr_forward_tiled_kernel<true, STAGES_LARGE>, STAGES_LARGE, 2);
+        else     launch(corr_forward_tiled_kernel<false, STAGES_LARGE>, STAGES_LARGE, 2);
+        if (ksplit > 1) {
+            note_launch();
+            int e = check_launch("correlation forward (split-K)");
+            if (!e) {
+                const unsigned nb = (unsigned)std::min<size_t>((out_elems + 255) / 256, (size_t)sm_count() * 8);
+                corr_reduce_kernel<<<nb, 256, 0, s>>>(static_cast<const float *>(partial), output, out_elems, ksplit, 1.0f / (float)C);
+                note_launch();
+                e = check_launch("correlation forward (reduce)");
+            }
+            const int e2 = set_error(cudaFreeAsync(partial, s), "free correlation scratch");
+            return e ? e : e2;
         }
     } else {
         dim3 block(32, 8), grid(ceil_div(cs.ow, 32), ceil_div(cs.oh, 8), B);
