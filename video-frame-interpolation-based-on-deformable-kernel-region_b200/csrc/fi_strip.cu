@@ -162,6 +162,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 
         int xorg = 0, base = 0, hi = 0;   // window state: rows [max(base, hi - RROWS), hi) are resident
         int b = 0, bx = 0, ty = 0, left = 0;
+#pragma unroll 1
         for (int t = 0;; ++t) {
             bool new_item = false;
             if (left == 0) {
@@ -316,6 +317,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             advance(fold);
         }
 
+#pragma unroll 1
         for (int j = 0; cur.left != 0; ++j) {
             // box of slot j + LEAD from the flow requested one tile ago; then request the flow of slot j + LEAD + 1
             qx[LEAD] = nx; qy[LEAD] = ny;
