@@ -510,3 +510,78 @@ def test_fi_dkr_strip_kernel(lib, oracle, monkeypatch, variant, B, C, H, W, fk, 
     U.assert_close(host(a), ref, U.RTOL_FWD, f"{variant} strip kernel vs oracle")
     U.assert_close(host(b), ref, U.RTOL_FWD, f"{variant} direct kernel vs oracle")
     assert U.max_err(host(a), host(b).astype(np.float64)) < 3e-6
+
+
+@pytest.mark.parametrize("variant", ["ori", "dkr"])
+def test_fi_strip_window_is_not_reused_across_work_items(lib, monkeypatch, variant):
+    """Regression (found as a 1-in-5 flake of the full-size linearity check): a CTA that starts a new work item
+    (another frame / strip segment) must re-base its rolling window even when the item's first tiles never touch
+    the window.  Here the first tile row of every 36-tile segment is out of range (copy path, no window) and the
+    flow points 6 rows up, so without the re-base the next tile finds the previous item's rows "resident" whenever
+    that item was the segment above in the same strip of a different frame.  Full config-4 size: every CTA handles
+    several items; compared with the direct kernel (no shared-memory window)."""
+    B, C, H, W = 8, 3, 1152, 1984
+    g = torch.Generator(device="cuda").manual_seed(77)
+    I = torch.rand(B, C, H, W, device="cuda", generator=g)
+    fl = torch.zeros(B, 2, H, W, device="cuda")
+    fl[:, 1] = -6.0
+    rows = torch.arange(H, device="cuda")
+    for segt in (36, 32, 24, 18, 16, 12, 9, 8):                  # segment lengths the launcher may choose at this size
+        fl[:, 0, (rows // 4) % segt == 0, :] = float(W)           # |fx| >= W/2: out of range (:2735-2736)
+    ft = torch.softmax(torch.randn(B, 16, H, W, device="cuda", generator=g), 1)
+    off = (torch.rand(B, 32, H, W, device="cuda", generator=g) - 0.5) * 0.9
+    args = (I, fl, ft) if variant == "ori" else (I, fl, ft, off)
+    mod = lib.FilterInterpolationModule() if variant == "ori" else lib.FilterInterpolationModule(variant)
+    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    ref = mod(*args)
+    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    for _ in range(4):   # the item-to-CTA assignment is dynamic: several draws
+        out = mod(*args)
+        assert (out - ref).abs().max().item() < 3e-6
+
+
+# ------------------------------------------------------------------------------ backward: warp-tile vs per-pixel kernel
+@pytest.mark.parametrize("variant", ["ori", "dkr", "deforconv", "nofilterwithdeforconv"])
+@pytest.mark.parametrize("B,C,H,W,fk", [(2, 3, 131, 200, "stress"), (1, 3, 96, 256, "smooth"), (1, 3, 120, 224, "wild"),
+                                        (1, 5, 37, 70, "gauss"), (2, 1, 9, 33, "unit"), (1, 3, 64, 160, "compress")])
+def test_fi_backward_warp_tile_kernel(lib, oracle, monkeypatch, variant, B, C, H, W, fk):
+    """fi_tile_bwd.cu (warp-private shared-memory accumulation of the image gradient, duplicate window origins
+    ranked with match_any, border pixels and oversized boxes on global REDs) against the oracle and against the
+    per-pixel kernel.  "compress": a flow that maps runs of neighbouring pixels onto the same window origin."""
+    r = U.rng(2500 + H + W + len(variant))
+    I = U.image(r, B, C, H, W)
+    if fk == "compress":
+        xs = np.arange(W, dtype=np.float32)
+        fl = np.zeros((B, 2, H, W), np.float32)
+        fl[:, 0] = (np.floor(xs / 4) * 4 - xs + 0.25)[None, None, :]      # x + fx = 4*floor(x/4) + 0.25: 4 lanes per origin
+        fl[:, 1] = 0.5
+    elif fk in ("uniform_motion", "shear", "wild", "jump_back"):
+        fl = big_flow(r, B, H, W, fk)
+    else:
+        fl = U.flow(r, B, H, W, fk)
+    ft, off = U.filt(r, B, 4, H, W, "uniform"), U.offsets(r, B, 4, H, W, 0.45)
+    g = r.standard_normal((B, C, H, W)).astype(np.float32)
+    args = (I, fl, off) if variant == "nofilterwithdeforconv" else ((I, fl, ft) if variant == "ori" else (I, fl, ft, off))
+    mod = lib.FilterInterpolationModule() if variant == "ori" else lib.FilterInterpolationModule(variant)
+
+    def grads():
+        ts = [cu(a).requires_grad_() for a in args]
+        mod(*ts).backward(cu(g))
+        return [host(t.grad) for t in ts]
+
+    tile = grads()
+    monkeypatch.setenv("VFIDKR_FI_BWD_PATH", "direct")
+    direct = grads()
+    monkeypatch.delenv("VFIDKR_FI_BWD_PATH")
+    if variant == "nofilterwithdeforconv":
+        gi1, gi2, gi3, _ = oracle.fi_backward(variant, I, fl, off, None, g)
+        refs = [gi1, gi2, gi3]
+    elif variant == "ori":
+        gi1, gi2, gi3, _ = oracle.fi_backward(variant, I, fl, ft, None, g)
+        refs = [gi1, gi2, gi3]
+    else:
+        refs = list(oracle.fi_backward(variant, I, fl, ft, off, g))
+    for k, (a, d, ref) in enumerate(zip(tile, direct, refs)):
+        tol = U.RTOL_ATOMIC if k == 0 else U.RTOL_FWD   # gi1 is accumulated (order differs), the rest is thread-private
+        U.assert_close(a, ref, tol, f"{variant} warp-tile backward, grad {k + 1}")
+        U.assert_close(d, ref, tol, f"{variant} per-pixel backward, grad {k + 1}")

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Stress check of the FI forward strip kernel at full size: repeated runs against the direct kernel."""
+import os, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import torch
+import vfidkr_b200 as V
+
+iters = int(sys.argv[1]) if len(sys.argv) > 1 else 40
+torch.manual_seed(1800)
+B, C, H, W = 8, 3, 1152, 1984
+I = torch.rand(B, C, H, W, device="cuda")
+ft = torch.softmax(torch.randn(B, 16, H, W, device="cuda"), dim=1)
+fi = V.FilterInterpolationModule()
+flows = {
+    "iid": (torch.randn(B, 2, H, W, device="cuda") * 4).clamp_(-20, 20),
+    "up4": torch.nn.functional.interpolate((torch.randn(B, 2, H // 4, W // 4, device="cuda") * 4).clamp_(-20, 20),
+                                           scale_factor=4, mode="bilinear", align_corners=False).contiguous(),
+}
+
+def run(path, fl, img=I):
+    os.environ["VFIDKR_FI_FWD_PATH"] = path
+    return fi(img, fl, ft)
+
+for name, fl in flows.items():
+    ref = run("direct", fl)
+    torch.cuda.synchronize()
+    nbad = 0
+    for it in range(iters):
+        # perturb timing: some iterations run with a concurrent memory-bound kernel queued right before
+        if it % 3 == 1:
+            junk = torch.rand(64 << 20, device="cuda")
+        o = run("strip", fl)
+        d = (o - ref).abs()
+        bad = (d > 1e-5).nonzero()
+        if bad.shape[0]:
+            nbad += 1
+            bb = bad.cpu()
+            ys, xs = bb[:, 2], bb[:, 3]
+            print(f"{name} iter {it}: max diff {d.max().item():.3e}, bad pixels {bb.shape[0]}")
+            print("  batch items:", torch.unique(bb[:, 0]).tolist(), "channels:", torch.unique(bb[:, 1]).tolist())
+            print("  rows: min", ys.min().item(), "max", ys.max().item(), "tile rows:", torch.unique(ys // 4).tolist()[:30])
+            print("  cols: min", xs.min().item(), "max", xs.max().item(), "strips:", torch.unique(xs // 128).tolist())
+            for r in bb[:8].tolist():
+                b_, c_, y_, x_ = r
+                print("   ", r, "got", o[b_, c_, y_, x_].item(), "ref", ref[b_, c_, y_, x_].item(),
+                      "flow", fl[b_, 0, y_, x_].item(), fl[b_, 1, y_, x_].item())
+    print(f"{name}: {nbad} bad runs of {iters}")

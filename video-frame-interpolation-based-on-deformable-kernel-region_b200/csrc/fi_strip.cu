@@ -162,15 +162,18 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 
         int xorg = 0, base = 0, hi = 0;   // window state: rows [max(base, hi - RROWS), hi) are resident
         int b = 0, bx = 0, ty = 0, left = 0;
+        // The window of one item must never serve the next: `stale` is raised at every item start and cleared only by
+        // a re-base.  (It has to survive tiles that do not touch the window -- MODE_GLOBAL / MODE_NONE -- or the first
+        // shared-memory tile after them could find the previous item's rows "resident".)
+        bool stale = true;
 #pragma unroll 1
         for (int t = 0;; ++t) {
-            bool new_item = false;
             if (left == 0) {
                 ++item_no;
                 draw_items(item_no + 1);
                 if (!decode_item(item_no, b, bx, ty)) break;
                 left = segt;
-                new_item = true;
+                stale = true;
             } else {
                 ++ty;
             }
@@ -191,7 +194,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                     mode = MODE_GLOBAL;   // the tile's box does not fit the window at all
                 } else {
                     mode = MODE_SMEM;
-                    const bool rebase = new_item || bb.xmin < xorg || bb.xmax >= xorg + WB || bb.ymin < max(base, hi - RROWS);
+                    const bool rebase = stale || bb.xmin < xorg || bb.xmax >= xorg + WB || bb.ymin < max(base, hi - RROWS);
                     // bbox_done(t) means every compute warp has started tile t - LEAD: older tiles are consumed.  (Only
                     // these last LEAD tiles may be waited on: their tile_done phase is the barrier's current one.)
                     int oldest = max(0, t - LEAD);
@@ -200,6 +203,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                         for (; oldest < t; ++oldest) wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1));
                         xorg = (bb.xmin - (slack >= 14 ? slack / 2 : 0)) & ~7;   // sector-aligned, box centred when it can be
                         base = hi = bb.ymin;
+                        stale = false;
                     }
                     if (bb.ymin > hi) base = hi = bb.ymin;   // jumped ahead: nothing older is needed any more
                     // loading row y reuses the slot of row y - RROWS: every tile still in flight must be past it

@@ -129,9 +129,9 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         // stream 2: the image window, driven by the bounding boxes (see fi_strip.cu)
         int xorg = 0, base = 0, hi = 0;
         int b = 0, bx = 0, ty = 0, left = 0, item_no = -1;
+        bool stale = true;   // raised at every item start, cleared only by a re-base (see fi_strip.cu)
         for (int t = 0; t < n; ++t) {
-            bool new_item = false;
-            if (left == 0) { ++item_no; decode_item(item_no, b, bx, ty); left = segt; new_item = true; }
+            if (left == 0) { ++item_no; decode_item(item_no, b, bx, ty); left = segt; stale = true; }
             else ++ty;
             --left;
             const int sb = t % NB;
@@ -152,12 +152,13 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                     mode = MODE_GLOBAL;
                 } else {
                     mode = MODE_SMEM;
-                    const bool rebase = new_item || bb.xmin < xorg || bb.xmax >= xorg + WB || bb.ymin < max(base, hi - RROWS);
+                    const bool rebase = stale || bb.xmin < xorg || bb.xmax >= xorg + WB || bb.ymin < max(base, hi - RROWS);
                     int oldest = max(0, t - LEAD);   // bbox_done(t): every compute warp has started tile t - LEAD
                     if (rebase) {
                         for (; oldest < t; ++oldest) wait_pumping(&tile_done[oldest % NB], (uint32_t)((oldest / NB) & 1));
                         xorg = (bb.xmin - (slack >= 14 ? slack / 2 : 0)) & ~7;
                         base = hi = bb.ymin;
+                        stale = false;
                     }
                     if (bb.ymin > hi) base = hi = bb.ymin;
                     for (;;) {

@@ -26,6 +26,9 @@ int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, f
                          int B, int C, int H, int W, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
 int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
                          int B, int C, int H, int W, cudaStream_t s);   // fi_strip_dkr.cu; -1 = not applicable
+int fi_tile_backward(int variant, const float *in1, const float *in2, const float *in3, const float *in4,
+                     const float *gout, float *gi1, float *gi2, float *gi3, float *gi4,
+                     int B, int C, int H, int W, cudaStream_t s);       // fi_tile_bwd.cu; -1 = not applicable
 
 namespace {
 
@@ -46,6 +49,13 @@ inline int forced_forward_path()
     if (e[0] == 't') return PATH_TILE;
     if (e[0] == 'd') return PATH_DIRECT;
     return PATH_AUTO;
+}
+
+// VFIDKR_FI_BWD_PATH=direct forces the per-pixel backward kernel (tests compare it with the tile kernel)
+inline bool forced_backward_direct()
+{
+    const char *e = std::getenv("VFIDKR_FI_BWD_PATH");
+    return e && e[0] == 'd';
 }
 
 // resident blocks per SM the register allocator must leave room for
@@ -534,6 +544,11 @@ int launch_backward(const float *in1, const float *in2, const float *in3, const 
     if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
     int e = set_error(cudaMemsetAsync(gi1, 0, sizeof(float) * (size_t)B * C * H * W, s), "clear gradinput1");
     if (e) return e;
+    if (F == 4 && !forced_backward_direct()) {
+        // production path: shared-memory tiles (staged image region, shared-memory gradient accumulation)
+        const int r = fi_tile_backward(V, in1, in2, in3, in4, gout, gi1, gi2, gi3, gi4, B, C, H, W, s);
+        if (r >= 0) return r;
+    }
     dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
     if (F == 4) {
         if (C == 3) fi_backward_kernel<V, 4, 3><<<grid, block, 0, s>>>(in1, in2, in3, in4, gout, gi1, gi2, gi3, gi4, C, H, W, F);
