@@ -9,7 +9,11 @@
 //     and loops channels inside, instead of re-reading them from HBM for every channel;
 //   * the backward fuses the reference's 3 (ori) / 5 (DKR) passes over the taps into one and
 //     accumulates the thread-private gradients (flow, filter, offsets) in registers with plain
-//     stores -- only the image gradient, which really scatters, uses RED atomics;
+//     stores -- only the image gradient, which really scatters, uses RED atomics.  Two shared-memory
+//     accumulation schemes for that scatter were built and measured slower than the REDs (CTA tile
+//     with shared atomics: fp32 atomicAdd on shared memory is an ATOMS.CAST.SPIN retry loop, 4100
+//     instructions per warp; warp-private tile with ranked duplicates: twice the instructions and
+//     the shared-memory carve-out leaves ~30 KB of L1 for the image gathers) -- see DESIGN.md 4.2;
 //   * out-of-range pixels write their zeros/copies themselves, so no buffer but gradinput1
 //     needs clearing;
 //   * 64-bit plane offsets (B*C*H*W exceeds 2^31 for the 196-channel context tensors at 1080p).
@@ -26,9 +30,6 @@ int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, f
                          int B, int C, int H, int W, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
 int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
                          int B, int C, int H, int W, cudaStream_t s);   // fi_strip_dkr.cu; -1 = not applicable
-int fi_tile_backward(int variant, const float *in1, const float *in2, const float *in3, const float *in4,
-                     const float *gout, float *gi1, float *gi2, float *gi3, float *gi4,
-                     int B, int C, int H, int W, cudaStream_t s);       // fi_tile_bwd.cu; -1 = not applicable
 
 namespace {
 
@@ -49,13 +50,6 @@ inline int forced_forward_path()
     if (e[0] == 't') return PATH_TILE;
     if (e[0] == 'd') return PATH_DIRECT;
     return PATH_AUTO;
-}
-
-// VFIDKR_FI_BWD_PATH=direct forces the per-pixel backward kernel (tests compare it with the tile kernel)
-inline bool forced_backward_direct()
-{
-    const char *e = std::getenv("VFIDKR_FI_BWD_PATH");
-    return e && e[0] == 'd';
 }
 
 // resident blocks per SM the register allocator must leave room for
@@ -410,12 +404,35 @@ fi_backward_kernel(const float *__restrict__ in1, const float *__restrict__ in2,
 #pragma unroll 1
         for (int j = 0; j < F; ++j) {
             const int cy = clampi(p.T + j, 0, H - 1);
+            // Everything one tap row reads from HBM (filter taps, offsets) is requested before the first use: issued
+            // tap by tap, each load sat behind the previous tap's REDs / stores and a warp paid 16 DRAM round trips
+            // in sequence (ncu: 58 % of the stall samples on the first use of the tap weight; 2.34 -> 1.23 ms at
+            // 1080p x 8).  Requesting a row further ahead was measured slower (2.14 ms).
+            constexpr int FR = FT > 0 ? FT : 1;
+            float wrow[FR], oyrow[FR], oxrow[FR];
+            if (FT > 0) {
+#pragma unroll
+                for (int i = 0; i < FR; ++i) {
+                    const int k = j * F + i;
+                    wrow[i] = (V == V_NOFILT) ? 1.0f : ld_stream(wp + (size_t)k * HW);
+                    if (V != V_ORI) { oyrow[i] = ld_stream(op + (size_t)k * HW); oxrow[i] = ld_stream(op + (size_t)(T2 + k) * HW); }
+                }
+            }
+            float vrow[FR][CCH];
+            if (FT > 0 && V == V_ORI) {
+#pragma unroll
+                for (int i = 0; i < FT; ++i) {
+                    const int a = cy * W + clampi(p.L + i, 0, W - 1);
+#pragma unroll
+                    for (int cc = 0; cc < CCH; ++cc) vrow[i][cc] = (c0 + cc < C) ? __ldg(pl + (size_t)cc * HW + a) : 0.0f;
+                }
+            }
 #pragma unroll
             for (int i = 0; i < (FT > 0 ? FT : F); ++i) {
                 const int cx = clampi(p.L + i, 0, W - 1);
                 const int k = j * F + i;
                 const int a = cy * W + cx;
-                const float wgt = (V == V_NOFILT) ? 1.0f : __ldg(wp + (size_t)k * HW);
+                const float wgt = (V == V_NOFILT) ? 1.0f : (FT > 0 ? wrow[FT > 0 ? i : 0] : __ldg(wp + (size_t)k * HW));
                 float s3 = 0.0f, soy = 0.0f, sox = 0.0f;
                 if (V == V_ORI) {
                     const QuadCoef qc = quad_coef(j < F / 2, i < F / 2, p.alpha, p.beta);
@@ -423,7 +440,7 @@ fi_backward_kernel(const float *__restrict__ in1, const float *__restrict__ in2,
                     for (int cc = 0; cc < CCH; ++cc)
                         if (c0 + cc < C) {
                             const float gq = g[cc] * qc.q;                       // TL_grad (:2885)
-                            const float v = __ldg(pl + (size_t)cc * HW + a);
+                            const float v = FT > 0 ? vrow[FT > 0 ? i : 0][cc] : __ldg(pl + (size_t)cc * HW + a);
                             red_add(gpl + (size_t)cc * HW + a, gq * wgt);       // :2890-2892
                             s3 += gq * v;                                       // :2893-2895
                             const float t = g[cc] * (v * wgt);
@@ -431,19 +448,26 @@ fi_backward_kernel(const float *__restrict__ in1, const float *__restrict__ in2,
                             gy += qc.cy * t;
                         }
                 } else {
-                    const float oy = __ldg(op + (size_t)k * HW), ox = __ldg(op + (size_t)(T2 + k) * HW);
+                    const float oy = FT > 0 ? oyrow[FT > 0 ? i : 0] : __ldg(op + (size_t)k * HW);
+                    const float ox = FT > 0 ? oxrow[FT > 0 ? i : 0] : __ldg(op + (size_t)(T2 + k) * HW);
                     const Deform d = fi_deform(cy, cx, oy, ox, p, H, W);
                     const bool top = (V == V_DKR) ? (j < F / 2) : d.top;
                     const bool left = (V == V_DKR) ? (i < F / 2) : d.left;
                     const QuadCoef qc = quad_coef(top, left, p.alpha, p.beta);
                     const float PTL = (1 - d.phiX) * (1 - d.phiY), PTR = d.phiX * (1 - d.phiY);
                     const float PBL = (1 - d.phiX) * d.phiY, PBR = d.phiY * d.phiX;
+                    float vc[CCH][4];
 #pragma unroll
                     for (int cc = 0; cc < CCH; ++cc)
                         if (c0 + cc < C) {
                             const float *qp = pl + (size_t)cc * HW;
-                            const float vTL = __ldg(qp + d.aTL), vTR = __ldg(qp + d.aTR);
-                            const float vBL = __ldg(qp + d.aBL), vBR = __ldg(qp + d.aBR);
+                            vc[cc][0] = __ldg(qp + d.aTL); vc[cc][1] = __ldg(qp + d.aTR);
+                            vc[cc][2] = __ldg(qp + d.aBL); vc[cc][3] = __ldg(qp + d.aBR);
+                        }
+#pragma unroll
+                    for (int cc = 0; cc < CCH; ++cc)
+                        if (c0 + cc < C) {
+                            const float vTL = vc[cc][0], vTR = vc[cc][1], vBL = vc[cc][2], vBR = vc[cc][3];
                             const float S = PTL * vTL + PTR * vTR + PBL * vBL + PBR * vBR;
                             const float dSy = -(1 - d.phiX) * vTL + (1 - d.phiX) * vBL - d.phiX * vTR + d.phiX * vBR;  // :986-989
                             const float dSx = -(1 - d.phiY) * vTL + (1 - d.phiY) * vTR - d.phiY * vBL + d.phiY * vBR;  // :1104-1107
@@ -544,11 +568,6 @@ int launch_backward(const float *in1, const float *in2, const float *in3, const 
     if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
     int e = set_error(cudaMemsetAsync(gi1, 0, sizeof(float) * (size_t)B * C * H * W, s), "clear gradinput1");
     if (e) return e;
-    if (F == 4 && !forced_backward_direct()) {
-        // production path: shared-memory tiles (staged image region, shared-memory gradient accumulation)
-        const int r = fi_tile_backward(V, in1, in2, in3, in4, gout, gi1, gi2, gi3, gi4, B, C, H, W, s);
-        if (r >= 0) return r;
-    }
     dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
     if (F == 4) {
         if (C == 3) fi_backward_kernel<V, 4, 3><<<grid, block, 0, s>>>(in1, in2, in3, in4, gout, gi1, gi2, gi3, gi4, C, H, W, F);

@@ -45,15 +45,18 @@ __device__ __forceinline__ Corners corners(int w_i, int h_i, float fx, float fy,
 // S; the box pass below then forms, with the reference's border behaviour (R = min(L+1, W-1), Bm = min(T+1, H-1):
 // a block on the last column / row hits that column / row twice),
 //   A[y][x] = sum_{dy,dx in {0,1}} wy(y,dy) * wx(x,dx) * S[y-dy][x-dx],   w(.,1) = 1,  wx(x,0) = (x == W-1 ? 2 : 1), wy alike.
+// `clear` (may be null): the scratch image of the NEXT chunk of frames, zeroed here cell for cell (plain write-back
+// stores: the lines stay in L2, where that chunk's REDs will find them).
 template <bool DEPTH>
 __global__ void __launch_bounds__(BX *BY)
 projection_splat_kernel(const float *__restrict__ flow, const float *__restrict__ depth, float4 *__restrict__ S,
-                        int H, int W)
+                        float4 *__restrict__ clear, int H, int W)
 {
     const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
     if (w_i >= W || h_i >= H) return;
     const int b = blockIdx.z;
     const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
+    if (clear) clear[(size_t)b * HW + pix] = make_float4(0.f, 0.f, 0.f, 0.f);
     const float fx = ld_stream(flow + ((size_t)b * 2 + 0) * HW + pix);
     const float fy = ld_stream(flow + ((size_t)b * 2 + 1) * HW + pix);
     const Corners c = corners(w_i, h_i, fx, fy, W, H);
@@ -127,6 +130,26 @@ projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count
 
 // hole filling (:171-232).  Reads only non-hole pixels (count != 0), which this kernel never writes,
 // so running it in place is race-free.  The four scans are unbounded as in the reference.
+// One scan direction of the hole filling: the count of the nearest pixel with count != 0 walking from (h_i, w_i) in
+// steps of `step` elements (at most `room` of them), and how many steps away it is; 0 when the scan leaves the
+// plane first (the reference's loop then ends with the last count read, which is 0: :175-213).  The reference
+// reads one pixel per iteration; here SCAN pixels are requested at once, so a hole of width n costs n / SCAN
+// dependent round trips instead of n.
+constexpr int SCAN = 8;
+__device__ __forceinline__ float scan_nonhole(const float *__restrict__ c, long long step, int room, int &dist)
+{
+    for (int base = 0; base < room; base += SCAN) {
+        float v[SCAN];
+#pragma unroll
+        for (int k = 0; k < SCAN; ++k) v[k] = (base + k < room) ? __ldg(c + (long long)(base + k + 1) * step) : 0.0f;
+#pragma unroll
+        for (int k = 0; k < SCAN; ++k)
+            if (v[k] != 0.0f) { dist = base + k + 1; return v[k]; }
+    }
+    dist = room;
+    return 0.0f;
+}
+
 __global__ void __launch_bounds__(BX *BY)
 projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ out, int H, int W)
 {
@@ -134,27 +157,23 @@ projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ 
     if (w_i >= W || h_i >= H) return;
     const int b = blockIdx.z;
     const size_t HW = (size_t)H * W;
-    const float *cn = count + (size_t)b * HW;
-    if (cn[(size_t)h_i * W + w_i] > 0.0f) return;
-    int lo = w_i; float lt = 0.0f;
-    while (lt == 0.0f && lo - 1 >= 0) { --lo; lt = cn[(size_t)h_i * W + lo]; }
-    int ro = w_i; float rt = 0.0f;
-    while (rt == 0.0f && ro + 1 <= W - 1) { ++ro; rt = cn[(size_t)h_i * W + ro]; }
-    int uo = h_i; float ut = 0.0f;
-    while (ut == 0.0f && uo - 1 >= 0) { --uo; ut = cn[(size_t)uo * W + w_i]; }
-    int dn = h_i; float dt = 0.0f;
-    while (dt == 0.0f && dn + 1 <= H - 1) { ++dn; dt = cn[(size_t)dn * W + w_i]; }
+    const float *cn = count + (size_t)b * HW + (size_t)h_i * W + w_i;
+    if (__ldcs(cn) > 0.0f) return;
+    int dl, dr, du, dd;
+    const float lt = scan_nonhole(cn, -1, w_i, dl);
+    const float rt = scan_nonhole(cn, 1, W - 1 - w_i, dr);
+    const float ut = scan_nonhole(cn, -(long long)W, h_i, du);
+    const float dt = scan_nonhole(cn, W, H - 1 - h_i, dd);
     if (lt + rt + ut + dt <= 0.0f) return;
     const float l = lt > 0.0f ? 1.f : 0.f, r = rt > 0.0f ? 1.f : 0.f;
     const float u = ut > 0.0f ? 1.f : 0.f, d = dt > 0.0f ? 1.f : 0.f;
     const float den = l + r + u + d;
 #pragma unroll
     for (int ch = 0; ch < 2; ++ch) {
-        float *o = out + ((size_t)b * 2 + ch) * HW;
-        // volatile-free plain loads: the sources are non-hole pixels, final since the averaging pass
-        const float v = l * o[(size_t)h_i * W + lo] + r * o[(size_t)h_i * W + ro] +
-                        u * o[(size_t)uo * W + w_i] + d * o[(size_t)dn * W + w_i];
-        o[(size_t)h_i * W + w_i] = v / den;
+        float *o = out + ((size_t)b * 2 + ch) * HW + (size_t)h_i * W + w_i;
+        // plain loads: the sources are non-hole pixels, final since the averaging pass and never written here
+        const float v = l * o[-dl] + r * o[dr] + u * o[-(long long)du * W] + d * o[(long long)dd * W];
+        *o = v / den;
     }
 }
 
@@ -227,18 +246,34 @@ int projection_forward(const float *flow, const float *depth, float *count, floa
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !flow || !count || !out || (DEPTH && !depth)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
+    // The scratch image is kept L2-RESIDENT: frames are processed in chunks whose scratch (16 B per pixel) is at
+    // most SCRATCH_BYTES, two such buffers alternate, and the splat of one chunk clears the buffer of the next.
+    // The REDs and the box pass then run against L2 instead of HBM (ncu before: 731 MB of DRAM traffic per 1080p x 8
+    // splat for 219 MB of input, 66 % of the DRAM peak).  A frame larger than the budget is its own chunk.
+    constexpr size_t SCRATCH_BYTES = 40u << 20;
+    const int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, SCRATCH_BYTES / (sizeof(float4) * HW)));
+    const int nchunks = (B + per_chunk - 1) / per_chunk;
+    const size_t chunk_cells = (size_t)per_chunk * HW;
     void *scratch = nullptr;
-    int e = stream_scratch_alloc(&scratch, sizeof(float4) * B * HW, s);
+    int e = stream_scratch_alloc(&scratch, sizeof(float4) * chunk_cells * (nchunks > 1 ? 2 : 1), s);
     if (e) return e;
     float4 *S = static_cast<float4 *>(scratch);
-    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * B * HW, s), "clear projection scratch");
+    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * chunk_cells, s), "clear projection scratch");
     if (!e) {
-        dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
-        projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(flow, depth, S, H, W);
-        dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), B);
-        projection_finish_kernel<<<fgrid, fblock, 0, s>>>(S, count, out, H, W);
-        note_launch(2);
+        for (int c = 0; c < nchunks; ++c) {
+            const int b0 = c * per_chunk, nb = std::min(per_chunk, B - b0);
+            float4 *cur = S + (size_t)(c & 1) * chunk_cells;
+            float4 *nxt = (c + 1 < nchunks) ? S + (size_t)((c + 1) & 1) * chunk_cells : nullptr;
+            dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), nb);
+            // the next chunk may be shorter than this one; clearing nb frames of it is always enough or more
+            projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(flow + (size_t)b0 * 2 * HW, DEPTH ? depth + (size_t)b0 * HW : nullptr,
+                                                                   cur, nxt, H, W);
+            dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), nb);
+            projection_finish_kernel<<<fgrid, fblock, 0, s>>>(cur, count + (size_t)b0 * HW, out + (size_t)b0 * 2 * HW, H, W);
+            note_launch(2);
+        }
         if (fillhole) {
+            dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
             projection_fillhole_kernel<<<grid, block, 0, s>>>(count, out, H, W);
             note_launch();
         }
