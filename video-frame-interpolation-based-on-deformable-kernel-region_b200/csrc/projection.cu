@@ -69,7 +69,7 @@ projection_splat_kernel(const float *__restrict__ flow, const float *__restrict_
 // Box pass + averaging (:128-135).  One warp owns a 32-column block of a row segment and walks it downwards,
 // carrying the horizontally summed previous row in registers: S is read once (plus one halo row per segment and
 // one halo column per block), count and output are written once, planar.
-constexpr int FIN_ROWS = 32, FIN_WARPS = 4, FIN_UNROLL = 4;
+constexpr int FIN_ROWS = 8, FIN_WARPS = 4, FIN_UNROLL = 4;   // short segments: one frame per launch must still fill 148 SMs
 
 // raw loads of one row: this lane's cell and (lane 0 only) the cell left of the block
 __device__ __forceinline__ void load_row(const float4 *__restrict__ Srow, int x, int W, int lane, bool valid,
@@ -150,30 +150,51 @@ __device__ __forceinline__ float scan_nonhole(const float *__restrict__ c, long 
     return 0.0f;
 }
 
+// Holes are sparse (a few per cent of the pixels) but scattered, so with one thread per pixel most warps would run
+// the scans for one or two live lanes.  The CTA therefore first COMPACTS its holes into a shared list (ballot +
+// one shared atomic per warp) and then fills them with dense warps.
 __global__ void __launch_bounds__(BX *BY)
 projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ out, int H, int W)
 {
+    __shared__ int s_n;
+    __shared__ unsigned short s_list[BX * BY];
+    const int tid = threadIdx.y * BX + threadIdx.x, lane = threadIdx.x;
     const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
-    if (w_i >= W || h_i >= H) return;
     const int b = blockIdx.z;
     const size_t HW = (size_t)H * W;
-    const float *cn = count + (size_t)b * HW + (size_t)h_i * W + w_i;
-    if (__ldcs(cn) > 0.0f) return;
-    int dl, dr, du, dd;
-    const float lt = scan_nonhole(cn, -1, w_i, dl);
-    const float rt = scan_nonhole(cn, 1, W - 1 - w_i, dr);
-    const float ut = scan_nonhole(cn, -(long long)W, h_i, du);
-    const float dt = scan_nonhole(cn, W, H - 1 - h_i, dd);
-    if (lt + rt + ut + dt <= 0.0f) return;
-    const float l = lt > 0.0f ? 1.f : 0.f, r = rt > 0.0f ? 1.f : 0.f;
-    const float u = ut > 0.0f ? 1.f : 0.f, d = dt > 0.0f ? 1.f : 0.f;
-    const float den = l + r + u + d;
+    const float *cnb = count + (size_t)b * HW;
+    if (tid == 0) s_n = 0;
+    __syncthreads();
+    const bool hole = w_i < W && h_i < H && !(__ldcs(cnb + (size_t)h_i * W + w_i) > 0.0f);
+    const unsigned m = __ballot_sync(0xffffffffu, hole);
+    if (m) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_n, __popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hole) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)tid;
+    }
+    __syncthreads();
+    const int n = s_n;
+    for (int q = tid; q < n; q += BX * BY) {
+        const int t = s_list[q];
+        const int x = blockIdx.x * BX + (t & (BX - 1)), y = blockIdx.y * BY + t / BX;
+        const float *cn = cnb + (size_t)y * W + x;
+        int dl, dr, du, dd;
+        const float lt = scan_nonhole(cn, -1, x, dl);
+        const float rt = scan_nonhole(cn, 1, W - 1 - x, dr);
+        const float ut = scan_nonhole(cn, -(long long)W, y, du);
+        const float dt = scan_nonhole(cn, W, H - 1 - y, dd);
+        if (lt + rt + ut + dt <= 0.0f) continue;
+        const float l = lt > 0.0f ? 1.f : 0.f, r = rt > 0.0f ? 1.f : 0.f;
+        const float u = ut > 0.0f ? 1.f : 0.f, d = dt > 0.0f ? 1.f : 0.f;
+        const float den = l + r + u + d;
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-        float *o = out + ((size_t)b * 2 + ch) * HW + (size_t)h_i * W + w_i;
-        // plain loads: the sources are non-hole pixels, final since the averaging pass and never written here
-        const float v = l * o[-dl] + r * o[dr] + u * o[-(long long)du * W] + d * o[(long long)dd * W];
-        *o = v / den;
+        for (int ch = 0; ch < 2; ++ch) {
+            float *o = out + ((size_t)b * 2 + ch) * HW + (size_t)y * W + x;
+            // plain loads: the sources are non-hole pixels, final since the averaging pass and never written here
+            const float v = l * o[-dl] + r * o[dr] + u * o[-(long long)du * W] + d * o[(long long)dd * W];
+            *o = v / den;
+        }
     }
 }
 
