@@ -417,16 +417,29 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
         if (num_tiles >= (1ll << 31)) return VFIDKR_ERR_ARG;
         const FastDiv dx((unsigned)tiles_x), di((unsigned)(tiles_x * tiles_y));
         CUtensorMap m1, m2;
-        const bool tma = (W % 4 == 0) && aligned16(input1) && aligned16(input2) &&
+        // (TMA box origins are kept at multiples of 4 elements: pad != max_displacement shifts them by md - pad, and an
+        // origin of -2 was observed to fault -- such configurations, which VFIDKR never uses, take the cp.async path)
+        const bool tma = ((md - pad) % 4 == 0) && (W % 4 == 0) && aligned16(input1) && aligned16(input2) &&
                          encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
                          encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK);
         if (!tma) { memset(&m1, 0, sizeof m1); memset(&m2, 0, sizeof m2); }
         // Too few tiles to fill the machine (the two coarsest PWC levels at 1080p): split the channels over
         // ksplit work items per tile and add the partial volumes in a second, tiny kernel.
         const int nchunks = (C + CK - 1) / CK;
+        // The slice count is chosen by cost, not by "as many items as CTA slots": an item costs its chunks plus ~2
+        // chunk-times of pipeline fill / partial write, and items are dealt in rounds of (2 x SMs).  (80 tiles x 16
+        // chunks at PWC level 5: 4 slices made 320 items = 2 rounds of 4 chunks; 3 slices make 240 items = 1 round of 6.)
         int ksplit = 1;
-        if (num_tiles <= (long long)sm_count())
-            ksplit = (int)std::min<long long>(nchunks, (2ll * sm_count() + num_tiles - 1) / num_tiles);
+        if (num_tiles <= (long long)sm_count()) {
+            const long long slots = 2ll * sm_count();
+            long long best = -1;
+            for (int ks = 1; ks <= nchunks; ++ks) {
+                const int cp = (nchunks + ks - 1) / ks, eff = (nchunks + cp - 1) / cp;
+                const long long rounds = (num_tiles * eff + slots - 1) / slots;
+                const long long cost = rounds * (cp + 2) + (eff > 1 ? 1 : 0);   // + the reduce kernel
+                if (best < 0 || cost < best) { best = cost; ksplit = eff; }
+            }
+        }
         const int cps = (nchunks + ksplit - 1) / ksplit;
         ksplit = (nchunks + cps - 1) / cps;   // drop slices that would be empty
         const long long num_items = num_tiles * ksplit;
