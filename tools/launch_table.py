@@ -18,7 +18,8 @@ def main(path):
             continue
         d[r[ki]][0] += 1
         d[r[ki]][1] += float(r[vi].replace(",", ""))
-    ours = {k: v for k, v in d.items() if "vfidkr" in k or "strip::" in k}
+    mine = ("corr_", "fi_forward", "fi_backward", "projection_", "interp_", "sepconv")
+    ours = {k: v for k, v in d.items() if any(m in k for m in mine)}
     tot = sum(v[1] for v in ours.values())
     print(f"| kernel (libvfidkr_b200.so) | launches | total us | us / launch | share of our kernels |")
     print("|---|---|---|---|---|")

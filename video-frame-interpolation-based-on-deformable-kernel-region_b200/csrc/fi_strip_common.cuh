@@ -15,7 +15,7 @@ namespace strip {
 constexpr int TW = 128, TH = 4, NPIX = TW * TH;    // tile = 512 pixels, one per compute thread
 constexpr int NCOMP_WARPS = NPIX / 32;             // 16 compute warps
 constexpr int NTHREADS = NPIX + 32;                // + 1 producer warp
-constexpr int LEAD = 3;                            // flow / bounding box / image window run this many tiles ahead
+constexpr int LEAD = 4;                            // flow / bounding box / image window run this many tiles ahead
 constexpr int NB = 8;                              // ring of bounding boxes and tile descriptors (> LEAD)
 constexpr int WB = 160;                            // columns held by the rolling window (tile + 16 either side)
 constexpr int RROWS = 48;                          // rows held by the rolling window (a ring indexed by y % RROWS)
