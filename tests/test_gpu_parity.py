@@ -575,3 +575,24 @@ def test_fi_backward_all_families_hard_flows(lib, oracle, variant, B, C, H, W, f
     for k, (a, ref) in enumerate(zip(got, refs)):
         tol = U.RTOL_ATOMIC if k == 0 else U.RTOL_FWD   # gi1 is accumulated atomically, the rest is thread-private
         U.assert_close(a, ref, tol, f"{variant} backward, grad {k + 1}")
+
+
+# ------------------------------------------------------------------------------ many-channel forward (fi_bigc.cu)
+@pytest.mark.parametrize("B,C,H,W,fk", [(1, 196, 40, 128, "smooth"), (2, 9, 37, 132, "stress"), (1, 16, 64, 160, "wild"),
+                                        (1, 7, 20, 64, "unit"), (1, 24, 50, 96, "uniform_motion"), (1, 12, 33, 68, "gauss")])
+def test_fi_ori_many_channel_kernel(lib, oracle, monkeypatch, B, C, H, W, fk):
+    """fi_bigc.cu (C > 4: image regions streamed channel group by channel group through shared memory, taps in
+    registers) against the oracle and the direct kernel: staged tiles, oversized boxes (global fallback), channel
+    counts that are not a multiple of the group size, ragged tiles, out-of-range pixels."""
+    r = U.rng(2700 + C + H + W)
+    I = U.image(r, B, C, H, W)
+    fl = big_flow(r, B, H, W, fk) if fk in ("uniform_motion", "shear", "wild", "jump_back") else U.flow(r, B, H, W, fk)
+    ft = U.filt(r, B, 4, H, W, "uniform")
+    a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
+    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    b = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
+    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    ref = oracle.fi_forward("ori", I, fl, ft)
+    U.assert_close(host(a), ref, U.RTOL_FWD, f"many-channel kernel vs oracle ({fk})")
+    U.assert_close(host(b), ref, U.RTOL_FWD, f"direct kernel vs oracle ({fk})")
+    assert U.max_err(host(a), host(b).astype(np.float64)) < 2e-6

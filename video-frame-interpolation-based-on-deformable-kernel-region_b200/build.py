@@ -20,7 +20,7 @@ INCLUDE = PKG_DIR.parent / "include"
 OBJ_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "libvfidkr_b200.so"
 
-SOURCES = ["capi.cu", "filterinterpolation.cu", "fi_strip.cu", "fi_strip_dkr.cu", "projection.cu", "interpolation.cu", "separableconv.cu",
+SOURCES = ["capi.cu", "filterinterpolation.cu", "fi_strip.cu", "fi_strip_dkr.cu", "fi_bigc.cu", "projection.cu", "interpolation.cu", "separableconv.cu",
            "correlation.cu"]
 
 NVCC_FLAGS = [
