@@ -596,3 +596,67 @@ def test_fi_ori_many_channel_kernel(lib, oracle, monkeypatch, B, C, H, W, fk):
     U.assert_close(host(a), ref, U.RTOL_FWD, f"many-channel kernel vs oracle ({fk})")
     U.assert_close(host(b), ref, U.RTOL_FWD, f"direct kernel vs oracle ({fk})")
     assert U.max_err(host(a), host(b).astype(np.float64)) < 2e-6
+
+
+# ------------------------------------------------------------------------------ BASELINE configs 3 and 5 at full size
+def test_config3_training_step_dkr_and_projections_batch16(lib, oracle):
+    """BASELINE config 3 beyond the "_ori" warp: fwd+bwd of the 4-input DKR warp, FlowProjection (fillhole = 0)
+    and DepthFlowProjection at B = 16, 256x448, against the oracle; upstream gradient = the output."""
+    r = U.rng(1033)
+    B, C, H, W = 16, 3, 256, 448
+    I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "gauss"), U.filt(r, B, 4, H, W)
+    off, d = U.offsets(r, B, 4, H, W, 0.45), U.depth_inv(r, B, H, W)
+    ts = [cu(a).requires_grad_() for a in (I, fl, ft, off)]
+    out = lib.FilterInterpolationModule("dkr")(*ts)
+    U.assert_close(host(out), oracle.fi_forward("dkr", I, fl, ft, off), U.RTOL_FWD, "DKR forward")
+    out.backward(out.detach())
+    refs = oracle.fi_backward("dkr", I, fl, ft, off, host(out))
+    for k, (t, ref) in enumerate(zip(ts, refs)):
+        U.assert_close(host(t.grad), ref, U.RTOL_ATOMIC if k == 0 else U.RTOL_FWD, f"DKR gradinput{k + 1}")
+    for depth in (None, d):
+        tf = cu(fl).requires_grad_()
+        if depth is None:
+            po = lib.FlowProjectionModule(True)(tf)
+        else:
+            td = cu(depth).requires_grad_()
+            po = lib.DepthFlowProjectionModule(True)(tf, td)
+        ref, cnt = oracle.flowprojection_forward(fl, depth, 0)
+        U.assert_close(host(po), ref, U.RTOL_ATOMIC, "projection forward")
+        po.backward(po.detach())
+        gi1, gi2 = oracle.flowprojection_backward(fl, depth, cnt.astype(np.float32), ref.astype(np.float32), host(po))
+        U.assert_close(host(tf.grad), gi1, U.RTOL_ATOMIC, "projection gradinput1")
+        if depth is not None:
+            U.assert_close(host(td.grad), gi2, U.RTOL_ATOMIC, "projection gradinput2 (depth)")
+
+
+def test_config5_4k_pair_properties(lib, oracle, monkeypatch):
+    """BASELINE config 5 shape (4K padded to 2176x3904, one pair per step): the strip kernel against the direct kernel
+    on the whole frame, the oracle on a band of rows, and size-independent projection properties."""
+    B, C, H, W = 1, 3, 2176, 3904
+    g = torch.Generator(device="cuda").manual_seed(55)
+    I = torch.rand(B, C, H, W, device="cuda", generator=g)
+    lo = (torch.randn(B, 2, H // 8, W // 8, device="cuda", generator=g) * 6).clamp_(-30, 30)
+    fl = torch.nn.functional.interpolate(lo, scale_factor=8, mode="bilinear", align_corners=False).contiguous()
+    ft = torch.softmax(torch.randn(B, 16, H, W, device="cuda", generator=g), 1)
+    out = lib.FilterInterpolationModule()(I, fl, ft)
+    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    ref = lib.FilterInterpolationModule()(I, fl, ft)
+    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    assert (out - ref).abs().max().item() < 3e-6
+    assert out.min().item() >= -1e-6 and out.max().item() <= 1 + 1e-6        # convex filter, convex blend
+    # oracle on the first 64 rows: a pixel's window may reach below the band, so only rows whose windows stay inside count
+    band = 96
+    o_ref = oracle.fi_forward("ori", host(I[:, :, :band]), host(fl[:, :, :band]), host(ft[:, :, :band]))
+    safe = (torch.arange(band, device="cuda")[None, :, None] + fl[0, 1, :band] < band - 4).cpu().numpy()[0]
+    got = host(out[:, :, :band])
+    err = np.abs(got - o_ref) / (np.abs(o_ref) + np.abs(o_ref).max())
+    assert err[:, :, safe].max() <= U.RTOL_FWD
+    # projection: zero flow -> zero output and count 4 in the interior; count mass = 4 x in-range pixels
+    z = torch.zeros(B, 2, H, W, device="cuda")
+    assert not lib.FlowProjectionModule(False)(z).any()
+    tf = fl.clone().requires_grad_()
+    po = lib.FlowProjectionModule(True)(tf)
+    assert torch.isfinite(po).all()
+    ref_p, _ = oracle.flowprojection_forward(host(fl[:, :, :band]), None, 0)
+    # rows of the band that no pixel from below the band can reach (|fy| <= 30)
+    U.assert_close(host(po[:, :, :band - 32]), ref_p[:, :, :band - 32], U.RTOL_ATOMIC, "4K projection band")
