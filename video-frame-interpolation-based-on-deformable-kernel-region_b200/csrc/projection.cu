@@ -95,8 +95,13 @@ __device__ __forceinline__ float4 hsum_row(const float4 &cur, const float4 &edge
 }
 
 __global__ void __launch_bounds__(32 * FIN_WARPS)
-projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count, float *__restrict__ out, int H, int W)
+projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count, float *__restrict__ out,
+                         unsigned *__restrict__ rowmask, unsigned char *__restrict__ colmask, int H, int W)
 {
+    // rowmask / colmask (inference only, else null): one bit per pixel, set where count != 0 -- the pixels the hole
+    // filling may take values from (:175-213) -- packed along rows (32 columns per word) and along columns (the 8 rows
+    // of this segment per byte), so that its scans step 32 columns / 8 rows per load instead of one pixel.
+    static_assert(FIN_ROWS == 8, "colmask packs one box-pass segment per byte");
     const int lane = threadIdx.x, x = (blockIdx.x * FIN_WARPS + threadIdx.y) * 32 + lane;
     if ((blockIdx.x * FIN_WARPS + threadIdx.y) * 32 >= W) return;   // whole warp outside
     const int b = blockIdx.z, y0 = blockIdx.y * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
@@ -106,6 +111,7 @@ projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count
     float4 c0, e0;
     load_row(Sb + (size_t)max(y0 - 1, 0) * W, x, W, lane, y0 > 0, c0, e0);
     float4 prev = hsum_row(c0, e0, x, W, lane);
+    unsigned colbits = 0;
     for (int yb = y0; yb < y1; yb += FIN_UNROLL) {
         float4 cur[FIN_UNROLL], edge[FIN_UNROLL];
 #pragma unroll
@@ -119,42 +125,75 @@ projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count
             float su = w0 * h.x + prev.x, sv = w0 * h.y + prev.y;
             const float sc = w0 * h.z + prev.z;
             prev = h;
-            if (y < y1 && x < W) {
+            const bool live = y < y1 && x < W;
+            if (live) {
                 if (sc > 0.0f) { su = su / sc; sv = sv / sc; }   // :130-134
                 const size_t a = (size_t)y * W + x;
                 st_stream(cn + a, sc); st_stream(ou + a, su); st_stream(ov + a, sv);
             }
+            if (rowmask) {   // uniform
+                const bool src = live && sc != 0.0f;
+                const unsigned m = __ballot_sync(0xffffffffu, src);
+                if (lane == 0 && y < y1) rowmask[((size_t)b * H + y) * ((W + 31) >> 5) + (x >> 5)] = m;
+                colbits |= (src ? 1u : 0u) << (y - y0);
+            }
         }
     }
+    if (colmask && x < W) colmask[((size_t)b * ((H + 7) >> 3) + blockIdx.y) * W + x] = (unsigned char)colbits;
 }
 
-// hole filling (:171-232).  Reads only non-hole pixels (count != 0), which this kernel never writes,
-// so running it in place is race-free.  The four scans are unbounded as in the reference.
-// One scan direction of the hole filling: the count of the nearest pixel with count != 0 walking from (h_i, w_i) in
-// steps of `step` elements (at most `room` of them), and how many steps away it is; 0 when the scan leaves the
-// plane first (the reference's loop then ends with the last count read, which is 0: :175-213).  The reference
-// reads one pixel per iteration; here SCAN pixels are requested at once, so a hole of width n costs n / SCAN
-// dependent round trips instead of n.
-constexpr int SCAN = 8;
-__device__ __forceinline__ float scan_nonhole(const float *__restrict__ c, long long step, int room, int &dist)
+// hole filling (:171-232).  Reads only non-hole pixels (count != 0), which this kernel never writes, so running it in
+// place is race-free.  The reference walks from every hole pixel one pixel at a time in four directions, unbounded;
+// here the walks run over the source bitmaps written by the box pass: a word covers 32 columns, a byte 8 rows, so a hole
+// n pixels wide costs n / 32 (n / 8) loads per direction instead of n, and the nearest source inside a word is a
+// clz / ffs.  Each scan returns the distance to the nearest source (0: none before the edge of the plane).
+__device__ __forceinline__ int scan_left(const unsigned *__restrict__ rm, int x)
 {
-    for (int base = 0; base < room; base += SCAN) {
-        float v[SCAN];
-#pragma unroll
-        for (int k = 0; k < SCAN; ++k) v[k] = (base + k < room) ? __ldg(c + (long long)(base + k + 1) * step) : 0.0f;
-#pragma unroll
-        for (int k = 0; k < SCAN; ++k)
-            if (v[k] != 0.0f) { dist = base + k + 1; return v[k]; }
+    int wi = x >> 5;
+    unsigned m = __ldg(rm + wi) & ((1u << (x & 31)) - 1u);
+    for (;;) {
+        if (m) return x - ((wi << 5) + 31 - __clz(m));
+        if (--wi < 0) return 0;
+        m = __ldg(rm + wi);
     }
-    dist = room;
-    return 0.0f;
+}
+__device__ __forceinline__ int scan_right(const unsigned *__restrict__ rm, int x, int WW)
+{
+    int wi = x >> 5;
+    unsigned m = __ldg(rm + wi) & ~((2u << (x & 31)) - 1u);   // bits above x (none when x & 31 == 31)
+    for (;;) {
+        if (m) return (wi << 5) + __ffs(m) - 1 - x;
+        if (++wi >= WW) return 0;
+        m = __ldg(rm + wi);
+    }
+}
+__device__ __forceinline__ int scan_up(const unsigned char *__restrict__ cm, int y, int W)
+{
+    int bi = y >> 3;
+    unsigned m = __ldg(cm + (size_t)bi * W) & ((1u << (y & 7)) - 1u);
+    for (;;) {
+        if (m) return y - ((bi << 3) + 31 - __clz(m));
+        if (--bi < 0) return 0;
+        m = __ldg(cm + (size_t)bi * W);
+    }
+}
+__device__ __forceinline__ int scan_down(const unsigned char *__restrict__ cm, int y, int W, int HB)
+{
+    int bi = y >> 3;
+    unsigned m = __ldg(cm + (size_t)bi * W) & 0xffu & ~((2u << (y & 7)) - 1u);
+    for (;;) {
+        if (m) return (bi << 3) + __ffs(m) - 1 - y;
+        if (++bi >= HB) return 0;
+        m = __ldg(cm + (size_t)bi * W);
+    }
 }
 
 // Holes are sparse (a few per cent of the pixels) but scattered, so with one thread per pixel most warps would run
 // the scans for one or two live lanes.  The CTA therefore first COMPACTS its holes into a shared list (ballot +
 // one shared atomic per warp) and then fills them with dense warps.
 __global__ void __launch_bounds__(BX *BY)
-projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ out, int H, int W)
+projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ out, const unsigned *__restrict__ rowmask,
+                           const unsigned char *__restrict__ colmask, int H, int W)
 {
     __shared__ int s_n;
     __shared__ unsigned short s_list[BX * BY];
@@ -162,10 +201,11 @@ projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ 
     const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
     const int b = blockIdx.z;
     const size_t HW = (size_t)H * W;
+    const int WW = (W + 31) >> 5, HB = (H + 7) >> 3;
     const float *cnb = count + (size_t)b * HW;
     if (tid == 0) s_n = 0;
     __syncthreads();
-    const bool hole = w_i < W && h_i < H && !(__ldcs(cnb + (size_t)h_i * W + w_i) > 0.0f);
+    const bool hole = w_i < W && h_i < H && !(__ldcs(cnb + (size_t)h_i * W + w_i) > 0.0f);   // count <= 0 (:171)
     const unsigned m = __ballot_sync(0xffffffffu, hole);
     if (m) {
         int base = 0;
@@ -179,11 +219,13 @@ projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ 
         const int t = s_list[q];
         const int x = blockIdx.x * BX + (t & (BX - 1)), y = blockIdx.y * BY + t / BX;
         const float *cn = cnb + (size_t)y * W + x;
-        int dl, dr, du, dd;
-        const float lt = scan_nonhole(cn, -1, x, dl);
-        const float rt = scan_nonhole(cn, 1, W - 1 - x, dr);
-        const float ut = scan_nonhole(cn, -(long long)W, y, du);
-        const float dt = scan_nonhole(cn, W, H - 1 - y, dd);
+        const int dl = scan_left(rowmask + ((size_t)b * H + y) * WW, x);
+        const int dr = scan_right(rowmask + ((size_t)b * H + y) * WW, x, WW);
+        const int du = scan_up(colmask + (size_t)b * HB * W + x, y, W);
+        const int dd = scan_down(colmask + (size_t)b * HB * W + x, y, W, HB);
+        // the counts the reference's loops end on (0 when a scan ran off the plane)
+        const float lt = dl ? __ldg(cn - dl) : 0.0f, rt = dr ? __ldg(cn + dr) : 0.0f;
+        const float ut = du ? __ldg(cn - (long long)du * W) : 0.0f, dt = dd ? __ldg(cn + (long long)dd * W) : 0.0f;
         if (lt + rt + ut + dt <= 0.0f) continue;
         const float l = lt > 0.0f ? 1.f : 0.f, r = rt > 0.0f ? 1.f : 0.f;
         const float u = ut > 0.0f ? 1.f : 0.f, d = dt > 0.0f ? 1.f : 0.f;
@@ -275,10 +317,16 @@ int projection_forward(const float *flow, const float *depth, float *count, floa
     const int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, SCRATCH_BYTES / (sizeof(float4) * HW)));
     const int nchunks = (B + per_chunk - 1) / per_chunk;
     const size_t chunk_cells = (size_t)per_chunk * HW;
+    // one stream-ordered block: [scratch image(s) | row bitmap | column bitmap] (bitmaps only for hole filling)
+    const size_t scratch_bytes = sizeof(float4) * chunk_cells * (nchunks > 1 ? 2 : 1);
+    const size_t WW = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
+    const size_t rowmask_bytes = fillhole ? sizeof(unsigned) * B * H * WW : 0, colmask_bytes = fillhole ? (size_t)B * HB * W : 0;
     void *scratch = nullptr;
-    int e = stream_scratch_alloc(&scratch, sizeof(float4) * chunk_cells * (nchunks > 1 ? 2 : 1), s);
+    int e = stream_scratch_alloc(&scratch, scratch_bytes + rowmask_bytes + colmask_bytes, s);
     if (e) return e;
     float4 *S = static_cast<float4 *>(scratch);
+    unsigned *rowmask = fillhole ? reinterpret_cast<unsigned *>(static_cast<char *>(scratch) + scratch_bytes) : nullptr;
+    unsigned char *colmask = fillhole ? reinterpret_cast<unsigned char *>(rowmask) + rowmask_bytes : nullptr;
     e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * chunk_cells, s), "clear projection scratch");
     if (!e) {
         for (int c = 0; c < nchunks; ++c) {
@@ -290,12 +338,14 @@ int projection_forward(const float *flow, const float *depth, float *count, floa
             projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(flow + (size_t)b0 * 2 * HW, DEPTH ? depth + (size_t)b0 * HW : nullptr,
                                                                    cur, nxt, H, W);
             dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), nb);
-            projection_finish_kernel<<<fgrid, fblock, 0, s>>>(cur, count + (size_t)b0 * HW, out + (size_t)b0 * 2 * HW, H, W);
+            projection_finish_kernel<<<fgrid, fblock, 0, s>>>(cur, count + (size_t)b0 * HW, out + (size_t)b0 * 2 * HW,
+                                                              fillhole ? rowmask + (size_t)b0 * H * WW : nullptr,
+                                                              fillhole ? colmask + (size_t)b0 * HB * W : nullptr, H, W);
             note_launch(2);
         }
         if (fillhole) {
             dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
-            projection_fillhole_kernel<<<grid, block, 0, s>>>(count, out, H, W);
+            projection_fillhole_kernel<<<grid, block, 0, s>>>(count, out, rowmask, colmask, H, W);
             note_launch();
         }
         e = check_launch("flow projection forward");
