@@ -660,3 +660,30 @@ def test_config5_4k_pair_properties(lib, oracle, monkeypatch):
     ref_p, _ = oracle.flowprojection_forward(host(fl[:, :, :band]), None, 0)
     # rows of the band that no pixel from below the band can reach (|fy| <= 30)
     U.assert_close(host(po[:, :, :band - 32]), ref_p[:, :, :band - 32], U.RTOL_ATOMIC, "4K projection band")
+
+
+# ------------------------------------------------------------------------------ host-side pair streaming
+def test_pair_stream_matches_whole_batch(lib):
+    """vfidkr_b200.PairStream (copies in / kernels / copies out of successive pairs on three streams) must return
+    exactly what one whole-batch call returns, for any chunking, and leave the caller's stream ordered after it."""
+    g = torch.Generator().manual_seed(9)
+    n, C, H, W = 5, 3, 96, 224
+    hd = {"frame": torch.rand(n, C, H, W, generator=g).pin_memory(),
+          "flow": (torch.randn(n, 2, H, W, generator=g) * 3).pin_memory(),
+          "filter": torch.softmax(torch.randn(n, 16, H, W, generator=g), 1).pin_memory(),
+          "depth": (torch.rand(n, 1, H, W, generator=g) * 0.9 + 0.1).pin_memory()}
+    fi, dp = lib.FilterInterpolationModule(), lib.DepthFlowProjectionModule(False)
+
+    def step(d):
+        return fi(d["frame"], d["flow"], d["filter"]), dp(d["flow"], d["depth"])
+    with torch.no_grad():
+        ref = [t.cpu() for t in step({k: v.cuda() for k, v in hd.items()})]
+        for chunk in (1, 2, 5):
+            outs = [torch.empty(n, C, H, W).pin_memory(), torch.empty(n, 2, H, W).pin_memory()]
+            ps = lib.PairStream(torch.device("cuda", 0), step, pairs_per_chunk=chunk)
+            for _ in range(3):                       # back-to-back runs reuse the streams
+                ps.run(hd, outs)
+            torch.cuda.current_stream().synchronize()   # the caller's stream was made to wait for the results
+            assert torch.equal(outs[0], ref[0]), chunk
+            # projection sums are atomically accumulated: order, hence rounding, may differ between calls
+            assert (outs[1] - ref[1]).abs().max().item() <= 1e-4 * ref[1].abs().max().item(), chunk

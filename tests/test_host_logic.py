@@ -102,3 +102,12 @@ def test_world_size_2_timing_reduction_over_gloo():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert res == [(0, 15.0, 9.0), (1, 15.0, 9.0)]
+
+
+def test_pair_stream_refuses_cpu():
+    """No CPU path: the host-side streamer insists on a CUDA device."""
+    import pytest
+    import torch
+    import vfidkr_b200 as V
+    with pytest.raises(ValueError):
+        V.PairStream(torch.device("cpu"), lambda d: ())

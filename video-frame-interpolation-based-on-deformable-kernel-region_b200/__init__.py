@@ -16,5 +16,6 @@ from .interpolation import InterpolationChLayer, InterpolationChModule, Interpol
 from .separable_conv import (SeparableConvFlowLayer, SeparableConvFlowModule, SeparableConvLayer,
                              SeparableConvModule)
 from .compat import install_reference_aliases
+from .host_stream import PairStream
 
 __version__ = "0.1.0"
