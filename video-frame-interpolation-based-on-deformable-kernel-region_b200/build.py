@@ -53,7 +53,9 @@ def _stale(target: Path, deps: list[Path]) -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
+    """VFIDKR_NVCC_EXTRA (space-separated) adds flags for debug builds, e.g. -DVFIDKR_STRIP_STATS; use with --force."""
     nvcc = _nvcc()
+    extra = os.environ.get("VFIDKR_NVCC_EXTRA", "").split()
     OBJ_DIR.mkdir(exist_ok=True)
     headers = sorted(CSRC.glob("*.cuh")) + sorted(INCLUDE.glob("*.h")) + [Path(__file__)]
     jobs = []
@@ -64,7 +66,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
 
     def compile_one(job):
         src, obj = job
-        cmd = [nvcc] + _host_compiler_flags() + NVCC_FLAGS + ["-c", str(src), "-o", str(obj)]
+        cmd = [nvcc] + _host_compiler_flags() + NVCC_FLAGS + extra + ["-c", str(src), "-o", str(obj)]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -33,9 +33,27 @@
 namespace vfidkr {
 namespace strip {
 
+// Optional pipeline statistics (build with -DVFIDKR_STRIP_STATS; read with vfidkr_debug_strip_stats): cycles the
+// producer spends in each kind of wait and the compute warps at the two "full" barriers.  Off in production builds.
+#ifdef VFIDKR_STRIP_STATS
+__device__ unsigned long long g_stats[16];
+#define STAT_DECL unsigned long long stat_local[8] = {0, 0, 0, 0, 0, 0, 0, 0}; const long long stat_begin = clock64()
+#define STAT_TIME(slot, stmt) do { const long long t_ = clock64(); stmt; stat_local[slot] += (unsigned long long)(clock64() - t_); } while (0)
+#define STAT_INC(slot) (++stat_local[slot])
+#define STAT_FLUSH(base, total_slot) do { stat_local[total_slot] = (unsigned long long)(clock64() - stat_begin); \
+        for (int i_ = 0; i_ < 8; ++i_) atomicAdd(&g_stats[(base) + i_], stat_local[i_]); } while (0)
+#else
+#define STAT_DECL ((void)0)
+#define STAT_TIME(slot, stmt) do { stmt; } while (0)
+#define STAT_INC(slot) ((void)0)
+#define STAT_FLUSH(base, total_slot) ((void)0)
+#endif
+
 constexpr int FILT_FLOATS = 16 * NPIX;
 constexpr uint32_t FILT_BYTES = FILT_FLOATS * sizeof(float);
 // filter pipeline depth: as deep as shared memory allows next to the window ring
+// (5 stages with a 35-row window were measured: no gain on smooth flows -- bytes in flight are not the limit -- and
+// 8 % slower on the bench flow, whose boxes need the rows)
 template <int CG> __host__ __device__ constexpr int stages() { return CG <= 3 ? 4 : 3; }
 template <int CG> __host__ __device__ constexpr size_t smem_bytes()
 {
@@ -73,7 +91,8 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
     float *s_ring = s_filt + SF * FILT_FLOATS;                                         // [RROWS][CG][WB]
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + RROWS * ROWF);
     uint64_t *filt_full = s_bar, *tile_done = s_bar + SF, *bbox_done = s_bar + 2 * SF, *img_full = bbox_done + NB;
-    Box *s_box = reinterpret_cast<Box *>(img_full + NB);                              // [NB]
+    uint64_t *filt_free = img_full + NB;                                              // [SF]
+    Box *s_box = reinterpret_cast<Box *>(filt_free + SF);                             // [NB]
     TileMeta *s_meta = reinterpret_cast<TileMeta *>(s_box + NB);                      // [NB]
     int *s_ymin = reinterpret_cast<int *>(s_meta + NB);                               // [NB], producer private
     ItemQueue *s_queue = reinterpret_cast<ItemQueue *>(s_ymin + NB);
@@ -87,6 +106,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         for (int s = 0; s < SF; ++s) {
             mbar_init(&filt_full[s], 1);
             mbar_init(&tile_done[s], NCOMP_WARPS);
+            mbar_init(&filt_free[s], NCOMP_WARPS);
         }
         for (int s = 0; s < NB; ++s) {
             mbar_init(&bbox_done[s], NCOMP_WARPS);
@@ -120,6 +140,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         // for "tile done"), the image window follows the bounding boxes.  The filter stream is advanced from
         // inside every wait of the image stream, so a window re-base never stalls the HBM prefetch.  The same pump
         // serves the compute warps' requests for the next work item.
+        STAT_DECL;   // producer: 0 box wait, 1 re-base drain, 2 slot-reuse wait, 3 re-bases, 4 global tiles, 5 tiles, 6 total
         bool exhausted = false;
         int item_no = -1;                                                   // image stream: current item
         auto draw_items = [&](int upto) {
@@ -130,7 +151,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         bool f_end = false;
         auto pump_filters = [&]() {
             draw_items(*(volatile int *)&s_queue->wanted);
-            while (!f_end && (f_t < SF || mbar_test(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1)))) {
+            while (!f_end && (f_t < SF || mbar_test(&filt_free[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1)))) {
                 if (f_left == 0) {
                     ++f_item;
                     draw_items(f_item + 1);
@@ -154,7 +175,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         };
         // wait for a barrier phase while keeping the filter stream going; traps instead of hanging on a protocol error
         auto wait_pumping = [&](uint64_t *bar, uint32_t parity) {
-            for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 400u); ++spins) {
+            for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 100u); ++spins) {
                 pump_filters();
                 if (spins > (1u << 24)) __trap();
             }
@@ -181,7 +202,8 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             const int sb = t % NB;
             pump_filters();
             // ---- image window of tile t, as soon as the compute warps have folded its bounding box ----
-            wait_pumping(&bbox_done[sb], (uint32_t)((t / NB) & 1));
+            STAT_TIME(0, wait_pumping(&bbox_done[sb], (uint32_t)((t / NB) & 1)));
+            STAT_INC(5);
             const Box bb = s_box[sb];
             __syncwarp();
             if (lane == 0) s_box[sb] = Box{INT_MAX, INT_MIN, INT_MAX, INT_MIN};   // ready for tile t + NB
@@ -192,6 +214,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 const int width = bb.xmax - bb.xmin + 1, slack = WB - width;
                 if (bb.ymax - bb.ymin + 1 > RROWS || slack < 7) {
                     mode = MODE_GLOBAL;   // the tile's box does not fit the window at all
+                    STAT_INC(4);
                 } else {
                     mode = MODE_SMEM;
                     const bool rebase = stale || bb.xmin < xorg || bb.xmax >= xorg + WB || bb.ymin < max(base, hi - RROWS);
@@ -200,7 +223,8 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                     int oldest = max(0, t - LEAD);
                     if (rebase) {
                         // everything in flight may still read the window: drain, then restart it around this tile
-                        for (; oldest < t; ++oldest) wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1));
+                        STAT_INC(3);
+                        STAT_TIME(1, for (; oldest < t; ++oldest) wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1)));
                         xorg = (bb.xmin - (slack >= 14 ? slack / 2 : 0)) & ~7;   // sector-aligned, box centred when it can be
                         base = hi = bb.ymin;
                         stale = false;
@@ -211,7 +235,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                         int need_lo = bb.ymin;
                         for (int q = oldest; q < t; ++q) need_lo = min(need_lo, s_ymin[q % NB]);
                         if (bb.ymax - need_lo + 1 <= RROWS) break;
-                        wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1));   // oldest < t here
+                        STAT_TIME(2, wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1)));   // oldest < t here
                         ++oldest;
                     }
                     load_lo = max(hi, bb.ymin);
@@ -235,15 +259,16 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             __syncwarp();
         }
         while (!f_end) {   // filter planes of the last tiles whose ring slots were still busy
-            if (f_t >= SF) mbar_wait_sleepy(&tile_done[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1));
+            if (f_t >= SF) mbar_wait_sleepy(&filt_free[f_t % SF], (uint32_t)(((f_t / SF) - 1) & 1));
             pump_filters();
         }
+        if (lane == 0) STAT_FLUSH(0, 6);
     } else {
         // ================================ compute warps ================================
         const int tx = tid % TW, tyy = tid / TW;   // position inside the tile
         const unsigned tile_step = (unsigned)(TH * W);
         // 32-bit shared addresses of the barrier / box rings, computed once
-        const uint32_t a_filt_full = smem_u32(filt_full), a_tile_done = smem_u32(tile_done);
+        const uint32_t a_filt_full = smem_u32(filt_full), a_tile_done = smem_u32(tile_done), a_filt_free = smem_u32(filt_free);
         const uint32_t a_bbox_done = smem_u32(bbox_done), a_img_full = smem_u32(img_full), a_box = smem_u32(s_box);
 
         // left == 0 marks the end of the work: the cursor stays there (no pixel, no further queue reads)
@@ -264,6 +289,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 
         // three cursors over the same sequence: the tile being computed, the tile whose box is folded (LEAD ahead)
         // and the tile whose flow is requested (LEAD + 1 ahead)
+        STAT_DECL;   // compute warps: 0 image-full wait, 1 filter-full wait, 2 tiles, 3 total
         Cursor cur{0, 0, 0, 0, 0, 0};
         start_item(cur);
         Cursor fold = cur, req = cur;
@@ -333,9 +359,18 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             const int sf = j % SF, sb = j % NB;
             const float *ft = s_filt + sf * FILT_FLOATS + tid;
 
-            mbar_wait_backoff_a(a_img_full + sb * 8, (uint32_t)((j / NB) & 1));
+            STAT_TIME(0, mbar_wait_backoff_a(a_img_full + sb * 8, (uint32_t)((j / NB) & 1)));
+            STAT_INC(2);
             const int mode = s_meta[sb].mode, xorg = s_meta[sb].xorg;
-            mbar_wait_backoff_a(a_filt_full + sf * 8, (uint32_t)((j / SF) & 1));
+            STAT_TIME(1, mbar_wait_backoff_a(a_filt_full + sf * 8, (uint32_t)((j / SF) & 1)));
+            // The 16 taps go to registers at once and the stage is handed back BEFORE the window arithmetic: the kernel
+            // is bound by the bytes it keeps in flight (4 stages x 32 KB per SM; a stage that waits for the slowest
+            // warp to finish the whole tile spends a third of its life neither in flight nor in use).
+            float w[16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) w[k] = ft[k * NPIX];
+            __syncwarp();
+            if (lane == 0) mbar_arrive_a(a_filt_free + sf * 8);   // release: this warp's reads of stage sf are complete
 
             if (has_pixel(cur)) {
                 float *o = out + (size_t)cur.b * CG * HW + cur.pix;
@@ -348,9 +383,6 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                     const int ix = (int)x2, iy = (int)y2;
                     const int L = ix - 1, T = iy - 1;                       // window origin for F = 4 (:2745-2748)
                     const float alpha = __fsub_rn(x2, (float)ix), beta = __fsub_rn(y2, (float)iy);
-                    float w[16];
-#pragma unroll
-                    for (int k = 0; k < 16; ++k) w[k] = ft[k * NPIX];
                     const float qTL = (1 - alpha) * (1 - beta), qTR = alpha * (1 - beta);
                     const float qBL = (1 - alpha) * beta, qBR = alpha * beta;
                     float res[CG];
@@ -402,11 +434,12 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_a(a_tile_done + sf * 8);   // this warp is done with filter stage sf and the window rows of tile j
+            if (lane == 0) mbar_arrive_a(a_tile_done + sf * 8);   // this warp is done with the window rows of tile j
             advance(cur);
 #pragma unroll
             for (int k = 0; k < LEAD; ++k) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; }
         }
+        if (tid == 0) STAT_FLUSH(8, 3);
     }
 }
 
@@ -440,6 +473,17 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
 }
 
 }  // namespace strip
+
+#ifdef VFIDKR_STRIP_STATS
+// debug builds only: reads and clears the pipeline statistics (16 counters, see STAT_DECL comments)
+extern "C" __attribute__((visibility("default"))) int vfidkr_debug_strip_stats(unsigned long long *out16)
+{
+    unsigned long long zero[16] = {0};
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    if (cudaMemcpyFromSymbol(out16, strip::g_stats, sizeof zero) != cudaSuccess) return 1;
+    return cudaMemcpyToSymbol(strip::g_stats, zero, sizeof zero) != cudaSuccess;
+}
+#endif
 
 // Returns VFIDKR_OK / VFIDKR_ERR_CUDA when the strip kernel was launched, -1 when it does not apply.
 int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
