@@ -23,7 +23,7 @@ enum { MODE_NONE = 0, MODE_SMEM = 1, MODE_GLOBAL = 2 };
 
 template <int CG> __host__ __device__ constexpr int row_floats() { return CG * WB; }   // one window row: [C][WB]
 
-struct TileMeta { int mode, xorg; };
+struct TileMeta { int mode, xorg, soff, pad_; };   // window descriptor of one tile: x origin and slot offset (row y -> slot (y + soff) mod RROWS)
 struct Box { int xmin, xmax, ymin, ymax; };
 
 // Position of one thread in the CTA's sequence of pipeline slots (tiles of its items, back to back), advanced
