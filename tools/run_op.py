@@ -64,6 +64,16 @@ ops = {
     "proj_fwd": lambda: V.FlowProjectionLayer.apply(fl, False),
     "dproj_fwd": lambda: V.DepthFlowProjectionLayer.apply(fl, dep, False),
 }
+if a.op in ("dproj_bwd", "proj_bwd"):
+    cnt, po = torch.empty(B, 1, H, W, device=dev), torch.empty(B, 2, H, W, device=dev)
+    g2, gd = torch.randn(B, 2, H, W, device=dev), torch.empty(B, 1, H, W, device=dev)
+    if a.op == "dproj_bwd":
+        _lib.call("vfidkr_depthflowprojection_forward", ptr(fl), ptr(dep), ptr(cnt), ptr(po), B, H, W, 0, sp)
+        ops[a.op] = lambda: _lib.call("vfidkr_depthflowprojection_backward", ptr(fl), ptr(dep), ptr(cnt), ptr(po), ptr(g2),
+                                      ptr(gi2), ptr(gd), B, H, W, sp)
+    else:
+        _lib.call("vfidkr_flowprojection_forward", ptr(fl), ptr(cnt), ptr(po), B, H, W, 0, sp)
+        ops[a.op] = lambda: _lib.call("vfidkr_flowprojection_backward", ptr(fl), ptr(cnt), ptr(g2), ptr(gi2), B, H, W, sp)
 if a.op == "fi_bench":
     # the FilterInterpolation calls of bench.py, on bench.py's own inputs (both directions)
     import bench

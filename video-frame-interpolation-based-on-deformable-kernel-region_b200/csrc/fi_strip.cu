@@ -177,7 +177,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         auto wait_pumping = [&](uint64_t *bar, uint32_t parity) {
             for (uint32_t spins = 0; !mbar_try_wait_hint(bar, parity, 100u); ++spins) {
                 pump_filters();
-                if (spins > (1u << 24)) __trap();
+                if (spins > (1u << 26)) __trap();   // several seconds of polling: a protocol error, not a slow neighbour
             }
         };
 

@@ -260,19 +260,21 @@ projection_backward_kernel(const float *__restrict__ flow, const float *__restri
         const float d = DEPTH ? ld_stream(depth + (size_t)b * HW + pix) : 1.0f;
         const float *gu = gout + ((size_t)b * 2 + 0) * HW, *gv = gu + HW, *cn = count + (size_t)b * HW;
         const float *ou = DEPTH ? out + ((size_t)b * 2 + 0) * HW : nullptr;
-        const size_t a[4] = {(size_t)c.T * W + c.L, (size_t)c.T * W + c.R, (size_t)c.Bm * W + c.L, (size_t)c.Bm * W + c.R};
+        const int a[4] = {c.T * W + c.L, c.T * W + c.R, c.Bm * W + c.L, c.Bm * W + c.R};   // 32-bit: H * W < 2^31 (launcher)
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const float cnt = __ldg(cn + a[k]);
-            const float gU = __ldg(gu + a[k]), gV = __ldg(gv + a[k]);
+            // one IEEE division per corner (1 / count) instead of the reference's four: products differ from its
+            // quotients by at most an ulp or two, far inside the gradient tolerance
+            const float rc = 1.0f / __ldg(cn + a[k]);
+            const float gU = __ldg(gu + a[k]) * rc, gV = __ldg(gv + a[k]) * rc;   // gradout / count
             if (DEPTH) {
-                su += -gU * d / cnt;                                   // depth :289-296
-                sv += -gV * d / cnt;
-                sd += -gU / cnt * (fx - __ldg(ou + a[k]));             // depth :311-322
-                sd += -gV / cnt * (fy - __ldg(ou + HW + a[k]));        // depth :324-335
+                su += -gU * d;                                         // depth :289-296
+                sv += -gV * d;
+                sd += -gU * (fx - __ldg(ou + a[k]));                   // depth :311-322
+                sd += -gV * (fy - __ldg(ou + HW + a[k]));              // depth :324-335
             } else {
-                su += -gU / cnt;                                       // :277-284
-                sv += -gV / cnt;
+                su += -gU;                                             // :277-284
+                sv += -gV;
             }
         }
     }
