@@ -594,6 +594,29 @@ def op_table(torch, V, device, path):
         ftc = torch.softmax(torch.randn(Bc, 16, H, W, device=device), 1)
         add("FI_ori_fwd_C196_B2", timeit(lambda: V.FilterInterpolationLayer.apply(ctx, fl[:Bc].contiguous(), ftc), iters=3),
             4 * (2 * 196 + 18), Bc * H * W)
+        del ctx, ftc
+        torch.cuda.empty_cache()
+    # BASELINE configs 3 (training step, B = 16 at 256x448) and 5 (one 4K pair, padded to 2176x3904) on the same operators
+    for tag, (Bx, Hx, Wx) in (("cfg3_B16_256x448", (16, 256, 448)), ("cfg5_4K_B1", (1, 2176, 3904))):
+        pxx = Bx * Hx * Wx
+        gen.manual_seed(78)
+        Ix = torch.rand(Bx, 3, Hx, Wx, device=device)
+        flx = scene_flow(torch, gen, device, Bx, Hx, Wx)
+        ftx = torch.softmax(torch.randn(Bx, 16, Hx, Wx, device=device), 1)
+        offx = (torch.rand(Bx, 32, Hx, Wx, device=device) - 0.5) * 0.9
+        depx = torch.rand(Bx, 1, Hx, Wx, device=device) * 0.9 + 0.1
+        gx = torch.randn(Bx, 3, Hx, Wx, device=device)
+        o1, o2, o3, o4 = torch.empty_like(Ix), torch.empty_like(flx), torch.empty_like(ftx), torch.empty_like(offx)
+        with torch.no_grad():
+            add(f"FI_ori_fwd_C3_{tag}", timeit(lambda: V.FilterInterpolationLayer.apply(Ix, flx, ftx), iters=20), 96, pxx)
+            add(f"FI_dkr_fwd_C3_{tag}", timeit(lambda: V.FilterInterpolationLayerDKR.apply(Ix, flx, ftx, offx), iters=20), 224, pxx)
+            add(f"DepthFlowProjection_fwd_{tag}", timeit(lambda: V.DepthFlowProjectionLayer.apply(flx, depx, True), iters=20), 24, pxx)
+        add(f"FI_ori_bwd_C3_{tag}", timeit(lambda: _lib.call("vfidkr_filterinterpolation_backward_ori", ptr(Ix), ptr(flx), ptr(ftx), ptr(gx),
+                                                              ptr(o1), ptr(o2), ptr(o3), Bx, 3, Hx, Wx, 4, sp), iters=20), 180, pxx)
+        add(f"FI_dkr_bwd_C3_{tag}", timeit(lambda: _lib.call("vfidkr_filterinterpolation_backward_dkr", ptr(Ix), ptr(flx), ptr(ftx), ptr(offx),
+                                                              ptr(gx), ptr(o1), ptr(o2), ptr(o3), ptr(o4), Bx, 3, Hx, Wx, 4, sp), iters=20), 436, pxx)
+        del Ix, flx, ftx, offx, depx, gx, o1, o2, o3, o4
+        torch.cuda.empty_cache()
     with open(path, "w") as f:
         for r in rows:
             f.write(json.dumps(r) + "\n")
