@@ -58,10 +58,10 @@ static encode_tiled_fn resolve_encode()
 // Encoding a tensor map is a driver call; callers hit the same (base, shape, box) repeatedly (the allocator
 // recycles blocks), so a small thread-local direct-mapped cache removes it from the steady-state launch path.
 struct MapKey {
-    const float *base; uint64_t d[4]; uint32_t b[4]; uint32_t rank;
+    const float *base; uint64_t d[4]; uint32_t b[4]; uint32_t rank; uint64_t row_pitch;   // row pitch in elements
     bool operator==(const MapKey &o) const
     {
-        return base == o.base && rank == o.rank && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && d[3] == o.d[3] &&
+        return base == o.base && rank == o.rank && row_pitch == o.row_pitch && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && d[3] == o.d[3] &&
                b[0] == o.b[0] && b[1] == o.b[1] && b[2] == o.b[2] && b[3] == o.b[3];
     }
 };
@@ -73,6 +73,7 @@ static bool encode_cached(CUtensorMap *map, const MapKey &key)
     static thread_local MapSlot cache[SLOTS];
     uint64_t h = (reinterpret_cast<uintptr_t>(key.base) >> 8) * 0x9E3779B97F4A7C15ull;
     for (int i = 0; i < 4; ++i) h ^= (key.d[i] * 0x100000001B3ull + key.b[i]) << (7 * i);
+    h ^= key.row_pitch * 0x9E3779B1ull;
     MapSlot &slot = cache[(h >> 32) % SLOTS];
     if (slot.valid && slot.key == key) { *map = slot.map; return true; }
 
@@ -83,7 +84,7 @@ static bool encode_cached(CUtensorMap *map, const MapKey &key)
     uint64_t pitch = sizeof(float);
     for (uint32_t i = 0; i < key.rank; ++i) {
         dims[i] = key.d[i]; box[i] = key.b[i]; estr[i] = 1;
-        pitch *= key.d[i];
+        pitch *= (i == 0 ? key.row_pitch : key.d[i]);   // rows may be padded (extent d[0], pitch row_pitch)
         if (i + 1 < key.rank) strides[i] = pitch;   // byte stride of dimension i+1
     }
     const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, key.rank, const_cast<float *>(key.base), dims, strides, box,
@@ -97,14 +98,21 @@ static bool encode_cached(CUtensorMap *map, const MapKey &key)
 bool encode_tensor_map_3d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t D,
                           uint32_t boxW, uint32_t boxH, uint32_t boxD)
 {
-    const MapKey key{base, {W, H, D, 1}, {boxW, boxH, boxD, 1}, 3};
+    const MapKey key{base, {W, H, D, 1}, {boxW, boxH, boxD, 1}, 3, W};
     return encode_cached(map, key);
 }
 
 bool encode_tensor_map_4d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t C, uint64_t N,
                           uint32_t boxW, uint32_t boxH, uint32_t boxC)
 {
-    const MapKey key{base, {W, H, C, N}, {boxW, boxH, boxC, 1}, 4};
+    const MapKey key{base, {W, H, C, N}, {boxW, boxH, boxC, 1}, 4, W};
+    return encode_cached(map, key);
+}
+
+bool encode_tensor_map_4d_pitched(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t C, uint64_t N,
+                                  uint64_t row_pitch, uint32_t boxW, uint32_t boxH, uint32_t boxC)
+{
+    const MapKey key{base, {W, H, C, N}, {boxW, boxH, boxC, 1}, 4, row_pitch};
     return encode_cached(map, key);
 }
 

@@ -91,6 +91,21 @@ corr_forward_generic_kernel(const float *__restrict__ in1, const float *__restri
 // per channel it reads 1 + 3*3 float4 from shared memory (conflict-free, 16 B lane stride) for 108 FMAs.
 // When W % 4 != 0 (TMA needs 16-byte row pitch) the same kernel stages the tiles with plain loads.
 // ---------------------------------------------------------------------------------------------
+// copies both feature maps into row-padded scratch (pitch a multiple of 4 floats) so that TMA can describe them
+__global__ void __launch_bounds__(256)
+corr_pad_rows_kernel(const float *__restrict__ a, const float *__restrict__ b, float *__restrict__ pa, float *__restrict__ pb,
+                     size_t rows, int W, int pitch)
+{
+    const size_t n = rows * (size_t)pitch;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / pitch;
+        const int x = (int)(i - r * pitch);
+        const bool in = x < W;
+        pa[i] = in ? __ldg(a + r * W + x) : 0.0f;
+        pb[i] = in ? __ldg(b + r * W + x) : 0.0f;
+    }
+}
+
 namespace cfast {
 constexpr int DR = 4, D = 2 * DR + 1;
 constexpr int TX = 32, TY = 8, CK = 8, PX = 4, TJ = 3;
@@ -419,9 +434,35 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
         CUtensorMap m1, m2;
         // (TMA box origins are kept at multiples of 4 elements: pad != max_displacement shifts them by md - pad, and an
         // origin of -2 was observed to fault -- such configurations, which VFIDKR never uses, take the cp.async path)
-        const bool tma = ((md - pad) % 4 == 0) && (W % 4 == 0) && aligned16(input1) && aligned16(input2) &&
-                         encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
-                         encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK);
+        const bool tma_ok = (md - pad) % 4 == 0;
+        bool tma = tma_ok && (W % 4 == 0) && aligned16(input1) && aligned16(input2) &&
+                   encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
+                   encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK);
+        // Rows that are not a multiple of 16 bytes (the two coarsest PWC levels at 1080p are 62 and 31 wide) cannot be
+        // described to TMA.  Both feature maps are then copied once into a row-padded scratch (one small kernel, a few
+        // MB) and the tensor maps keep the true width as extent -- reads past it are zero-filled, which is the op's own
+        // padding -- so these levels run the TMA kernel too instead of the 4-byte cp.async staging path.
+        void *pitched = nullptr;
+        // (worth it between ~1.5 M and 64 M elements per map: below, the extra launch costs more than the staging path
+        // loses -- measured 44 -> 50 us at 18 x 31 x 196 x 8, 66 -> 51 us at 36 x 62 x 128 x 8 -- above, the copy is real traffic)
+        const size_t map_elems = (size_t)B * C * H * W;
+        if (!tma && tma_ok && map_elems >= ((size_t)3 << 19) && map_elems <= ((size_t)64 << 20)) {
+            const size_t pitch = ((size_t)W + 3) & ~(size_t)3, rows = (size_t)B * C * H;
+            if (stream_scratch_alloc(&pitched, 2 * rows * pitch * sizeof(float), s) == VFIDKR_OK) {
+                float *p1 = static_cast<float *>(pitched), *p2 = p1 + rows * pitch;
+                const unsigned nb = (unsigned)std::min<size_t>((rows * pitch + 255) / 256, (size_t)sm_count() * 16);
+                corr_pad_rows_kernel<<<nb, 256, 0, s>>>(input1, input2, p1, p2, rows, W, (int)pitch);
+                note_launch();
+                tma = cudaGetLastError() == cudaSuccess &&
+                      encode_tensor_map_4d_pitched(&m1, p1, W, H, C, B, pitch, TX, TY, CK) &&
+                      encode_tensor_map_4d_pitched(&m2, p2, W, H, C, B, pitch, F2W, F2H, CK);
+            }
+            (void)cudaGetLastError();
+        }
+        struct PitchedGuard {   // the scratch is released on the stream, after the kernel that reads it
+            void *p; cudaStream_t s;
+            ~PitchedGuard() { if (p) cudaFreeAsync(p, s); }
+        } pitched_guard{pitched, s};
         if (!tma) { memset(&m1, 0, sizeof m1); memset(&m2, 0, sizeof m2); }
         // Too few tiles to fill the machine (the two coarsest PWC levels at 1080p): split the channels over
         // ksplit work items per tile and add the partial volumes in a second, tiny kernel.

@@ -299,18 +299,15 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             for (int g = 0; g < 4; ++g) {
                 const int u = 4 * j + g, st = u % NS;
                 mbar_wait_sleepy(&sub_full[st], (uint32_t)((u / NS) & 1));
+                // geometry of the four taps of this window row: everything the sub-stage holds goes to registers here, and
+                // the sub-stage is handed back BEFORE the window arithmetic (cf. the filter-free barrier of fi_strip.cu)
+                const int cy = clampi(T + g, 0, H - 1);          // clamped tap row (:100,:1392)
+                float qw[4], phiX[4], phiY[4];
+                int Top[4], Left[4];
+                bool near_all = mode == MODE_SMEM;
                 if (in_range) {
                     const float *sp = s_sub + st * SUB_FLOATS + tid;
-                    const int cy = clampi(T + g, 0, H - 1);          // clamped tap row (:100,:1392)
                     const float cyf = (float)cy;
-                    // ring offsets of rows cy-1, cy, cy+1 (clamped to the plane) -- only used on the window path
-                    const int r_m = (int)((unsigned)max(cy - 1, 0) % RROWS) * ROWF - xorg;
-                    const int r_0 = (int)((unsigned)cy % RROWS) * ROWF - xorg;
-                    const int r_p = (int)((unsigned)min(cy + 1, H - 1) % RROWS) * ROWF - xorg;
-                    // geometry of the four taps of this window row
-                    float qw[4], phiX[4], phiY[4];
-                    int Top[4], Left[4];
-                    bool near_all = mode == MODE_SMEM;
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
                         const float wgt = HAS_FILTER ? sp[i * NPIX] : 1.0f;
@@ -325,6 +322,14 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                         // in-contract tap: Top in {cy-1, cy}, Left in {cx-1, cx} -> all four corners are in the window
                         near_all = near_all && (unsigned)(Top[i] - cy + 1) < 2u && (unsigned)(Left[i] - cxi[i] + 1) < 2u;
                     }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sub_empty[st]);   // release: this warp's reads of the sub-stage are complete
+                if (in_range) {
+                    // ring offsets of rows cy-1, cy, cy+1 (clamped to the plane) -- only used on the window path
+                    const int r_m = (int)((unsigned)max(cy - 1, 0) % RROWS) * ROWF - xorg;
+                    const int r_0 = (int)((unsigned)cy % RROWS) * ROWF - xorg;
+                    const int r_p = (int)((unsigned)min(cy + 1, H - 1) % RROWS) * ROWF - xorg;
                     if (near_all) {
                         // branch-free block: 16 x C window loads in flight together
                         float v[4][4][CG];
@@ -382,8 +387,6 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                         }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sub_empty[st]);
             }
             if (pixel) {
                 float *o = out + (size_t)cur.b * CG * HW + cur.pix;

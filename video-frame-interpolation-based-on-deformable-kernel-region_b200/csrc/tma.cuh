@@ -20,6 +20,9 @@ bool encode_tensor_map_3d(CUtensorMap *map, const float *base, uint64_t W, uint6
 // instead of running into the next batch item.
 bool encode_tensor_map_4d(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t C, uint64_t N,
                           uint32_t boxW, uint32_t boxH, uint32_t boxC);
+// same with padded rows: extent W (reads past it are zero-filled), row pitch `row_pitch` elements (a multiple of 4)
+bool encode_tensor_map_4d_pitched(CUtensorMap *map, const float *base, uint64_t W, uint64_t H, uint64_t C, uint64_t N,
+                                  uint64_t row_pitch, uint32_t boxW, uint32_t boxH, uint32_t boxC);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
