@@ -306,7 +306,8 @@ def test_separableconvflow(lib, oracle, B, Ho, Wo, F):
 
 
 # ------------------------------------------------------------------------------ Correlation
-@pytest.mark.parametrize("B,C,H,W", [(1, 32, 64, 112), (2, 196, 4, 7), (1, 64, 18, 31), (2, 5, 9, 13), (1, 128, 8, 14)])
+@pytest.mark.parametrize("B,C,H,W", [(1, 32, 64, 112), (2, 196, 4, 7), (1, 64, 18, 31), (2, 5, 9, 13), (1, 128, 8, 14),
+                                     (8, 128, 36, 62)])   # last: PWC level 5 at 1080p x 8 -- odd width, row-padded TMA path
 def test_correlation_pwc_configuration(lib, oracle, B, C, H, W):
     r = U.rng(1700)
     f1, f2 = U.image(r, B, C, H, W, "normal"), U.image(r, B, C, H, W, "normal")
