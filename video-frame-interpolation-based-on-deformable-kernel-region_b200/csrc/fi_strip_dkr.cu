@@ -26,6 +26,7 @@
 namespace vfidkr {
 namespace strip {
 
+constexpr int LEAD_D = 3;                                        // lookahead of THIS kernel: 4 (fi_strip.cu's) costs registers it does not have
 constexpr int SUB_PLANES = 12;                                   // 4 filter + 4 offY + 4 offX planes per sub-stage
 constexpr int SUB_FLOATS = SUB_PLANES * NPIX;
 constexpr int GROUP_FLOATS = 4 * NPIX;                           // one TMA box: 4 planes x tile
@@ -153,7 +154,7 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 } else {
                     mode = MODE_SMEM;
                     const bool rebase = stale || bb.xmin < xorg || bb.xmax >= xorg + WB || bb.ymin < max(base, hi - RROWS);
-                    int oldest = max(0, t - LEAD);   // bbox_done(t): every compute warp has started tile t - LEAD
+                    int oldest = max(0, t - LEAD_D);   // bbox_done(t): every compute warp has started tile t - LEAD_D
                     if (rebase) {
                         for (; oldest < t; ++oldest) wait_pumping(&tile_done[oldest % NB], (uint32_t)((oldest / NB) & 1));
                         xorg = (bb.xmin - (slack >= 14 ? slack / 2 : 0)) & ~7;
@@ -251,23 +252,23 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             }
         };
 
-        float qx[LEAD + 1], qy[LEAD + 1], nx, ny;
+        float qx[LEAD_D + 1], qy[LEAD_D + 1], nx, ny;
 #pragma unroll
-        for (int k = 0; k < LEAD; ++k) {
+        for (int k = 0; k < LEAD_D; ++k) {
             request_flow(req, qx[k], qy[k]);
             advance(req);
         }
         request_flow(req, nx, ny);
         advance(req);
 #pragma unroll
-        for (int k = 0; k < LEAD; ++k) {
+        for (int k = 0; k < LEAD_D; ++k) {
             fold_box(fold, k, qx[k], qy[k]);
             advance(fold);
         }
 
         for (int j = 0; j < n; ++j) {
-            qx[LEAD] = nx; qy[LEAD] = ny;
-            fold_box(fold, j + LEAD, qx[LEAD], qy[LEAD]);
+            qx[LEAD_D] = nx; qy[LEAD_D] = ny;
+            fold_box(fold, j + LEAD_D, qx[LEAD_D], qy[LEAD_D]);
             advance(fold);
             request_flow(req, nx, ny);
             advance(req);
@@ -402,7 +403,7 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             if (lane == 0) mbar_arrive(&tile_done[sb]);
             advance(cur);
 #pragma unroll
-            for (int k = 0; k < LEAD; ++k) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; }
+            for (int k = 0; k < LEAD_D; ++k) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; }
         }
     }
 }
