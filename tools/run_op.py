@@ -61,6 +61,7 @@ ops = {
     "fi_dkr_bwd": lambda: _lib.call("vfidkr_filterinterpolation_backward_dkr", ptr(I), ptr(fl), ptr(ft), ptr(off), ptr(g),
                                     ptr(gi1), ptr(gi2), ptr(gi3), ptr(gi4), B, C, H, W, 4, sp),
     "interp_fwd": lambda: V.InterpolationChLayer.apply(I, fl),
+    "interp_bwd": lambda: _lib.call("vfidkr_interpolation_backward", ptr(I), ptr(fl), ptr(g), ptr(gi1), ptr(gi2), B, C, H, W, 0, sp),
     "proj_fwd": lambda: V.FlowProjectionLayer.apply(fl, False),
     "dproj_fwd": lambda: V.DepthFlowProjectionLayer.apply(fl, dep, False),
 }
