@@ -333,7 +333,7 @@ def bench_ours(args):
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_arm(steps=5, warmup=1)
-        print(json.dumps(line), flush=True)
+        emit_result(line)
     if args.table and rank == 0 and world == 1:
         op_table(torch, V, device, args.table)
     if world > 1:
@@ -476,7 +476,7 @@ def bench_reference_cuda(args, mods):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_arm(steps=3, warmup=1)
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 def bench_reference(args):
@@ -502,7 +502,7 @@ def bench_reference(args):
         "e2e": {"value": res["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_result(line)
 
 
 # ----------------------------------------------------------------------------- per-op table (not the bench line)
@@ -624,6 +624,18 @@ def op_table(torch, V, device, path):
         print(f"[op] {r['op']:34s} {r['ms']*1e3:10.1f} us  {r['GBps']:8.1f} GB/s  {100*r['frac_of_hbm']:5.1f} % of HBM peak", file=sys.stderr)
 
 
+_RESULT_FD = None
+
+
+def emit_result(line: dict) -> None:
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -637,6 +649,12 @@ def main():
     ap.add_argument("--reference-cpu", action="store_true", help="--impl reference: force the CPU oracle port")
     ap.add_argument("--table", default=None, help="also write the per-operator timing table (JSON lines) here")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON result: everything else a library may print there (NCCL's version banner
+    # under NCCL_DEBUG=VERSION, for instance) is sent to stderr, and the result goes to a private copy of the real stdout
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         bench_reference(args)
     else:
