@@ -550,6 +550,10 @@ def op_table(torch, V, device, path):
         fl_smooth = torch.stack([6 * torch.sin(xx) + 3 * torch.cos(yy), 5 * torch.cos(0.7 * xx) - 3 * torch.sin(yy)], 0)[None].repeat(B, 1, 1, 1).contiguous()
         add("FI_ori_fwd_C3_smoothflow", timeit(lambda: V.FilterInterpolationLayer.apply(I, fl_smooth, ft)), 96, px)
         del fl_smooth, yy, xx
+        # both directions warped and blended in two launches (2 x 84 B/px in, 12 B/px out)
+        I2 = torch.rand_like(I)
+        add("FI_ori_blend_two_directions_C3", timeit(lambda: V.filter_interpolate_blend(I, I2, fl, fl_up4, ft, ft)), 180, px)
+        del I2
         add("FI_dkr_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDKR.apply(I, fl, ft, off)), 224, px)
         add("FI_deforconv_fwd_C3", timeit(lambda: V.FilterInterpolationLayerDeforConv.apply(I, fl, ft, off)), 224, px)
         add("FI_nofilter_fwd_C3", timeit(lambda: V.FilterInterpolationLayerNoFilterWithDeforConv.apply(I, fl, off)), 160, px)

@@ -688,3 +688,33 @@ def test_pair_stream_matches_whole_batch(lib):
             assert torch.equal(outs[0], ref[0]), chunk
             # projection sums are atomically accumulated: order, hence rounding, may differ between calls
             assert (outs[1] - ref[1]).abs().max().item() <= 1e-4 * ref[1].abs().max().item(), chunk
+
+
+# ------------------------------------------------------------------------------ two directions + blend
+@pytest.mark.parametrize("B,C,H,W,w0,w2", [(2, 3, 96, 224, 0.5, 0.5),      # strip kernel (networks/DAIN.py:573)
+                                            (1, 3, 37, 70, 0.7, 0.3),       # direct kernel, (1-t), t (DAIN_slowmotion.py:335)
+                                            (1, 6, 20, 64, 0.25, 0.75)])    # C > 4: direct kernel in blend mode
+def test_fi_blend_two_directions(lib, oracle, B, C, H, W, w0, w2):
+    """filter_interpolate_blend = w0 * FI(ref0, ...) + w2 * FI(ref2, ...) in two launches with a blend epilogue
+    (no intermediate frames), forward and backward against the oracle composed the same way."""
+    r = U.rng(2900 + H + W)
+    I0, I2 = U.image(r, B, C, H, W), U.image(r, B, C, H, W)
+    f0, f2 = U.flow(r, B, H, W, "stress"), U.flow(r, B, H, W, "gauss")
+    k0, k2 = U.filt(r, B, 4, H, W), U.filt(r, B, 4, H, W, "uniform")
+    ts = [cu(a).requires_grad_() for a in (I0, I2, f0, f2, k0, k2)]
+    out = lib.filter_interpolate_blend(*ts, w0, w2)
+    ref = w0 * oracle.fi_forward("ori", I0, f0, k0) + w2 * oracle.fi_forward("ori", I2, f2, k2)
+    U.assert_close(host(out), ref, U.RTOL_FWD, "blend forward")
+    # the unfused composition gives the same numbers up to one rounding of the scaling
+    with torch.no_grad():
+        fi = lib.FilterInterpolationModule()
+        unfused = w0 * fi(ts[0], ts[2], ts[4]) + w2 * fi(ts[1], ts[3], ts[5])
+    assert (out.detach() - unfused).abs().max().item() < 1e-6
+    g = r.standard_normal((B, C, H, W)).astype(np.float32)
+    out.backward(cu(g))
+    a = oracle.fi_backward("ori", I0, f0, k0, None, (g * np.float32(w0)).astype(np.float32))
+    b = oracle.fi_backward("ori", I2, f2, k2, None, (g * np.float32(w2)).astype(np.float32))
+    for t, refg, tol, name in ((ts[0], a[0], U.RTOL_ATOMIC, "ref0"), (ts[1], b[0], U.RTOL_ATOMIC, "ref2"),
+                               (ts[2], a[1], U.RTOL_FWD, "offset0"), (ts[3], b[1], U.RTOL_FWD, "offset2"),
+                               (ts[4], a[2], U.RTOL_FWD, "filter0"), (ts[5], b[2], U.RTOL_FWD, "filter2")):
+        U.assert_close(host(t.grad), refg, tol, f"blend grad {name}")

@@ -7,7 +7,8 @@ C ABI of libvfidkr_b200.so (include/vfidkr_b200.h); there is no CPU or framework
 from . import _lib
 from ._lib import VfidkrError, abi_version, launch_count
 from .correlation import Correlation, CorrelationFunction, correlation_output_shape
-from .filter_interpolation import (FilterInterpolationLayer, FilterInterpolationLayerDeforConv,
+from .filter_interpolation import (FilterInterpolationBlendLayer, filter_interpolate_blend,
+                                   FilterInterpolationLayer, FilterInterpolationLayerDeforConv,
                                    FilterInterpolationLayerDKR, FilterInterpolationLayerNoFilterWithDeforConv,
                                    FilterInterpolationModule)
 from .flow_projection import (DepthFlowProjectionLayer, DepthFlowProjectionModule, FlowProjectionLayer,

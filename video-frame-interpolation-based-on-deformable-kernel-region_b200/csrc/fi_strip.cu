@@ -82,8 +82,10 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const __grid_constant__ CUtensorMap map_img,
                             const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
                             int H, int W, int tiles_x, int tiles_y, int nseg, int segt, int num_items,
-                            const FastDiv div_tiles_x, const FastDiv div_nseg, int *__restrict__ work_counter)
+                            const FastDiv div_tiles_x, const FastDiv div_nseg, int *__restrict__ work_counter,
+                            float scale, int accumulate)
 {
+    // epilogue (warp both directions and blend): output = scale * result (+ what output held)
     constexpr int SF = stages<CG>();
     constexpr int ROWF = row_floats<CG>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -370,6 +372,15 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 
             const int sf = j % SF, sb = j % NB;
             const float *ft = s_filt + sf * FILT_FLOATS + tid;
+            // blend mode: what the output holds is requested now, a whole tile's work before it is added
+            float prev[CG];
+#pragma unroll
+            for (int c = 0; c < CG; ++c) prev[c] = 0.0f;
+            if (accumulate && has_pixel(cur)) {
+                const float *op = out + (size_t)cur.b * CG * HW + cur.pix;
+#pragma unroll
+                for (int c = 0; c < CG; ++c) prev[c] = __ldcs(op + (size_t)c * HW);
+            }
 
             STAT_TIME(0, mbar_wait_backoff_a(a_img_full + sb * 8, (uint32_t)((j / NB) & 1)));
             STAT_INC(2);
@@ -390,7 +401,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 if (x2 < 0.0f) {   // out of range: :2814-2819 copies input1
                     const float *img = in1 + (size_t)cur.b * CG * HW + cur.pix;
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, __ldg(img + (size_t)c * HW));
+                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, scale * __ldg(img + (size_t)c * HW) + prev[c]);
                 } else {
                     const int ix = (int)x2, iy = (int)y2;
                     const int L = ix - 1, T = iy - 1;                       // window origin for F = 4 (:2745-2748)
@@ -442,7 +453,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, res[c]);
+                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, scale * res[c] + prev[c]);
                 }
             }
             __syncwarp();
@@ -457,7 +468,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 
 template <int CG>
 static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, float *out, int B, int H, int W,
-                  cudaStream_t s)
+                  float scale, int accumulate, cudaStream_t s)
 {
     CUtensorMap mimg;
     if (!encode_tensor_map_4d(&mimg, in1, W, H, CG, B, WB, 1, CG)) return -1;
@@ -476,7 +487,8 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
     e = set_error(cudaMemsetAsync(counter, 0, sizeof(int), s), "clear work counter");
     if (!e) {
         kernel<<<nblk, NTHREADS, smem_bytes<CG>(), s>>>(mfilt, mimg, in1, in2, out, H, W, tiles_x, tiles_y, nseg, segt, (int)items,
-                                                       FastDiv((unsigned)tiles_x), FastDiv((unsigned)nseg), static_cast<int *>(counter));
+                                                       FastDiv((unsigned)tiles_x), FastDiv((unsigned)nseg), static_cast<int *>(counter),
+                                                       scale, accumulate);
         note_launch();
         e = check_launch("filterinterpolation forward (strip)");
     }
@@ -499,7 +511,7 @@ extern "C" __attribute__((visibility("default"))) int vfidkr_debug_strip_stats(u
 
 // Returns VFIDKR_OK / VFIDKR_ERR_CUDA when the strip kernel was launched, -1 when it does not apply.
 int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
-                         int B, int C, int H, int W, cudaStream_t s)
+                         int B, int C, int H, int W, float scale, int accumulate, cudaStream_t s)
 {
     using namespace strip;
     if (C < 1 || C > 4 || W % 4 != 0 || W < WB) return -1;
@@ -507,10 +519,10 @@ int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, f
     CUtensorMap mfilt;
     if (!encode_tensor_map_3d(&mfilt, in3, W, H, (uint64_t)B * 16, TW, TH, 16)) return -1;
     switch (C) {
-    case 1: return launch<1>(mfilt, in1, in2, out, B, H, W, s);
-    case 2: return launch<2>(mfilt, in1, in2, out, B, H, W, s);
-    case 3: return launch<3>(mfilt, in1, in2, out, B, H, W, s);
-    default: return launch<4>(mfilt, in1, in2, out, B, H, W, s);
+    case 1: return launch<1>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
+    case 2: return launch<2>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
+    case 3: return launch<3>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
+    default: return launch<4>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
     }
 }
 

@@ -27,7 +27,7 @@
 namespace vfidkr {
 
 int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
-                         int B, int C, int H, int W, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
+                         int B, int C, int H, int W, float scale, int accumulate, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
 int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
                         int B, int C, int H, int W, cudaStream_t s);    // fi_bigc.cu (C > 4); -1 = not applicable
 int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
@@ -66,8 +66,14 @@ __host__ __device__ constexpr int minb_bwd(int V) { return V == V_ORI ? 3 : 2; }
 template <int FT>
 __global__ void __launch_bounds__(BX *BY, MINB_FWD_ORI)
 fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ in2, const float *__restrict__ in3,
-                      float *__restrict__ out, int C, int H, int W, int Frt)
+                      float *__restrict__ out, int C, int H, int W, int Frt, float scale, int accumulate)
 {
+    // epilogue: output = scale * result (+ what output held) -- see vfidkr_filterinterpolation_forward_ori_blend
+    auto put = [&](float *dst, float v) {
+        v *= scale;
+        if (accumulate) v += __ldcs(dst);
+        st_stream(dst, v);
+    };
     const int F = FT > 0 ? FT : Frt;
     const int w_i = blockIdx.x * BX + threadIdx.x;
     const int h_i = blockIdx.y * BY + threadIdx.y;
@@ -83,7 +89,7 @@ fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ i
     const float *img = in1 + (size_t)b * C * HW;
     float *o = out + (size_t)b * C * HW + pix;
     if (!p.in_range) {  // :2814-2819 copies input1
-        for (int c = 0; c < C; ++c) st_stream(o + (size_t)c * HW, __ldg(img + (size_t)c * HW + pix));
+        for (int c = 0; c < C; ++c) put(o + (size_t)c * HW, __ldg(img + (size_t)c * HW + pix));
         return;
     }
     const float *wp = in3 + (size_t)b * F * F * HW + pix;
@@ -109,7 +115,7 @@ fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ i
 #pragma unroll
                 for (int i = 0; i < FT; ++i)
                     Q[(j < FT / 2 ? 0 : 2) + (i < FT / 2 ? 0 : 1)] += __ldg(pl + ro[j] + co[i]) * w[j * FT + i];
-            st_stream(o + (size_t)c * HW, qTL * Q[0] + qTR * Q[1] + qBL * Q[2] + qBR * Q[3]);
+            put(o + (size_t)c * HW, qTL * Q[0] + qTR * Q[1] + qBL * Q[2] + qBR * Q[3]);
         }
     } else {
         for (int c = 0; c < C; ++c) {
@@ -123,7 +129,7 @@ fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ i
                     if (top) { if (left) TL += t; else TR += t; } else { if (left) BL += t; else BR += t; }
                 }
             }
-            st_stream(o + (size_t)c * HW, qTL * TL + qTR * TR + qBL * BL + qBR * BR);
+            put(o + (size_t)c * HW, qTL * TL + qTR * TR + qBL * BL + qBR * BR);
         }
     }
 }
@@ -503,8 +509,9 @@ fi_backward_kernel(const float *__restrict__ in1, const float *__restrict__ in2,
 // ---- launchers -----------------------------------------------------------------------------
 template <int V>
 int launch_forward(const float *in1, const float *in2, const float *in3, const float *in4, float *out,
-                   int B, int C, int H, int W, int F, cudaStream_t s)
+                   int B, int C, int H, int W, int F, cudaStream_t s, float scale = 1.0f, int accumulate = 0)
 {
+    const bool blend = scale != 1.0f || accumulate != 0;   // "_ori" only: strip kernel or direct kernel
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || F <= 0 || B > 65535) return VFIDKR_ERR_ARG;
     if (!in1 || !in2 || !in3 || !out || ((V == V_DKR || V == V_DEFOR) && !in4)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
@@ -512,18 +519,18 @@ int launch_forward(const float *in1, const float *in2, const float *in3, const f
     if constexpr (V == V_ORI) {
         if (F == 4) {
             const int path = forced_forward_path();
-            if (path == PATH_AUTO && C > 4) {
+            if (path == PATH_AUTO && C > 4 && !blend) {
                 // many channels (context features): shared-memory regions streamed channel group by channel group
                 const int e = fi_bigc_forward_ori(in1, in2, in3, out, B, C, H, W, s);
                 if (e >= 0) return e;
             }
             if (path == PATH_AUTO || path == PATH_STRIP) {
                 // production path: strip-walking kernel, image gathers from a rolling shared-memory window
-                const int e = fi_strip_forward_ori(in1, in2, in3, out, B, C, H, W, s);
+                const int e = fi_strip_forward_ori(in1, in2, in3, out, B, C, H, W, scale, accumulate, s);
                 if (e >= 0) return e;
             }
             // TMA-streamed taps, gathers through L1; needs 16-byte aligned rows for the tensor maps
-            if (W % 4 == 0 && aligned16(in2) && aligned16(in3) && path != PATH_DIRECT) {
+            if (W % 4 == 0 && aligned16(in2) && aligned16(in3) && path != PATH_DIRECT && !blend) {
                 using namespace tmafwd;
                 CUtensorMap mflow, mfilt;
                 if (encode_tensor_map_3d(&mflow, in2, W, H, (uint64_t)B * 2, TW, TH, 2) &&
@@ -544,9 +551,9 @@ int launch_forward(const float *in1, const float *in2, const float *in3, const f
                     }
                 }
             }
-            fi_forward_ori_kernel<4><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
+            fi_forward_ori_kernel<4><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F, scale, accumulate);
         } else {
-            fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F);
+            fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F, scale, accumulate);
         }
     } else if (F == 4) {
         if (forced_forward_path() != PATH_DIRECT) {
@@ -594,6 +601,11 @@ using namespace vfidkr;
 VFIDKR_API int vfidkr_filterinterpolation_forward_ori(const float *i1, const float *i2, const float *i3, float *out,
                                                       int B, int C, int H, int W, int F, vfidkr_stream_t s)
 { return launch_forward<V_ORI>(i1, i2, i3, nullptr, out, B, C, H, W, F, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_filterinterpolation_forward_ori_blend(const float *i1, const float *i2, const float *i3, float *out,
+                                                            int B, int C, int H, int W, int F, float scale, int accumulate,
+                                                            vfidkr_stream_t s)
+{ return launch_forward<V_ORI>(i1, i2, i3, nullptr, out, B, C, H, W, F, (cudaStream_t)s, scale, accumulate != 0); }
 
 VFIDKR_API int vfidkr_filterinterpolation_backward_ori(const float *i1, const float *i2, const float *i3,
                                                        const float *g, float *gi1, float *gi2, float *gi3,

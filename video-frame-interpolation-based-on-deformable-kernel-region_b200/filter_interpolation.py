@@ -152,6 +152,53 @@ _THREE_INPUT = {"ori": FilterInterpolationLayer, "nofilterwithdeforconv": Filter
 _FOUR_INPUT = {"dkr": FilterInterpolationLayerDKR, "deforconv": FilterInterpolationLayerDeforConv}
 
 
+class FilterInterpolationBlendLayer(Function):
+    """Warps both temporal directions with the "_ori" family and blends them in the same two launches:
+    w0 * FI(ref0, offset0, filter0) + w2 * FI(ref2, offset2, filter2) -- `ref0/2 + ref2/2` of networks/DAIN.py:573
+    (w0 = w2 = 0.5) and `(1-t)*ref0 + t*ref2` of DAIN_slowmotion.py:335 -- without the two intermediate frames and the
+    blend pass.  The backward runs the two "_ori" backward kernels on the scaled gradient."""
+
+    @staticmethod
+    def forward(ctx, ref0, ref2, offset0, offset2, filter0, filter2, w0=0.5, w2=0.5):
+        for t, n in ((ref0, "ref0"), (ref2, "ref2"), (offset0, "offset0"), (offset2, "offset2"),
+                     (filter0, "filter0"), (filter2, "filter2")):
+            check_input(t, n)
+        B, C, H, W, F = _check_shapes(ref0, offset0, filter0)
+        if _check_shapes(ref2, offset2, filter2) != (B, C, H, W, F):
+            raise _lib.VfidkrError("both directions must have the same shapes")
+        output = torch.empty_like(ref0)
+        with torch.cuda.device(ref0.device):
+            sp = stream_ptr(ref0.device)
+            _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(ref0), ptr(offset0), ptr(filter0), ptr(output),
+                      B, C, H, W, F, float(w0), 0, sp)
+            _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(ref2), ptr(offset2), ptr(filter2), ptr(output),
+                      B, C, H, W, F, float(w2), 1, sp)
+        ctx.save_for_backward(ref0, ref2, offset0, offset2, filter0, filter2)
+        ctx.weights = (float(w0), float(w2))
+        return output
+
+    @staticmethod
+    def backward(ctx, gradoutput):
+        ref0, ref2, offset0, offset2, filter0, filter2 = ctx.saved_tensors
+        B, C, H, W = ref0.shape
+        F = _filter_size(filter0.shape[1])
+        grads = []
+        with torch.cuda.device(ref0.device):
+            for img, off, flt, wgt in ((ref0, offset0, filter0, ctx.weights[0]), (ref2, offset2, filter2, ctx.weights[1])):
+                g = (gradoutput * wgt).contiguous()
+                gi1, gi2, gi3 = torch.empty_like(img), torch.empty_like(off), torch.empty_like(flt)
+                _lib.call("vfidkr_filterinterpolation_backward_ori", ptr(img), ptr(off), ptr(flt), ptr(g),
+                          ptr(gi1), ptr(gi2), ptr(gi3), B, C, H, W, F, stream_ptr(img.device))
+                grads.append((gi1, gi2, gi3))
+        (a1, a2, a3), (b1, b2, b3) = grads
+        return a1, b1, a2, b2, a3, b3, None, None
+
+
+def filter_interpolate_blend(ref0, ref2, offset0, offset2, filter0, filter2, w0=0.5, w2=0.5):
+    """w0 * FilterInterpolation(ref0, offset0, filter0) + w2 * FilterInterpolation(ref2, offset2, filter2), fused."""
+    return FilterInterpolationBlendLayer.apply(ref0, ref2, offset0, offset2, filter0, filter2, w0, w2)
+
+
 class FilterInterpolationModule(Module):
     """FilterInterpolationModule()(input1, input2, input3)            -> "_ori" (FilterInterpolationModule.py:13-17)
     FilterInterpolationModule()(input1, input2, input3, input4)      -> 4-input DKR (:18-20)
