@@ -61,11 +61,15 @@ int vfidkr_filterinterpolation_forward_ori(const float *input1, const float *inp
                                            vfidkr_stream_t stream);
 /* The same forward with a blend epilogue: output = scale * FI(input1, input2, input3) (+ output's previous contents when
  * accumulate != 0).  Two calls warp both directions and blend them -- ref0/2 + ref2/2 (networks/DAIN.py:573),
- * (1-t)*ref0 + t*ref2 (DAIN_slowmotion.py:335) -- without the two intermediate frames and the blend pass.  The
- * reference has no such symbol; scale = 1, accumulate = 0 is vfidkr_filterinterpolation_forward_ori. */
+ * (1-t)*ref0 + t*ref2 (DAIN_slowmotion.py:335) -- without the two intermediate frames and the blend pass.
+ * out_batch_stride (elements; 0 = dense, C*H*W) lets `output` be a channel slice of a wider tensor, e.g. the
+ * rectify-input concat of networks/DAIN.py:264-269: channels stay H*W apart, batch items out_batch_stride apart.
+ * The reference has no such symbol; scale = 1, accumulate = 0, out_batch_stride = 0 is
+ * vfidkr_filterinterpolation_forward_ori. */
 int vfidkr_filterinterpolation_forward_ori_blend(const float *input1, const float *input2, const float *input3,
                                                  float *output, int B, int C, int H, int W, int filter_size,
-                                                 float scale, int accumulate, vfidkr_stream_t stream);
+                                                 float scale, int accumulate, long long out_batch_stride,
+                                                 vfidkr_stream_t stream);
 /* replaces ..._gpu_backward_ori (filterinterpolation_cuda.cc:608-687; kernel :2827-3125) */
 int vfidkr_filterinterpolation_backward_ori(const float *input1, const float *input2, const float *input3,
                                             const float *gradoutput, float *gradinput1, float *gradinput2,

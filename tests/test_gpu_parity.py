@@ -718,3 +718,21 @@ def test_fi_blend_two_directions(lib, oracle, B, C, H, W, w0, w2):
                                (ts[2], a[1], U.RTOL_FWD, "offset0"), (ts[3], b[1], U.RTOL_FWD, "offset2"),
                                (ts[4], a[2], U.RTOL_FWD, "filter0"), (ts[5], b[2], U.RTOL_FWD, "filter2")):
         U.assert_close(host(t.grad), refg, tol, f"blend grad {name}")
+
+
+def test_fi_blend_writes_into_a_channel_slice(lib):
+    """out= : the blended frame goes straight into a channel slice of a wider tensor (the rectify-input concat of
+    networks/DAIN.py:264-269), other channels untouched; strip kernel (W = 224) and direct kernel (W = 70)."""
+    for (B, C, H, W) in [(2, 3, 96, 224), (2, 3, 37, 70)]:
+        g = torch.Generator(device="cuda").manual_seed(H)
+        I0, I2 = (torch.rand(B, C, H, W, device="cuda", generator=g) for _ in range(2))
+        f0, f2 = ((torch.randn(B, 2, H, W, device="cuda", generator=g) * 3) for _ in range(2))
+        k0, k2 = (torch.softmax(torch.randn(B, 16, H, W, device="cuda", generator=g), 1) for _ in range(2))
+        with torch.no_grad():
+            ref = lib.filter_interpolate_blend(I0, I2, f0, f2, k0, k2, 0.3, 0.7)
+            cat = torch.full((B, 11, H, W), -5.0, device="cuda")
+            ret = lib.filter_interpolate_blend(I0, I2, f0, f2, k0, k2, 0.3, 0.7, out=cat[:, 4:7])
+        assert torch.equal(cat[:, 4:7], ref) and ret.data_ptr() == cat[:, 4:7].data_ptr()
+        assert (cat[:, :4] == -5).all() and (cat[:, 7:] == -5).all()
+    with pytest.raises(lib.VfidkrError):   # not differentiable through out=
+        lib.filter_interpolate_blend(I0.requires_grad_(), I2, f0, f2, k0, k2, out=cat[:, 4:7])

@@ -6,7 +6,7 @@ PyTorch is used by the callers only for device memory and streams; no torch type
 from __future__ import annotations
 
 import ctypes
-from ctypes import c_float, c_int, c_void_p
+from ctypes import c_float, c_int, c_longlong, c_void_p
 from pathlib import Path
 
 PKG_DIR = Path(__file__).resolve().parent
@@ -26,7 +26,7 @@ _I = c_int
 # name -> argtypes (restype is always int unless listed in _SPECIAL)
 _SIGNATURES = {
     "vfidkr_filterinterpolation_forward_ori": [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P],
-    "vfidkr_filterinterpolation_forward_ori_blend": [_P, _P, _P, _P, _I, _I, _I, _I, _I, c_float, _I, _P],
+    "vfidkr_filterinterpolation_forward_ori_blend": [_P, _P, _P, _P, _I, _I, _I, _I, _I, c_float, _I, c_longlong, _P],
     "vfidkr_filterinterpolation_backward_ori": [_P] * 7 + [_I] * 5 + [_P],
     "vfidkr_filterinterpolation_forward_dkr": [_P] * 5 + [_I] * 5 + [_P],
     "vfidkr_filterinterpolation_backward_dkr": [_P] * 9 + [_I] * 5 + [_P],

@@ -83,7 +83,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                             const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
                             int H, int W, int tiles_x, int tiles_y, int nseg, int segt, int num_items,
                             const FastDiv div_tiles_x, const FastDiv div_nseg, int *__restrict__ work_counter,
-                            float scale, int accumulate)
+                            float scale, int accumulate, size_t out_bs)
 {
     // epilogue (warp both directions and blend): output = scale * result (+ what output held)
     constexpr int SF = stages<CG>();
@@ -377,7 +377,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 #pragma unroll
             for (int c = 0; c < CG; ++c) prev[c] = 0.0f;
             if (accumulate && has_pixel(cur)) {
-                const float *op = out + (size_t)cur.b * CG * HW + cur.pix;
+                const float *op = out + (size_t)cur.b * out_bs + cur.pix;   // out_bs: elements between batch items of the output
 #pragma unroll
                 for (int c = 0; c < CG; ++c) prev[c] = __ldcs(op + (size_t)c * HW);
             }
@@ -396,7 +396,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             if (lane == 0) mbar_arrive_a(a_filt_free + sf * 8);   // release: this warp's reads of stage sf are complete
 
             if (has_pixel(cur)) {
-                float *o = out + (size_t)cur.b * CG * HW + cur.pix;
+                float *o = out + (size_t)cur.b * out_bs + cur.pix;
                 const float x2 = qx[0], y2 = qy[0];
                 if (x2 < 0.0f) {   // out of range: :2814-2819 copies input1
                     const float *img = in1 + (size_t)cur.b * CG * HW + cur.pix;
@@ -468,7 +468,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 
 template <int CG>
 static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, float *out, int B, int H, int W,
-                  float scale, int accumulate, cudaStream_t s)
+                  float scale, int accumulate, size_t out_bs, cudaStream_t s)
 {
     CUtensorMap mimg;
     if (!encode_tensor_map_4d(&mimg, in1, W, H, CG, B, WB, 1, CG)) return -1;
@@ -488,7 +488,7 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
     if (!e) {
         kernel<<<nblk, NTHREADS, smem_bytes<CG>(), s>>>(mfilt, mimg, in1, in2, out, H, W, tiles_x, tiles_y, nseg, segt, (int)items,
                                                        FastDiv((unsigned)tiles_x), FastDiv((unsigned)nseg), static_cast<int *>(counter),
-                                                       scale, accumulate);
+                                                       scale, accumulate, out_bs);
         note_launch();
         e = check_launch("filterinterpolation forward (strip)");
     }
@@ -511,7 +511,7 @@ extern "C" __attribute__((visibility("default"))) int vfidkr_debug_strip_stats(u
 
 // Returns VFIDKR_OK / VFIDKR_ERR_CUDA when the strip kernel was launched, -1 when it does not apply.
 int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
-                         int B, int C, int H, int W, float scale, int accumulate, cudaStream_t s)
+                         int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s)
 {
     using namespace strip;
     if (C < 1 || C > 4 || W % 4 != 0 || W < WB) return -1;
@@ -519,10 +519,10 @@ int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, f
     CUtensorMap mfilt;
     if (!encode_tensor_map_3d(&mfilt, in3, W, H, (uint64_t)B * 16, TW, TH, 16)) return -1;
     switch (C) {
-    case 1: return launch<1>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
-    case 2: return launch<2>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
-    case 3: return launch<3>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
-    default: return launch<4>(mfilt, in1, in2, out, B, H, W, scale, accumulate, s);
+    case 1: return launch<1>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+    case 2: return launch<2>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+    case 3: return launch<3>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+    default: return launch<4>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
     }
 }
 

@@ -27,7 +27,7 @@
 namespace vfidkr {
 
 int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
-                         int B, int C, int H, int W, float scale, int accumulate, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
+                         int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
 int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
                         int B, int C, int H, int W, cudaStream_t s);    // fi_bigc.cu (C > 4); -1 = not applicable
 int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
@@ -66,7 +66,7 @@ __host__ __device__ constexpr int minb_bwd(int V) { return V == V_ORI ? 3 : 2; }
 template <int FT>
 __global__ void __launch_bounds__(BX *BY, MINB_FWD_ORI)
 fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ in2, const float *__restrict__ in3,
-                      float *__restrict__ out, int C, int H, int W, int Frt, float scale, int accumulate)
+                      float *__restrict__ out, int C, int H, int W, int Frt, float scale, int accumulate, size_t out_bs)
 {
     // epilogue: output = scale * result (+ what output held) -- see vfidkr_filterinterpolation_forward_ori_blend
     auto put = [&](float *dst, float v) {
@@ -87,7 +87,7 @@ fi_forward_ori_kernel(const float *__restrict__ in1, const float *__restrict__ i
     const FiPix p = fi_pixel(w_i, h_i, fx, fy, W, H, F);
 
     const float *img = in1 + (size_t)b * C * HW;
-    float *o = out + (size_t)b * C * HW + pix;
+    float *o = out + (size_t)b * out_bs + pix;   // out_bs: elements between batch items of the output
     if (!p.in_range) {  // :2814-2819 copies input1
         for (int c = 0; c < C; ++c) put(o + (size_t)c * HW, __ldg(img + (size_t)c * HW + pix));
         return;
@@ -509,9 +509,10 @@ fi_backward_kernel(const float *__restrict__ in1, const float *__restrict__ in2,
 // ---- launchers -----------------------------------------------------------------------------
 template <int V>
 int launch_forward(const float *in1, const float *in2, const float *in3, const float *in4, float *out,
-                   int B, int C, int H, int W, int F, cudaStream_t s, float scale = 1.0f, int accumulate = 0)
+                   int B, int C, int H, int W, int F, cudaStream_t s, float scale = 1.0f, int accumulate = 0, size_t out_bs = 0)
 {
-    const bool blend = scale != 1.0f || accumulate != 0;   // "_ori" only: strip kernel or direct kernel
+    if (out_bs == 0) out_bs = (size_t)C * H * W;   // dense output
+    const bool blend = scale != 1.0f || accumulate != 0 || out_bs != (size_t)C * H * W;   // "_ori" only: strip kernel or direct kernel
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || F <= 0 || B > 65535) return VFIDKR_ERR_ARG;
     if (!in1 || !in2 || !in3 || !out || ((V == V_DKR || V == V_DEFOR) && !in4)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
@@ -526,7 +527,7 @@ int launch_forward(const float *in1, const float *in2, const float *in3, const f
             }
             if (path == PATH_AUTO || path == PATH_STRIP) {
                 // production path: strip-walking kernel, image gathers from a rolling shared-memory window
-                const int e = fi_strip_forward_ori(in1, in2, in3, out, B, C, H, W, scale, accumulate, s);
+                const int e = fi_strip_forward_ori(in1, in2, in3, out, B, C, H, W, scale, accumulate, out_bs, s);
                 if (e >= 0) return e;
             }
             // TMA-streamed taps, gathers through L1; needs 16-byte aligned rows for the tensor maps
@@ -551,9 +552,9 @@ int launch_forward(const float *in1, const float *in2, const float *in3, const f
                     }
                 }
             }
-            fi_forward_ori_kernel<4><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F, scale, accumulate);
+            fi_forward_ori_kernel<4><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F, scale, accumulate, out_bs);
         } else {
-            fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F, scale, accumulate);
+            fi_forward_ori_kernel<0><<<grid, block, 0, s>>>(in1, in2, in3, out, C, H, W, F, scale, accumulate, out_bs);
         }
     } else if (F == 4) {
         if (forced_forward_path() != PATH_DIRECT) {
@@ -604,8 +605,11 @@ VFIDKR_API int vfidkr_filterinterpolation_forward_ori(const float *i1, const flo
 
 VFIDKR_API int vfidkr_filterinterpolation_forward_ori_blend(const float *i1, const float *i2, const float *i3, float *out,
                                                             int B, int C, int H, int W, int F, float scale, int accumulate,
-                                                            vfidkr_stream_t s)
-{ return launch_forward<V_ORI>(i1, i2, i3, nullptr, out, B, C, H, W, F, (cudaStream_t)s, scale, accumulate != 0); }
+                                                            long long out_batch_stride, vfidkr_stream_t s)
+{
+    if (out_batch_stride != 0 && out_batch_stride < (long long)C * H * W) return VFIDKR_ERR_ARG;
+    return launch_forward<V_ORI>(i1, i2, i3, nullptr, out, B, C, H, W, F, (cudaStream_t)s, scale, accumulate != 0, (size_t)out_batch_stride);
+}
 
 VFIDKR_API int vfidkr_filterinterpolation_backward_ori(const float *i1, const float *i2, const float *i3,
                                                        const float *g, float *gi1, float *gi2, float *gi3,

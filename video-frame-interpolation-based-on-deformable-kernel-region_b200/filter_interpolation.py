@@ -159,20 +159,29 @@ class FilterInterpolationBlendLayer(Function):
     blend pass.  The backward runs the two "_ori" backward kernels on the scaled gradient."""
 
     @staticmethod
-    def forward(ctx, ref0, ref2, offset0, offset2, filter0, filter2, w0=0.5, w2=0.5):
+    def forward(ctx, ref0, ref2, offset0, offset2, filter0, filter2, w0=0.5, w2=0.5, out=None):
         for t, n in ((ref0, "ref0"), (ref2, "ref2"), (offset0, "offset0"), (offset2, "offset2"),
                      (filter0, "filter0"), (filter2, "filter2")):
             check_input(t, n)
         B, C, H, W, F = _check_shapes(ref0, offset0, filter0)
         if _check_shapes(ref2, offset2, filter2) != (B, C, H, W, F):
             raise _lib.VfidkrError("both directions must have the same shapes")
-        output = torch.empty_like(ref0)
+        if out is None:
+            output, bs = torch.empty_like(ref0), 0
+        else:
+            # a channel slice of a wider contiguous tensor (e.g. the rectify-input concat): channels H*W apart, any batch stride
+            if out.shape != ref0.shape or out.dtype != torch.float32 or out.device != ref0.device or \
+                    tuple(out.stride()[1:]) != (H * W, W, 1) or out.stride(0) < C * H * W:
+                raise _lib.VfidkrError("out must be a float32 [B,C,H,W] view with strides (>= C*H*W, H*W, W, 1) on the inputs' device")
+            output, bs = out, out.stride(0)
         with torch.cuda.device(ref0.device):
             sp = stream_ptr(ref0.device)
-            _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(ref0), ptr(offset0), ptr(filter0), ptr(output),
-                      B, C, H, W, F, float(w0), 0, sp)
-            _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(ref2), ptr(offset2), ptr(filter2), ptr(output),
-                      B, C, H, W, F, float(w2), 1, sp)
+            _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(ref0), ptr(offset0), ptr(filter0), output.data_ptr(),
+                      B, C, H, W, F, float(w0), 0, bs, sp)
+            _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(ref2), ptr(offset2), ptr(filter2), output.data_ptr(),
+                      B, C, H, W, F, float(w2), 1, bs, sp)
+        if out is not None:
+            ctx.mark_dirty(out)
         ctx.save_for_backward(ref0, ref2, offset0, offset2, filter0, filter2)
         ctx.weights = (float(w0), float(w2))
         return output
@@ -191,12 +200,15 @@ class FilterInterpolationBlendLayer(Function):
                           ptr(gi1), ptr(gi2), ptr(gi3), B, C, H, W, F, stream_ptr(img.device))
                 grads.append((gi1, gi2, gi3))
         (a1, a2, a3), (b1, b2, b3) = grads
-        return a1, b1, a2, b2, a3, b3, None, None
+        return a1, b1, a2, b2, a3, b3, None, None, None
 
 
-def filter_interpolate_blend(ref0, ref2, offset0, offset2, filter0, filter2, w0=0.5, w2=0.5):
-    """w0 * FilterInterpolation(ref0, offset0, filter0) + w2 * FilterInterpolation(ref2, offset2, filter2), fused."""
-    return FilterInterpolationBlendLayer.apply(ref0, ref2, offset0, offset2, filter0, filter2, w0, w2)
+def filter_interpolate_blend(ref0, ref2, offset0, offset2, filter0, filter2, w0=0.5, w2=0.5, out=None):
+    """w0 * FilterInterpolation(ref0, offset0, filter0) + w2 * FilterInterpolation(ref2, offset2, filter2), fused.
+    `out` (inference): a [B,C,H,W] channel slice of a wider contiguous tensor to write into, e.g. `cat[:, 3:6]`."""
+    if out is not None and torch.is_grad_enabled() and any(t.requires_grad for t in (ref0, ref2, offset0, offset2, filter0, filter2)):
+        raise _lib.VfidkrError("out= is for inference (no_grad): writing into a slice of another tensor is not differentiable here")
+    return FilterInterpolationBlendLayer.apply(ref0, ref2, offset0, offset2, filter0, filter2, w0, w2, out)
 
 
 class FilterInterpolationModule(Module):
