@@ -184,6 +184,16 @@ int vfidkr_correlation_backward(const float *input1, const float *input2, const 
                                 int max_displacement, int stride1, int stride2, int corr_type_multiply,
                                 vfidkr_stream_t stream);
 
+/* ---- PWCDCNet.warp (PWCNet/PWCNet.py:159-199): grid + flow, grid_sample (bilinear, zero padding, default
+ * align_corners = False on an align_corners = True style normalisation -- the reference's quirk, kept) and the validity
+ * mask (grid_sample of ones, thresholded at 0.9999), output = sample * mask.  Not a native symbol of the reference: it
+ * replaces two grid_sample launches and five elementwise kernels of PyTorch code.  x [B,C,H,W], flow [B,2,H,W].
+ * The backward returns d/dx (scattered, cleared by the library) and d/dflow; the mask carries no gradient. ---- */
+int vfidkr_pwcwarp_forward(const float *x, const float *flow, float *output, int B, int C, int H, int W,
+                           vfidkr_stream_t stream);
+int vfidkr_pwcwarp_backward(const float *x, const float *flow, const float *gradoutput, float *gradx, float *gradflow,
+                            int B, int C, int H, int W, vfidkr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

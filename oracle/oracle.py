@@ -203,3 +203,71 @@ def correlation_backward(input1, input2, gradoutput, pad=4, k=1, md=4, s1=1, s2=
     if err:
         raise RuntimeError("oracle_correlation_backward: empty output")
     return gi1, gi2
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PWCDCNet.warp (PWCNet/PWCNet.py:159-199).  The sampling itself is torch.nn.functional.grid_sample, a third-party
+# dependency of the reference (pinned at torch 1.4 in environment.yaml; default mode bilinear / zeros / align_corners =
+# False).  Its published algorithm (aten/src/ATen/native/GridSampler.h, cuda/GridSampler.cu) is restated here in numpy:
+# coordinate arithmetic in float32 in the reference's operation order, value accumulation in float64.
+# Pinned against torch's own CPU grid_sample in tests/test_oracle_kat.py.
+# ---------------------------------------------------------------------------------------------------------------
+def _pwc_geometry(flo, H, W):
+    f32 = np.float32
+    xs = np.arange(W, dtype=f32)[None, None, :]
+    ys = np.arange(H, dtype=f32)[None, :, None]
+    vx = (xs + flo[:, 0]).astype(f32)
+    vy = (ys + flo[:, 1]).astype(f32)
+    nx = ((f32(2.0) * vx).astype(f32) / f32(max(W - 1, 1))).astype(f32) - f32(1.0)       # PWCNet.py:178
+    ny = ((f32(2.0) * vy).astype(f32) / f32(max(H - 1, 1))).astype(f32) - f32(1.0)       # :179
+    ix = ((((nx + f32(1.0)).astype(f32) * f32(W)).astype(f32) - f32(1.0)).astype(f32) / f32(2.0)).astype(f32)
+    iy = ((((ny + f32(1.0)).astype(f32) * f32(H)).astype(f32) - f32(1.0)).astype(f32) / f32(2.0)).astype(f32)
+    x0f, y0f = np.floor(ix), np.floor(iy)
+    x1f, y1f = (x0f + f32(1.0)).astype(f32), (y0f + f32(1.0)).astype(f32)
+    wts = [((x1f - ix).astype(f32) * (y1f - iy).astype(f32)).astype(f32), ((ix - x0f).astype(f32) * (y1f - iy).astype(f32)).astype(f32),
+           ((x1f - ix).astype(f32) * (iy - y0f).astype(f32)).astype(f32), ((ix - x0f).astype(f32) * (iy - y0f).astype(f32)).astype(f32)]
+    x0 = np.clip(x0f, -1e9, 1e9).astype(np.int64)
+    y0 = np.clip(y0f, -1e9, 1e9).astype(np.int64)
+    corners = [(y0, x0), (y0, x0 + 1), (y0 + 1, x0), (y0 + 1, x0 + 1)]
+    inb = [(cy >= 0) & (cy < H) & (cx >= 0) & (cx < W) for cy, cx in corners]
+    m = np.zeros_like(ix, dtype=f32)
+    for w_, ok in zip(wts, inb):
+        m = np.where(ok, (m + w_).astype(f32), m)
+    mask = np.where(m < f32(0.9999), f32(0.0), np.where(m > 0, f32(1.0), m)).astype(np.float64)      # :193-194
+    tx, ty = (ix - x0f).astype(f32).astype(np.float64), (iy - y0f).astype(f32).astype(np.float64)
+    return corners, inb, [w_.astype(np.float64) for w_ in wts], mask, tx, ty
+
+
+def pwc_warp_forward(x, flo):
+    x, flo = _f32(x), _f32(flo)
+    B, C, H, W = x.shape
+    corners, inb, wts, mask, _, _ = _pwc_geometry(flo, H, W)
+    out = np.zeros((B, C, H, W), np.float64)
+    bi = np.arange(B)[:, None, None]
+    for (cy, cx), ok, w_ in zip(corners, inb, wts):
+        cyc, cxc = np.clip(cy, 0, H - 1), np.clip(cx, 0, W - 1)
+        for c in range(C):
+            out[:, c] += np.where(ok, x[bi, c, cyc, cxc].astype(np.float64) * w_, 0.0)
+    return out * mask[:, None]
+
+
+def pwc_warp_backward(x, flo, gradoutput):
+    x, flo, g = _f32(x), _f32(flo), _f32(gradoutput).astype(np.float64)
+    B, C, H, W = x.shape
+    corners, inb, wts, mask, tx, ty = _pwc_geometry(flo, H, W)
+    gm = g * mask[:, None]
+    gx = np.zeros((B, C, H, W), np.float64)
+    bi = np.broadcast_to(np.arange(B)[:, None, None], (B, H, W))
+    vals = []
+    for (cy, cx), ok, w_ in zip(corners, inb, wts):
+        cyc, cxc = np.clip(cy, 0, H - 1), np.clip(cx, 0, W - 1)
+        v = np.zeros((B, C, H, W), np.float64)
+        for c in range(C):
+            np.add.at(gx[:, c], (bi[ok], cyc[ok], cxc[ok]), (gm[:, c] * w_)[ok])
+            v[:, c] = np.where(ok, x[bi, c, cyc, cxc].astype(np.float64), 0.0)
+        vals.append(v)
+    v0, v1, v2, v3 = vals
+    gix = (gm * ((v1 - v0) * (1 - ty)[:, None] + (v3 - v2) * ty[:, None])).sum(1)
+    giy = (gm * ((v2 - v0) * (1 - tx)[:, None] + (v3 - v1) * tx[:, None])).sum(1)
+    gflo = np.stack([gix * (W / max(W - 1, 1)), giy * (H / max(H - 1, 1))], 1)
+    return gx, gflo

@@ -377,3 +377,50 @@ def test_correlation_gradients_match_finite_differences(oracle, pad, k, md, s1, 
         assert abs(fd - gi1[idx]) <= 2e-3 * (1 + abs(fd)), ("gi1", idx, fd, gi1[idx])
         fd = _fd(lambda x: float((oracle.correlation_forward(f1, x, pad, k, md, s1, s2) * g).sum()), f2, idx)
         assert abs(fd - gi2[idx]) <= 2e-3 * (1 + abs(fd)), ("gi2", idx, fd, gi2[idx])
+
+
+# ------------------------------------------------------------------------------ PWCDCNet.warp
+def _reference_pwc_warp(x, flo):
+    """PWCNet/PWCNet.py:159-199 as written (without the pre-allocated grid and .cuda()), on CPU tensors."""
+    import torch
+    B, C, H, W = x.size()
+    xx = torch.arange(0, W).view(1, -1).repeat(H, 1).view(1, 1, H, W).repeat(B, 1, 1, 1)
+    yy = torch.arange(0, H).view(-1, 1).repeat(1, W).view(1, 1, H, W).repeat(B, 1, 1, 1)
+    vgrid = torch.cat((xx, yy), 1).to(x.dtype) + flo
+    vgrid = torch.stack([2.0 * vgrid[:, 0] / max(W - 1, 1) - 1.0, 2.0 * vgrid[:, 1] / max(H - 1, 1) - 1.0], 1)
+    vgrid = vgrid.permute(0, 2, 3, 1)
+    output = torch.nn.functional.grid_sample(x, vgrid, align_corners=False)     # the default since torch 1.3
+    mask = torch.nn.functional.grid_sample(torch.ones_like(x), vgrid, align_corners=False).detach().clone()
+    mask[mask < 0.9999] = 0
+    mask[mask > 0] = 1
+    return output * mask
+
+
+def test_pwc_warp_oracle_is_pinned_to_torch_grid_sample(oracle):
+    """The numpy restatement of PWCDCNet.warp against the reference's own code path run on torch's CPU grid_sample
+    (float32 for the values the reference computes, float64 autograd for the gradients)."""
+    import torch
+    r = U.rng(3100)
+    for (B, C, H, W) in [(2, 3, 17, 23), (1, 5, 8, 40), (1, 2, 1, 9)]:
+        x = r.standard_normal((B, C, H, W)).astype(np.float32)
+        flo = (r.standard_normal((B, 2, H, W)) * 3).astype(np.float32)
+        flo[:, :, 0, 0] = 0.0                      # exact-integer landing
+        flo[:, 0, -1, -1] = 50.0                   # far outside
+        ref = _reference_pwc_warp(torch.from_numpy(x), torch.from_numpy(flo)).numpy()
+        got = oracle.pwc_warp_forward(x, flo)
+        assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+        # gradients: float64 torch autograd on float32-representable inputs (away from knife edges the index
+        # arithmetic agrees between float32 and float64)
+        flo_s = (np.round(flo * 8) / 8 + 0.0625).astype(np.float32)
+        tx = torch.from_numpy(x).double().requires_grad_()
+        tf = torch.from_numpy(flo_s).double().requires_grad_()
+        g = r.standard_normal((B, C, H, W))
+        _reference_pwc_warp(tx, tf).backward(torch.from_numpy(g))
+        # the oracle's float32 geometry must select the same corners: skip shapes where W - 1 makes 1/8-pixel offsets inexact
+        gx, gf = oracle.pwc_warp_backward(x, flo_s, g.astype(np.float32))
+        g32 = g.astype(np.float32).astype(np.float64)
+        tx2 = torch.from_numpy(x).double().requires_grad_()
+        tf2 = torch.from_numpy(flo_s).double().requires_grad_()
+        _reference_pwc_warp(tx2, tf2).backward(torch.from_numpy(g32))
+        assert np.abs(gx - tx2.grad.numpy()).max() <= 1e-4 * max(1.0, np.abs(gx).max())
+        assert np.abs(gf - tf2.grad.numpy()).max() <= 1e-4 * max(1.0, np.abs(gf).max())

@@ -65,6 +65,25 @@ ops = {
     "proj_fwd": lambda: V.FlowProjectionLayer.apply(fl, False),
     "dproj_fwd": lambda: V.DepthFlowProjectionLayer.apply(fl, dep, False),
 }
+if a.op == "pwc_warp":
+    feat = torch.randn(B, 32, H // 4, W // 4, device=dev)
+    flo4 = torch.nn.functional.avg_pool2d(fl, 4) / 4
+    ops["pwc_warp"] = lambda: V.pwc_warp(feat, flo4)
+if a.op == "pwc_warp_torch":
+    feat = torch.randn(B, 32, H // 4, W // 4, device=dev)
+    flo4 = torch.nn.functional.avg_pool2d(fl, 4) / 4
+    def _ref():
+        Bq, Cq, Hq, Wq = feat.shape
+        xx = torch.arange(Wq, device=dev).view(1, 1, 1, Wq).expand(Bq, 1, Hq, Wq)
+        yy = torch.arange(Hq, device=dev).view(1, 1, Hq, 1).expand(Bq, 1, Hq, Wq)
+        vg = torch.cat((xx, yy), 1).float() + flo4
+        vg = torch.stack([2.0 * vg[:, 0] / max(Wq - 1, 1) - 1.0, 2.0 * vg[:, 1] / max(Hq - 1, 1) - 1.0], 1).permute(0, 2, 3, 1)
+        o = torch.nn.functional.grid_sample(feat, vg, align_corners=False)
+        m = torch.nn.functional.grid_sample(torch.ones_like(o), vg, align_corners=False)
+        m[m < 0.9999] = 0
+        m[m > 0] = 1
+        return o * m
+    ops["pwc_warp_torch"] = _ref
 if a.op in ("dproj_bwd", "proj_bwd"):
     cnt, po = torch.empty(B, 1, H, W, device=dev), torch.empty(B, 2, H, W, device=dev)
     g2, gd = torch.randn(B, 2, H, W, device=dev), torch.empty(B, 1, H, W, device=dev)

@@ -18,5 +18,6 @@ from .separable_conv import (SeparableConvFlowLayer, SeparableConvFlowModule, Se
                              SeparableConvModule)
 from .compat import install_reference_aliases
 from .host_stream import PairStream
+from .pwc_warp import PWCWarpLayer, pwc_warp
 
 __version__ = "0.1.0"
