@@ -592,6 +592,11 @@ def op_table(torch, V, device, path):
             a = torch.randn(B, C, H // s, W // s, device=device)
             b = torch.randn_like(a)
             add(f"Correlation_fwd_C{C}_{H // s}x{W // s}", timeit(lambda: corr(a, b)), 4 * (2 * C + 81), B * (H // s) * (W // s))
+        # PWCDCNet.warp at the PWC level-2 shape (reads C features + 2 flow planes, writes C)
+        feat = torch.randn(B, 32, H // 4, W // 4, device=device)
+        flo4 = torch.nn.functional.avg_pool2d(fl, 4) / 4
+        add("PWC_warp_C32_288x496", timeit(lambda: V.pwc_warp(feat, flo4), iters=20), 4 * (2 * 32 + 2), B * (H // 4) * (W // 4))
+        del feat, flo4
         # the 196-channel context warp of DAIN_slowmotion, once (two batch items keep it at 7 GB)
         Bc = 2
         ctx = torch.rand(Bc, 196, H, W, device=device)
