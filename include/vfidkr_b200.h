@@ -184,6 +184,18 @@ int vfidkr_correlation_backward(const float *input1, const float *input2, const 
                                 int max_displacement, int stride1, int stride2, int corr_type_multiply,
                                 vfidkr_stream_t stream);
 
+/* ---- MinDepthFlowProjection (my_package/MinDepthFlowProjection/mindepthflowprojection_cuda.cc; kernels
+ * mindepthflowprojection_cuda_kernel.cu:29-312): the in-range source pixel with the largest input2 wins its top-left
+ * cell, output = -flow of the winner, count = its input2; hole filling as in the other projections.  The reference's
+ * forward is a non-atomic read-compare-write and therefore timing-dependent; this is the deterministic version of the
+ * same rule (64-bit atomicMax; ties go to the lowest pixel index).  input1 [B,2,H,W], input2 [B,1,H,W];
+ * gradinput2 is written as zeros (the reference leaves the caller's zeros). ---- */
+int vfidkr_mindepthflowprojection_forward(const float *input1, const float *input2, float *count, float *output,
+                                          int B, int H, int W, int fillhole, vfidkr_stream_t stream);
+int vfidkr_mindepthflowprojection_backward(const float *input1, const float *input2, const float *count,
+                                           const float *gradoutput, float *gradinput1, float *gradinput2,
+                                           int B, int H, int W, vfidkr_stream_t stream);
+
 /* ---- PWCDCNet.warp (PWCNet/PWCNet.py:159-199): grid + flow, grid_sample (bilinear, zero padding, default
  * align_corners = False on an align_corners = True style normalisation -- the reference's quirk, kept) and the validity
  * mask (grid_sample of ones, thresholded at 0.9999), output = sample * mask.  Not a native symbol of the reference: it

@@ -271,3 +271,72 @@ def pwc_warp_backward(x, flo, gradoutput):
     giy = (gm * ((v2 - v0) * (1 - tx)[:, None] + (v3 - v1) * tx[:, None])).sum(1)
     gflo = np.stack([gix * (W / max(W - 1, 1)), giy * (H / max(H - 1, 1))], 1)
     return gx, gflo
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# MinDepthFlowProjection (my_package/MinDepthFlowProjection/mindepthflowprojection_cuda_kernel.cu:29-312), numpy.
+# The reference's forward is a racy read-compare-write (:79-84); this restates the rule it implements when the race does
+# not strike -- per cell (top-left corner only), the in-range source with the largest input2 > 0 wins; among equal
+# input2 the lowest pixel index (raster order) -- which is what the product's atomicMax computes.  Parity is by this
+# property, not by reference fixtures.
+# ---------------------------------------------------------------------------------------------------------------
+def _mindepth_corners(flo, H, W):
+    f32 = np.float32
+    xs = np.arange(W, dtype=f32)[None, None, :]
+    ys = np.arange(H, dtype=f32)[None, :, None]
+    x2 = (xs + flo[:, 0]).astype(f32)
+    y2 = (ys + flo[:, 1]).astype(f32)
+    ok = (x2 >= 0) & (y2 >= 0) & (x2 <= f32(W - 1)) & (y2 <= f32(H - 1))
+    L = np.where(ok, x2, 0).astype(np.int64)
+    T = np.where(ok, y2, 0).astype(np.int64)
+    return ok, L, T, np.minimum(L + 1, W - 1), np.minimum(T + 1, H - 1)
+
+
+def mindepth_forward(input1, input2, fillhole=0):
+    flo, dep = _f32(input1), _f32(input2)
+    B, _, H, W = flo.shape
+    ok, L, T, _, _ = _mindepth_corners(flo, H, W)
+    out = np.zeros((B, 2, H, W), np.float64)
+    cnt = np.zeros((B, 1, H, W), np.float64)
+    for b in range(B):
+        sel = ok[b] & (dep[b, 0] > 0)
+        src = np.flatnonzero(sel.ravel())
+        cell = (T[b].ravel() * W + L[b].ravel())[src]
+        d = dep[b, 0].ravel()[src]
+        order = np.lexsort((src, -d.astype(np.float64), cell))     # by cell, then largest depth, then lowest index
+        cell_s, src_s, d_s = cell[order], src[order], d[order]
+        first = np.ones(len(order), bool)
+        first[1:] = cell_s[1:] != cell_s[:-1]
+        wc, ws = cell_s[first], src_s[first]
+        cnt[b, 0].ravel()[wc] = d_s[first]
+        out[b, 0].ravel()[wc] = -flo[b, 0].ravel()[ws].astype(np.float64)
+        out[b, 1].ravel()[wc] = -flo[b, 1].ravel()[ws].astype(np.float64)
+    if fillhole:
+        filled = out.copy()
+        for b in range(B):
+            c = cnt[b, 0]
+            for y, x in zip(*np.nonzero(c <= 0)):
+                vals = []
+                for dy, dx in ((0, -1), (0, 1), (-1, 0), (1, 0)):
+                    yy, xx = y + dy, x + dx
+                    while 0 <= yy < H and 0 <= xx < W and c[yy, xx] == 0:
+                        yy, xx = yy + dy, xx + dx
+                    if 0 <= yy < H and 0 <= xx < W and c[yy, xx] > 0:
+                        vals.append(out[b, :, yy, xx])
+                if vals:
+                    filled[b, :, y, x] = np.sum(vals, 0) / len(vals)
+        out = filled
+    return out, cnt
+
+
+def mindepth_backward(input1, input2, count, gradoutput):
+    flo, dep, cnt, g = _f32(input1), _f32(input2), _f32(count), _f32(gradoutput).astype(np.float64)
+    B, _, H, W = flo.shape
+    ok, L, T, R, Bm = _mindepth_corners(flo, H, W)
+    gi1 = np.zeros((B, 2, H, W), np.float64)
+    bi = np.arange(B)[:, None, None]
+    for cy, cx in ((T, L), (T, R), (Bm, L), (Bm, R)):
+        hit = ok & (dep[:, 0] == cnt[bi, 0, cy, cx])
+        for ch in range(2):
+            gi1[:, ch] += np.where(hit, -g[bi, ch, cy, cx], 0.0)
+    return gi1, np.zeros((B, 1, H, W), np.float64)

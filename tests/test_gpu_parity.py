@@ -767,3 +767,28 @@ def test_pwc_warp(lib, oracle, B, C, H, W):
         m[m < 0.9999] = 0
         m[m > 0] = 1
         assert (out.detach() - o * m).abs().max().item() <= 1e-5 * max(1.0, float(np.abs(x).max()))
+
+
+# ------------------------------------------------------------------------------ MinDepthFlowProjection
+@pytest.mark.parametrize("B,H,W,fk", [(2, 37, 29, "stress"), (1, 256, 448, "gauss"), (2, 64, 96, "smooth"), (1, 1, 1, "unit")])
+def test_mindepth_flow_projection(lib, oracle, B, H, W, fk):
+    """Deterministic MinDepthFlowProjection against the restated rule: forward (with and without hole filling),
+    backward, repeatability, and ties resolved towards the lowest pixel index."""
+    r = U.rng(3300 + H + W)
+    fl = U.flow(r, B, H, W, fk)
+    d = U.depth_inv(r, B, H, W)
+    d[:, :, ::3, ::5] = d[:, :, :1, :1]                         # plenty of exact ties
+    d[:, :, 1::7, 2::9] = 0.0                                   # and sources that may not win
+    for requires_grad in (True, False):
+        tf, td = cu(fl).requires_grad_(requires_grad), cu(d).requires_grad_(requires_grad)
+        out = lib.minDepthFlowProjectionModule(requires_grad)(tf, td)
+        ref, cnt = oracle.mindepth_forward(fl, d, 0 if requires_grad else 1)
+        U.assert_close(host(out), ref, U.RTOL_FWD, f"min-depth projection forward fillhole={not requires_grad}")
+        again = lib.minDepthFlowProjectionModule(requires_grad)(tf, td)
+        assert torch.equal(out, again)                           # no race: bit-identical on every launch
+        if requires_grad:
+            g = r.standard_normal((B, 2, H, W)).astype(np.float32)
+            out.backward(cu(g))
+            gi1, gi2 = oracle.mindepth_backward(fl, d, cnt.astype(np.float32), g)
+            U.assert_close(host(tf.grad), gi1, U.RTOL_FWD, "min-depth gradinput1")
+            assert not td.grad.any()

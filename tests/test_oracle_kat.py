@@ -424,3 +424,36 @@ def test_pwc_warp_oracle_is_pinned_to_torch_grid_sample(oracle):
         _reference_pwc_warp(tx2, tf2).backward(torch.from_numpy(g32))
         assert np.abs(gx - tx2.grad.numpy()).max() <= 1e-4 * max(1.0, np.abs(gx).max())
         assert np.abs(gf - tf2.grad.numpy()).max() <= 1e-4 * max(1.0, np.abs(gf).max())
+
+
+def test_mindepth_oracle_known_answers(oracle):
+    """MinDepthFlowProjection restatement: the closest surface wins its cell, ties go to the lowest pixel index,
+    non-positive input2 never wins, zero flow is the identity."""
+    H, W = 4, 6
+    flo = np.zeros((1, 2, H, W), np.float32)
+    dep = np.full((1, 1, H, W), 0.5, np.float32)
+    out, cnt = oracle.mindepth_forward(flo, dep)
+    assert not out.any() and (cnt == 0.5).all()
+    # pixels (0,1) and (0,2) both land on cell (0,3): the larger input2 wins
+    flo[0, 0, 0, 1], flo[0, 0, 0, 2] = 2.0, 1.0
+    dep[0, 0, 0, 1], dep[0, 0, 0, 2], dep[0, 0, 0, 3] = 0.9, 0.7, 0.1
+    out, cnt = oracle.mindepth_forward(flo, dep)
+    assert cnt[0, 0, 0, 3] == np.float32(0.9) and out[0, 0, 0, 3] == -2.0
+    assert cnt[0, 0, 0, 1] == 0 and cnt[0, 0, 0, 2] == 0          # their own cells became holes
+    # a tie: the lowest pixel index wins
+    dep[0, 0, 0, 2] = 0.9
+    out, cnt = oracle.mindepth_forward(flo, dep)
+    assert out[0, 0, 0, 3] == -2.0
+    # non-positive input2 never wins
+    dep[:] = 0.0
+    out, cnt = oracle.mindepth_forward(flo, dep)
+    assert not cnt.any() and not out.any()
+    # hole filling: the hole at (0,1) takes the mean of its nearest non-hole neighbours
+    dep[:] = 0.5
+    dep[0, 0, 0, 1], dep[0, 0, 0, 2], dep[0, 0, 0, 3] = 0.9, 0.7, 0.1
+    out, cnt = oracle.mindepth_forward(flo, dep, fillhole=1)
+    assert cnt[0, 0, 0, 1] == 0 and out[0, 0, 0, 1] == (0.0 + -2.0 + 0.0) / 3     # left (0,0), right (0,3), down (1,1)
+    # backward: the winner receives -gradoutput of the matching corners
+    g = np.ones((1, 2, H, W), np.float32)
+    gi1, gi2 = oracle.mindepth_backward(flo, dep, cnt.astype(np.float32), g)
+    assert gi1[0, 0, 0, 1] == -1.0 and gi1[0, 0, 0, 2] == 0.0 and not gi2.any()

@@ -12,7 +12,7 @@ from .filter_interpolation import (FilterInterpolationBlendLayer, filter_interpo
                                    FilterInterpolationLayerDKR, FilterInterpolationLayerNoFilterWithDeforConv,
                                    FilterInterpolationModule)
 from .flow_projection import (DepthFlowProjectionLayer, DepthFlowProjectionModule, FlowProjectionLayer,
-                              FlowProjectionModule)
+                              FlowProjectionModule, minDepthFlowProjectionLayer, minDepthFlowProjectionModule)
 from .interpolation import InterpolationChLayer, InterpolationChModule, InterpolationLayer, InterpolationModule
 from .separable_conv import (SeparableConvFlowLayer, SeparableConvFlowModule, SeparableConvLayer,
                              SeparableConvModule)

@@ -34,6 +34,8 @@ _SIGNATURES = {
     "vfidkr_filterinterpolation_backward_deforconv": [_P] * 9 + [_I] * 5 + [_P],
     "vfidkr_filterinterpolation_forward_nofilterwithdeforconv": [_P] * 4 + [_I] * 5 + [_P],
     "vfidkr_filterinterpolation_backward_nofilterwithdeforconv": [_P] * 7 + [_I] * 5 + [_P],
+    "vfidkr_mindepthflowprojection_forward": [_P] * 4 + [_I] * 4 + [_P],
+    "vfidkr_mindepthflowprojection_backward": [_P] * 6 + [_I] * 3 + [_P],
     "vfidkr_pwcwarp_forward": [_P] * 3 + [_I] * 4 + [_P],
     "vfidkr_pwcwarp_backward": [_P] * 5 + [_I] * 4 + [_P],
     "vfidkr_flowprojection_forward": [_P] * 3 + [_I] * 4 + [_P],

@@ -17,6 +17,7 @@ _MY_PACKAGE = {
     "FilterInterpolation": ("filter_interpolation", ["FilterInterpolationModule", "FilterInterpolationLayer"]),
     "FlowProjection": ("flow_projection", ["FlowProjectionModule", "FlowProjectionLayer"]),
     "DepthFlowProjection": ("flow_projection", ["DepthFlowProjectionModule", "DepthFlowProjectionLayer"]),
+    "MinDepthFlowProjection": ("flow_projection", ["minDepthFlowProjectionModule", "minDepthFlowProjectionLayer"]),
     "Interpolation": ("interpolation", ["InterpolationModule", "InterpolationLayer"]),
     "InterpolationCh": ("interpolation", ["InterpolationChModule", "InterpolationChLayer"]),
     "SeparableConv": ("separable_conv", ["SeparableConvModule", "SeparableConvLayer"]),

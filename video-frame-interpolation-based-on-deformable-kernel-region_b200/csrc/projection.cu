@@ -283,6 +283,98 @@ projection_backward_kernel(const float *__restrict__ flow, const float *__restri
     if (DEPTH) st_stream(gi2 + (size_t)b * HW + pix, sd);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// MinDepthFlowProjection (my_package/MinDepthFlowProjection/mindepthflowprojection_cuda_kernel.cu:29-312), SURVEY.md 8f
+// rank 4.  Intended semantics of the reference: every in-range source pixel competes for ONE cell, the top-left one
+// (T, L) (the other three corners are commented out, :86-113); the source with the largest input2 (inverse depth:
+// the closest surface) wins, provided it is > 0 (count starts at 0, :79); output = -flow of the winner, count = its
+// input2.  The reference does this with a non-atomic read-compare-write (:79-84), so its result depends on thread
+// timing even without ties.  Here the competition is a 64-bit atomicMax on (bits of input2) << 32 | ~pixel index:
+// the largest input2 wins and, among equals, the lowest pixel index -- deterministic, and equal to what the reference
+// computes whenever its race does not strike.  A second pass decodes the winners and writes the hole-filling bitmaps.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BX *BY)
+mindepth_select_kernel(const float *__restrict__ flow, const float *__restrict__ depth, unsigned long long *__restrict__ keys,
+                       int H, int W)
+{
+    const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
+    if (w_i >= W || h_i >= H) return;
+    const int b = blockIdx.z;
+    const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
+    const float fx = ld_stream(flow + ((size_t)b * 2 + 0) * HW + pix);
+    const float fy = ld_stream(flow + ((size_t)b * 2 + 1) * HW + pix);
+    const Corners c = corners(w_i, h_i, fx, fy, W, H);
+    if (!c.in_range) return;
+    const float d = ld_stream(depth + (size_t)b * HW + pix);
+    if (!(d > 0.0f)) return;   // temp > old_exist with old_exist >= 0 (:79)
+    const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (0xffffffffu - (unsigned)pix);
+    atomicMax(keys + (size_t)b * HW + (size_t)c.T * W + c.L, key);   // positive floats order like their bit patterns
+}
+
+__global__ void __launch_bounds__(32 * FIN_WARPS)
+mindepth_resolve_kernel(const unsigned long long *__restrict__ keys, const float *__restrict__ flow, float *__restrict__ count,
+                        float *__restrict__ out, unsigned *__restrict__ rowmask, unsigned char *__restrict__ colmask, int H, int W)
+{
+    const int lane = threadIdx.x, x = (blockIdx.x * FIN_WARPS + threadIdx.y) * 32 + lane;
+    if ((blockIdx.x * FIN_WARPS + threadIdx.y) * 32 >= W) return;   // whole warp outside
+    const int b = blockIdx.z, y0 = blockIdx.y * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
+    const size_t HW = (size_t)H * W;
+    const float *fu = flow + (size_t)b * 2 * HW, *fv = fu + HW;
+    unsigned colbits = 0;
+    for (int y = y0; y < y0 + FIN_ROWS; ++y) {
+        const bool live = y < y1 && x < W;
+        float cnt = 0.0f, u = 0.0f, v = 0.0f;
+        if (live) {
+            const size_t a = (size_t)y * W + x;
+            const unsigned long long key = __ldcs(keys + (size_t)b * HW + a);
+            if (key != 0ull) {
+                const unsigned src = 0xffffffffu - (unsigned)(key & 0xffffffffull);
+                cnt = __uint_as_float((unsigned)(key >> 32));
+                u = -__ldg(fu + src);   // :80-81
+                v = -__ldg(fv + src);
+            }
+            st_stream(count + (size_t)b * HW + a, cnt);
+            st_stream(out + (size_t)b * 2 * HW + a, u);
+            st_stream(out + (size_t)b * 2 * HW + HW + a, v);
+        }
+        if (rowmask) {   // uniform
+            const bool src_ok = live && cnt != 0.0f;
+            const unsigned m = __ballot_sync(0xffffffffu, src_ok);
+            if (lane == 0 && y < y1) rowmask[((size_t)b * H + y) * ((W + 31) >> 5) + (x >> 5)] = m;
+            colbits |= (src_ok ? 1u : 0u) << (y - y0);
+        }
+    }
+    if (colmask && x < W) colmask[((size_t)b * ((H + 7) >> 3) + blockIdx.y) * W + x] = (unsigned char)colbits;
+}
+
+// backward (:216-312): a source pixel receives -gradoutput of each of its four corners whose count equals its input2
+// (all four are tested although the forward only writes the top-left one -- as written)
+__global__ void __launch_bounds__(BX *BY)
+mindepth_backward_kernel(const float *__restrict__ flow, const float *__restrict__ depth, const float *__restrict__ count,
+                         const float *__restrict__ gout, float *__restrict__ gi1, float *__restrict__ gi2, int H, int W)
+{
+    const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
+    if (w_i >= W || h_i >= H) return;
+    const int b = blockIdx.z;
+    const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
+    const float fx = ld_stream(flow + ((size_t)b * 2 + 0) * HW + pix);
+    const float fy = ld_stream(flow + ((size_t)b * 2 + 1) * HW + pix);
+    const Corners c = corners(w_i, h_i, fx, fy, W, H);
+    float su = 0.0f, sv = 0.0f;
+    if (c.in_range) {
+        const float d = ld_stream(depth + (size_t)b * HW + pix);
+        const float *gu = gout + (size_t)b * 2 * HW, *gv = gu + HW, *cn = count + (size_t)b * HW;
+        const int a[4] = {c.T * W + c.L, c.T * W + c.R, c.Bm * W + c.L, c.Bm * W + c.R};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (d == __ldg(cn + a[k])) { su += -__ldg(gu + a[k]); sv += -__ldg(gv + a[k]); }
+    }
+    st_stream(gi1 + ((size_t)b * 2 + 0) * HW + pix, su);
+    st_stream(gi1 + ((size_t)b * 2 + 1) * HW + pix, sv);
+    st_stream(gi2 + (size_t)b * HW + pix, 0.0f);   // the reference never writes gradinput2: it stays the caller's zeros
+}
+
 }  // namespace
 
 // stream-ordered scratch from the device's default memory pool; the pool keeps the block cached between calls
@@ -392,3 +484,48 @@ VFIDKR_API int vfidkr_depthflowprojection_backward(const float *input1, const fl
                                                    float *gradinput1, float *gradinput2,
                                                    int B, int H, int W, vfidkr_stream_t s)
 { return projection_backward<true>(input1, input2, count, output, gradoutput, gradinput1, gradinput2, B, H, W, (cudaStream_t)s); }
+
+VFIDKR_API int vfidkr_mindepthflowprojection_forward(const float *input1, const float *input2, float *count, float *output,
+                                                     int B, int H, int W, int fillhole, vfidkr_stream_t stream)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !input1 || !input2 || !count || !output) return VFIDKR_ERR_ARG;
+    if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t HW = (size_t)H * W, WW = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
+    const size_t key_bytes = sizeof(unsigned long long) * B * HW;
+    const size_t rowmask_bytes = fillhole ? sizeof(unsigned) * B * H * WW : 0, colmask_bytes = fillhole ? (size_t)B * HB * W : 0;
+    void *mem = nullptr;
+    int e = stream_scratch_alloc(&mem, key_bytes + rowmask_bytes + colmask_bytes, s);
+    if (e) return e;
+    unsigned long long *keys = static_cast<unsigned long long *>(mem);
+    unsigned *rowmask = fillhole ? reinterpret_cast<unsigned *>(static_cast<char *>(mem) + key_bytes) : nullptr;
+    unsigned char *colmask = fillhole ? reinterpret_cast<unsigned char *>(rowmask) + rowmask_bytes : nullptr;
+    e = set_error(cudaMemsetAsync(keys, 0, key_bytes, s), "clear min-depth keys");
+    if (!e) {
+        dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
+        mindepth_select_kernel<<<grid, block, 0, s>>>(input1, input2, keys, H, W);
+        dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), B);
+        mindepth_resolve_kernel<<<fgrid, fblock, 0, s>>>(keys, input1, count, output, rowmask, colmask, H, W);
+        note_launch(2);
+        if (fillhole) {
+            projection_fillhole_kernel<<<grid, block, 0, s>>>(count, output, rowmask, colmask, H, W);
+            note_launch();
+        }
+        e = check_launch("min-depth flow projection forward");
+    }
+    const int e2 = set_error(cudaFreeAsync(mem, s), "min-depth scratch (cudaFreeAsync)");
+    return e ? e : e2;
+}
+
+VFIDKR_API int vfidkr_mindepthflowprojection_backward(const float *input1, const float *input2, const float *count,
+                                                      const float *gradoutput, float *gradinput1, float *gradinput2,
+                                                      int B, int H, int W, vfidkr_stream_t stream)
+{
+    if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !input1 || !input2 || !count || !gradoutput || !gradinput1 || !gradinput2)
+        return VFIDKR_ERR_ARG;
+    if ((long long)H * W >= (1ll << 31)) return VFIDKR_ERR_ARG;
+    dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
+    mindepth_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(input1, input2, count, gradoutput, gradinput1, gradinput2, H, W);
+    note_launch();
+    return check_launch("min-depth flow projection backward");
+}

@@ -96,3 +96,46 @@ class DepthFlowProjectionModule(Module):
 
     def forward(self, input1, input2):
         return DepthFlowProjectionLayer.apply(input1, input2, self.requires_grad)
+
+
+class minDepthFlowProjectionLayer(Function):
+    """MinDepthFlowProjection (minDepthFlowProjectionLayer.py:7-100), deterministic: the closest surface (largest
+    input2) wins each cell; see include/vfidkr_b200.h.  Same signature and return values as the reference layer."""
+
+    @staticmethod
+    def forward(ctx, input1, input2, requires_grad):
+        check_input(input1, "input1")
+        check_input(input2, "input2")
+        B, ch, H, W = input1.shape
+        if ch != 2:
+            raise _lib.VfidkrError("input1 must be a [B,2,H,W] flow")
+        if input2.shape != (B, 1, H, W):
+            raise _lib.VfidkrError(f"input2 must be [B,1,H,W] = {(B, 1, H, W)}, got {tuple(input2.shape)}")
+        fillhole = 1 if requires_grad == False else 0   # noqa: E712  (minDepthFlowProjectionLayer.py:19)
+        count = torch.empty((B, 1, H, W), dtype=input1.dtype, device=input1.device)
+        output = torch.empty_like(input1)
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_mindepthflowprojection_forward", ptr(input1), ptr(input2), ptr(count), ptr(output),
+                      B, H, W, fillhole, stream_ptr(input1.device))
+        ctx.save_for_backward(input1, input2, count)
+        return output
+
+    @staticmethod
+    def backward(ctx, gradoutput):
+        input1, input2, count = ctx.saved_tensors
+        gradoutput = gradoutput.contiguous()
+        B, _, H, W = input1.shape
+        gradinput1, gradinput2 = torch.empty_like(input1), torch.empty_like(input2)
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_mindepthflowprojection_backward", ptr(input1), ptr(input2), ptr(count), ptr(gradoutput),
+                      ptr(gradinput1), ptr(gradinput2), B, H, W, stream_ptr(input1.device))
+        return gradinput1, gradinput2, None   # minDepthFlowProjectionLayer.py:100
+
+
+class minDepthFlowProjectionModule(Module):
+    def __init__(self, requires_grad=True):
+        super().__init__()
+        self.requires_grad = requires_grad
+
+    def forward(self, input1, input2):
+        return minDepthFlowProjectionLayer.apply(input1, input2, self.requires_grad)
