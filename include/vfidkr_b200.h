@@ -206,6 +206,16 @@ int vfidkr_pwcwarp_forward(const float *x, const float *flow, float *output, int
 int vfidkr_pwcwarp_backward(const float *x, const float *flow, const float *gradoutput, float *gradx, float *gradflow,
                             int B, int C, int H, int W, vfidkr_stream_t stream);
 
+/* ---- frame I/O boundary of the demo drivers (demo_MiddleBury.py:276-364; not native in the reference: numpy + torch
+ * ReplicationPad2d there).  frames: uint8 [B,H,W,3] (HWC) on the device.  padded: float32 [B,3,Hp,Wp] with
+ * Hp / Wp from vfidkr_frame_padding (next multiple of 128, or + 64 if already one; leading pad returned).
+ * u8 -> f32: v / 255, replication padding.  f32 -> u8: crop, 255 * clip(v, 0, 1), round half to even.  Bit-exact. ---- */
+int vfidkr_frame_padding(int size, int *padded);
+int vfidkr_frames_u8_to_padded_f32(const unsigned char *frames, float *padded, int B, int H, int W,
+                                   vfidkr_stream_t stream);
+int vfidkr_padded_f32_to_frames_u8(const float *padded, unsigned char *frames, int B, int H, int W,
+                                   vfidkr_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

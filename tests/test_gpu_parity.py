@@ -792,3 +792,24 @@ def test_mindepth_flow_projection(lib, oracle, B, H, W, fk):
             gi1, gi2 = oracle.mindepth_backward(fl, d, cnt.astype(np.float32), g)
             U.assert_close(host(tf.grad), gi1, U.RTOL_FWD, "min-depth gradinput1")
             assert not td.grad.any()
+
+
+# ------------------------------------------------------------------------------ frame I/O boundary
+@pytest.mark.parametrize("B,H,W", [(1, 480, 640), (2, 37, 129), (1, 128, 256), (1, 1080, 1920)])
+def test_frame_io_is_bit_exact(lib, B, H, W):
+    """uint8 HWC frames -> padded float CHW and back against the numpy / torch formulation of demo_MiddleBury.py:276-364."""
+    r = U.rng(3400 + H)
+    u8 = r.integers(0, 256, (B, H, W, 3), dtype=np.uint8)
+    pad = lib.frames_to_padded(torch.from_numpy(u8).cuda())
+    (top, Hp), (left, Wp) = lib.frame_padding(H), lib.frame_padding(W)
+    x = torch.from_numpy(np.transpose(u8, (0, 3, 1, 2)).astype("float32") / 255.0)                    # :276
+    ref = torch.nn.ReplicationPad2d([left, Wp - W - left, top, Hp - H - top])(x).numpy()               # :303-309
+    assert tuple(pad.shape) == ref.shape and np.array_equal(host(pad), ref)
+    # back: values beyond [0, 1], exact .5 cases and NaN-free noise
+    y = (ref + r.standard_normal(ref.shape).astype(np.float32) * 0.3).astype(np.float32)
+    y[0, 0, top, left:left + 4] = np.array([0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255], np.float32)
+    back = lib.padded_to_frames(torch.from_numpy(y).cuda(), H, W)
+    yy = np.transpose(255.0 * y.clip(0, 1.0)[:, :, top:top + H, left:left + W], (0, 2, 3, 1))          # :350-351
+    assert np.array_equal(host(back), np.round(yy).astype(np.uint8))                                  # :364
+    # round trip of an untouched frame
+    assert np.array_equal(host(lib.padded_to_frames(pad, H, W)), u8)

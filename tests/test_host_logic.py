@@ -111,3 +111,14 @@ def test_pair_stream_refuses_cpu():
     import vfidkr_b200 as V
     with pytest.raises(ValueError):
         V.PairStream(torch.device("cpu"), lambda d: ())
+
+
+def test_frame_padding_rule():
+    """demo_MiddleBury.py:286-301: next multiple of 128, split floor/ceil; + 32 + 32 when already a multiple."""
+    import vfidkr_b200 as V
+    assert V.frame_padding(1080) == (36, 1152)      # (1152 - 1080) / 2
+    assert V.frame_padding(1920) == (32, 1984)      # already a multiple of 128
+    assert V.frame_padding(2160) == (8, 2176)
+    assert V.frame_padding(3840) == (32, 3904)
+    assert V.frame_padding(480) == (16, 512) and V.frame_padding(640) == (32, 704)   # the demo's own comment: (512, 704)
+    assert V.frame_padding(1) == (63, 128) and V.frame_padding(129) == (63, 256)

@@ -19,5 +19,6 @@ from .separable_conv import (SeparableConvFlowLayer, SeparableConvFlowModule, Se
 from .compat import install_reference_aliases
 from .host_stream import PairStream
 from .pwc_warp import PWCWarpLayer, pwc_warp
+from .frame_io import frame_padding, frames_to_padded, padded_to_frames
 
 __version__ = "0.1.0"
