@@ -184,6 +184,16 @@ int vfidkr_correlation_backward(const float *input1, const float *input2, const 
                                 int max_displacement, int stride1, int stride2, int corr_type_multiply,
                                 vfidkr_stream_t stream);
 
+/* ---- flow pre-processing fused into the projection's read (networks/DAIN.py:306-308):
+ * FlowProjection / DepthFlowProjection of  Upsample(x4, bilinear, align_corners = False)(scale0 * flow_lowres * scale1)
+ * without materialising the full-resolution flow.  flow_lowres [B,2,h,w]; input2 [B,1,4h,4w] or NULL (FlowProjection);
+ * count [B,1,4h,4w], output [B,2,4h,4w].  vfidkr_flow_upsample4 writes the enlarged flow itself (same arithmetic). ---- */
+int vfidkr_flowprojection_forward_lowres(const float *flow_lowres, float scale0, float scale1, const float *input2,
+                                         float *count, float *output, int B, int h, int w, int fillhole,
+                                         vfidkr_stream_t stream);
+int vfidkr_flow_upsample4(const float *flow_lowres, float scale0, float scale1, float *output, int B, int h, int w,
+                          vfidkr_stream_t stream);
+
 /* ---- MinDepthFlowProjection (my_package/MinDepthFlowProjection/mindepthflowprojection_cuda.cc; kernels
  * mindepthflowprojection_cuda_kernel.cu:29-312): the in-range source pixel with the largest input2 wins its top-left
  * cell, output = -flow of the winner, count = its input2; hole filling as in the other projections.  The reference's

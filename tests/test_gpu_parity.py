@@ -813,3 +813,28 @@ def test_frame_io_is_bit_exact(lib, B, H, W):
     assert np.array_equal(host(back), np.round(yy).astype(np.uint8))                                  # :364
     # round trip of an untouched frame
     assert np.array_equal(host(lib.padded_to_frames(pad, H, W)), u8)
+
+
+# ------------------------------------------------------------------------------ flow pre-processing fused
+@pytest.mark.parametrize("B,h,w", [(2, 16, 24), (1, 64, 112), (1, 9, 7), (1, 1, 1)])
+def test_flow_projection_from_lowres_flow(lib, oracle, B, h, w):
+    """flow_upsample4 against nn.Upsample(x4, bilinear) of the scaled flow (networks/DAIN.py:306-308), and the fused
+    projections against the unfused ones fed with that enlarged flow (FlowProjection and DepthFlowProjection)."""
+    r = U.rng(3500 + h + w)
+    lo = (r.standard_normal((B, 2, h, w)) * 0.4).astype(np.float32)
+    t_lo = cu(lo)
+    up = lib.flow_upsample4(t_lo, 20.0, 0.5)
+    with torch.no_grad():
+        ref = torch.nn.Upsample(scale_factor=4, mode="bilinear", align_corners=False)(20.0 * t_lo * 0.5)
+    assert (up - ref).abs().max().item() <= 2e-6 * max(1.0, ref.abs().max().item())
+    d = cu(U.depth_inv(r, B, 4 * h, 4 * w))
+    with torch.no_grad():
+        for depth in (None, d):
+            for fill in (True, False):
+                fused = lib.flow_project_lowres(t_lo, 20.0, 0.5, depth=depth, fillhole=fill)
+                if depth is None:
+                    unfused = lib.FlowProjectionModule(not fill)(up)
+                else:
+                    unfused = lib.DepthFlowProjectionModule(not fill)(up, depth)
+                # same flow values bit for bit -> same cells; the sums are atomically accumulated in both
+                assert (fused - unfused).abs().max().item() <= 1e-4 * max(1.0, unfused.abs().max().item())

@@ -12,7 +12,8 @@ from .filter_interpolation import (FilterInterpolationBlendLayer, filter_interpo
                                    FilterInterpolationLayerDKR, FilterInterpolationLayerNoFilterWithDeforConv,
                                    FilterInterpolationModule)
 from .flow_projection import (DepthFlowProjectionLayer, DepthFlowProjectionModule, FlowProjectionLayer,
-                              FlowProjectionModule, minDepthFlowProjectionLayer, minDepthFlowProjectionModule)
+                              FlowProjectionModule, minDepthFlowProjectionLayer, minDepthFlowProjectionModule,
+                              flow_project_lowres, flow_upsample4)
 from .interpolation import InterpolationChLayer, InterpolationChModule, InterpolationLayer, InterpolationModule
 from .separable_conv import (SeparableConvFlowLayer, SeparableConvFlowModule, SeparableConvLayer,
                              SeparableConvModule)

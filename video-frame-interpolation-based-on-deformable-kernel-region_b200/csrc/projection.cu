@@ -45,11 +45,72 @@ __device__ __forceinline__ Corners corners(int w_i, int h_i, float fx, float fy,
 // S; the box pass below then forms, with the reference's border behaviour (R = min(L+1, W-1), Bm = min(T+1, H-1):
 // a block on the last column / row hits that column / row twice),
 //   A[y][x] = sum_{dy,dx in {0,1}} wy(y,dy) * wx(x,dx) * S[y-dy][x-dx],   w(.,1) = 1,  wx(x,0) = (x == W-1 ? 2 : 1), wy alike.
+// Where the splat takes its flow from.  lowres == 0: the full-resolution flow tensor [B,2,H,W].  lowres != 0 (SURVEY.md 8f
+// rank 3): a quarter-resolution flow [B,2,H/4,W/4] that networks/DAIN.py:306-308 would first scale
+// (`div_flow * temp * time_offset`, two fp32 multiplications) and then enlarge with nn.Upsample(scale_factor=4,
+// mode='bilinear') (align_corners = False) into a full-resolution tensor: the same values are computed here on the fly,
+// per pixel, from the four low-resolution neighbours (which stay in L1/L2) -- the full-resolution flow is never
+// written or read.  Arithmetic: PyTorch's published upsample_bilinear2d (aten/src/ATen/native/UpSample.h:
+// area_pixel_compute_source_index, cuda/UpSampleBilinear2d.cu), fp32, src = 0.25 * (dst + 0.5) - 0.5 clamped at 0.
+struct FlowSource {
+    const float *flow;
+    int lowres, h, w;      // low-resolution extent when lowres != 0
+    float s0, s1;          // the two scale factors, applied in this order to the low-resolution samples
+};
+
+__device__ __forceinline__ void upsample_coord(int dst, int in_size, int &i0, int &i1, float &l0, float &l1)
+{
+    float src = __fsub_rn(__fmul_rn(0.25f, __fadd_rn((float)dst, 0.5f)), 0.5f);
+    src = src < 0.0f ? 0.0f : src;
+    i0 = (int)src;
+    i1 = i0 + (i0 < in_size - 1 ? 1 : 0);
+    l1 = __fsub_rn(src, (float)i0);
+    l0 = __fsub_rn(1.0f, l1);
+}
+
+__device__ __forceinline__ void load_flow(const FlowSource &fs, int b, int h_i, int w_i, int H, int W, float &fx, float &fy)
+{
+    if (!fs.lowres) {
+        const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
+        fx = ld_stream(fs.flow + ((size_t)b * 2 + 0) * HW + pix);
+        fy = ld_stream(fs.flow + ((size_t)b * 2 + 1) * HW + pix);
+        return;
+    }
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    upsample_coord(h_i, fs.h, y0, y1, ly0, ly1);
+    upsample_coord(w_i, fs.w, x0, x1, lx0, lx1);
+    const size_t hw = (size_t)fs.h * fs.w;
+    float v[2];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const float *pl = fs.flow + ((size_t)b * 2 + ch) * hw;
+        const float a = __fmul_rn(__fmul_rn(fs.s0, __ldg(pl + y0 * fs.w + x0)), fs.s1), bq = __fmul_rn(__fmul_rn(fs.s0, __ldg(pl + y0 * fs.w + x1)), fs.s1);
+        const float c = __fmul_rn(__fmul_rn(fs.s0, __ldg(pl + y1 * fs.w + x0)), fs.s1), d = __fmul_rn(__fmul_rn(fs.s0, __ldg(pl + y1 * fs.w + x1)), fs.s1);
+        v[ch] = __fadd_rn(__fmul_rn(ly0, __fadd_rn(__fmul_rn(lx0, a), __fmul_rn(lx1, bq))),
+                          __fmul_rn(ly1, __fadd_rn(__fmul_rn(lx0, c), __fmul_rn(lx1, d))));
+    }
+    fx = v[0]; fy = v[1];
+}
+
+// the enlarged flow as a tensor (tests; callers that need it next to the projection)
+__global__ void __launch_bounds__(BX *BY)
+flow_upsample4_kernel(FlowSource fs, float *__restrict__ out, int H, int W)
+{
+    const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
+    if (w_i >= W || h_i >= H) return;
+    float fx, fy;
+    load_flow(fs, blockIdx.z, h_i, w_i, H, W, fx, fy);
+    const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
+    out[((size_t)blockIdx.z * 2 + 0) * HW + pix] = fx;
+    out[((size_t)blockIdx.z * 2 + 1) * HW + pix] = fy;
+}
+
 // `clear` (may be null): the scratch image of the NEXT chunk of frames, zeroed here cell for cell (plain write-back
 // stores: the lines stay in L2, where that chunk's REDs will find them).
 template <bool DEPTH>
 __global__ void __launch_bounds__(BX *BY)
-projection_splat_kernel(const float *__restrict__ flow, const float *__restrict__ depth, float4 *__restrict__ S,
+projection_splat_kernel(const FlowSource fs, int b0, const float *__restrict__ depth, float4 *__restrict__ S,
                         float4 *__restrict__ clear, int H, int W)
 {
     const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
@@ -57,8 +118,8 @@ projection_splat_kernel(const float *__restrict__ flow, const float *__restrict_
     const int b = blockIdx.z;
     const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
     if (clear) clear[(size_t)b * HW + pix] = make_float4(0.f, 0.f, 0.f, 0.f);
-    const float fx = ld_stream(flow + ((size_t)b * 2 + 0) * HW + pix);
-    const float fy = ld_stream(flow + ((size_t)b * 2 + 1) * HW + pix);
+    float fx, fy;
+    load_flow(fs, b0 + b, h_i, w_i, H, W, fx, fy);   // b0: first frame of this chunk in the flow tensor
     const Corners c = corners(w_i, h_i, fx, fy, W, H);
     if (!c.in_range) return;
     const float d = DEPTH ? ld_stream(depth + (size_t)b * HW + pix) : 1.0f;
@@ -397,9 +458,10 @@ int stream_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
 namespace {
 
 template <bool DEPTH>
-int projection_forward(const float *flow, const float *depth, float *count, float *out,
+int projection_forward(const FlowSource fs, const float *depth, float *count, float *out,
                        int B, int H, int W, int fillhole, cudaStream_t s)
 {
+    const float *flow = fs.flow;
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !flow || !count || !out || (DEPTH && !depth)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
@@ -429,8 +491,7 @@ int projection_forward(const float *flow, const float *depth, float *count, floa
             float4 *nxt = (c + 1 < nchunks) ? S + (size_t)((c + 1) & 1) * chunk_cells : nullptr;
             dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), nb);
             // the next chunk may be shorter than this one; clearing nb frames of it is always enough or more
-            projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(flow + (size_t)b0 * 2 * HW, DEPTH ? depth + (size_t)b0 * HW : nullptr,
-                                                                   cur, nxt, H, W);
+            projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(fs, b0, DEPTH ? depth + (size_t)b0 * HW : nullptr, cur, nxt, H, W);
             dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), nb);
             projection_finish_kernel<<<fgrid, fblock, 0, s>>>(cur, count + (size_t)b0 * HW, out + (size_t)b0 * 2 * HW,
                                                               fillhole ? rowmask + (size_t)b0 * H * WW : nullptr,
@@ -468,7 +529,7 @@ using namespace vfidkr;
 
 VFIDKR_API int vfidkr_flowprojection_forward(const float *input1, float *count, float *output,
                                              int B, int H, int W, int fillhole, vfidkr_stream_t s)
-{ return projection_forward<false>(input1, nullptr, count, output, B, H, W, fillhole, (cudaStream_t)s); }
+{ return projection_forward<false>(FlowSource{input1, 0, 0, 0, 1.f, 1.f}, nullptr, count, output, B, H, W, fillhole, (cudaStream_t)s); }
 
 VFIDKR_API int vfidkr_flowprojection_backward(const float *input1, const float *count, const float *gradoutput,
                                               float *gradinput1, int B, int H, int W, vfidkr_stream_t s)
@@ -477,7 +538,7 @@ VFIDKR_API int vfidkr_flowprojection_backward(const float *input1, const float *
 VFIDKR_API int vfidkr_depthflowprojection_forward(const float *input1, const float *input2, float *count,
                                                   float *output, int B, int H, int W, int fillhole,
                                                   vfidkr_stream_t s)
-{ return projection_forward<true>(input1, input2, count, output, B, H, W, fillhole, (cudaStream_t)s); }
+{ return projection_forward<true>(FlowSource{input1, 0, 0, 0, 1.f, 1.f}, input2, count, output, B, H, W, fillhole, (cudaStream_t)s); }
 
 VFIDKR_API int vfidkr_depthflowprojection_backward(const float *input1, const float *input2, const float *count,
                                                    const float *output, const float *gradoutput,
@@ -528,4 +589,27 @@ VFIDKR_API int vfidkr_mindepthflowprojection_backward(const float *input1, const
     mindepth_backward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(input1, input2, count, gradoutput, gradinput1, gradinput2, H, W);
     note_launch();
     return check_launch("min-depth flow projection backward");
+}
+
+// the projections fed by a quarter-resolution flow (see FlowSource).  h, w: low-resolution extent;
+// the outputs are [B,*,4h,4w].  input2 (inverse depth, full resolution) may be null: FlowProjection.
+VFIDKR_API int vfidkr_flowprojection_forward_lowres(const float *flow_lowres, float scale0, float scale1, const float *input2,
+                                                    float *count, float *output, int B, int h, int w, int fillhole,
+                                                    vfidkr_stream_t s)
+{
+    if (h <= 0 || w <= 0 || h > (1 << 20) || w > (1 << 20)) return VFIDKR_ERR_ARG;
+    const FlowSource fs{flow_lowres, 1, h, w, scale0, scale1};
+    return input2 ? projection_forward<true>(fs, input2, count, output, B, 4 * h, 4 * w, fillhole, (cudaStream_t)s)
+                  : projection_forward<false>(fs, nullptr, count, output, B, 4 * h, 4 * w, fillhole, (cudaStream_t)s);
+}
+
+VFIDKR_API int vfidkr_flow_upsample4(const float *flow_lowres, float scale0, float scale1, float *output, int B, int h, int w,
+                                     vfidkr_stream_t s)
+{
+    if (B <= 0 || B > 65535 || h <= 0 || w <= 0 || h > (1 << 20) || w > (1 << 20) || !flow_lowres || !output) return VFIDKR_ERR_ARG;
+    const int H = 4 * h, W = 4 * w;
+    dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
+    flow_upsample4_kernel<<<grid, block, 0, (cudaStream_t)s>>>(FlowSource{flow_lowres, 1, h, w, scale0, scale1}, output, H, W);
+    note_launch();
+    return check_launch("flow upsample x4");
 }

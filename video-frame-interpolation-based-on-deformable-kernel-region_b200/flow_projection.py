@@ -139,3 +139,36 @@ class minDepthFlowProjectionModule(Module):
 
     def forward(self, input1, input2):
         return minDepthFlowProjectionLayer.apply(input1, input2, self.requires_grad)
+
+
+def flow_upsample4(flow_lowres, scale0=1.0, scale1=1.0):
+    """Upsample(scale_factor=4, mode='bilinear')(scale0 * flow_lowres * scale1) (networks/DAIN.py:306-308) as one kernel."""
+    check_input(flow_lowres, "flow_lowres")
+    B, ch, h, w = flow_lowres.shape
+    out = torch.empty((B, ch, 4 * h, 4 * w), dtype=flow_lowres.dtype, device=flow_lowres.device)
+    if ch != 2:
+        raise _lib.VfidkrError("flow_lowres must be [B,2,h,w]")
+    with torch.cuda.device(flow_lowres.device):
+        _lib.call("vfidkr_flow_upsample4", ptr(flow_lowres), float(scale0), float(scale1), ptr(out), B, h, w,
+                  stream_ptr(flow_lowres.device))
+    return out
+
+
+def flow_project_lowres(flow_lowres, scale0=1.0, scale1=1.0, depth=None, fillhole=True):
+    """(Depth)FlowProjection of the x4-enlarged, scaled flow without materialising it (inference: no gradient).
+    Equals FlowProjectionModule(False)(flow_upsample4(flow_lowres, scale0, scale1)) -- DepthFlowProjection with `depth`."""
+    check_input(flow_lowres, "flow_lowres")
+    B, ch, h, w = flow_lowres.shape
+    if ch != 2:
+        raise _lib.VfidkrError("flow_lowres must be [B,2,h,w]")
+    if depth is not None:
+        check_input(depth, "depth")
+        if depth.shape != (B, 1, 4 * h, 4 * w):
+            raise _lib.VfidkrError(f"depth must be [B,1,4h,4w] = {(B, 1, 4 * h, 4 * w)}")
+    count = torch.empty((B, 1, 4 * h, 4 * w), dtype=flow_lowres.dtype, device=flow_lowres.device)
+    output = torch.empty((B, 2, 4 * h, 4 * w), dtype=flow_lowres.dtype, device=flow_lowres.device)
+    with torch.cuda.device(flow_lowres.device):
+        _lib.call("vfidkr_flowprojection_forward_lowres", ptr(flow_lowres), float(scale0), float(scale1),
+                  ptr(depth) if depth is not None else None, ptr(count), ptr(output), B, h, w, 1 if fillhole else 0,
+                  stream_ptr(flow_lowres.device))
+    return output
