@@ -287,7 +287,8 @@ def bench_ours(args):
 
             def e2e_step():
                 stream.run(hd, (host_out[0], host_out[1]))
-            e2e_step()
+            for _ in range(3):   # warm-up: the per-stream allocator pools and the pinned pages settle
+                e2e_step()
             sync_all()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
