@@ -593,6 +593,16 @@ def op_table(torch, V, device, path):
             a = torch.randn(B, C, H // s, W // s, device=device)
             b = torch.randn_like(a)
             add(f"Correlation_fwd_C{C}_{H // s}x{W // s}", timeit(lambda: corr(a, b)), 4 * (2 * C + 81), B * (H // s) * (W // s))
+        # correlation backward at the two finest PWC levels (reads f1, f2, gradoutput; writes both gradients)
+        for C, sdiv in ((64, 8), (32, 4)):
+            a = torch.randn(B, C, H // sdiv, W // sdiv, device=device)
+            b = torch.randn_like(a)
+            go = torch.randn(B, 81, H // sdiv, W // sdiv, device=device)
+            ga, gb = torch.empty_like(a), torch.empty_like(b)
+            add(f"Correlation_bwd_C{C}_{H // sdiv}x{W // sdiv}",
+                timeit(lambda: _lib.call("vfidkr_correlation_backward", ptr(a), ptr(b), ptr(go), ptr(ga), ptr(gb), B, C, H // sdiv, W // sdiv,
+                                         4, 1, 4, 1, 1, 1, sp)), 4 * (4 * C + 81), B * (H // sdiv) * (W // sdiv))
+            del a, b, go, ga, gb
         # PWCDCNet.warp at the PWC level-2 shape (reads C features + 2 flow planes, writes C)
         feat = torch.randn(B, 32, H // 4, W // 4, device=device)
         flo4 = torch.nn.functional.avg_pool2d(fl, 4) / 4

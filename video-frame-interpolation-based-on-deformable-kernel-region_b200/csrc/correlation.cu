@@ -9,8 +9,9 @@
 //     thread owns 4 adjacent pixels x 9 horizontal x 3 vertical displacements (108 accumulators), so a
 //     float4 fetched from shared memory feeds ~11 FMAs (the reference runs 81 serial warp reductions per
 //     output pixel over a padded NHWC copy);
-//   * backward for the fast path keeps the 81 upstream gradients of a pixel in registers and reuses
-//     them for every channel, one launch for the whole batch (the reference launches per batch item);
+//   * backward for the fast path keeps the 81 upstream gradients of a pixel in registers, stages the other feature
+//     map in shared-memory tiles (8 channels at a time) and reuses both for every channel; one launch per gradient for
+//     the whole batch (the reference launches per batch item);
 //   * a generic path restates the reference formulas for any (kernel_size, stride1, stride2).
 // fp32 FMA throughput, not HBM, bounds this op on SIMT (162*C flop vs 4*(2C+81) bytes per pixel);
 // tcgen05 is not used: the 9-wide band of the (T+8)-wide product wastes >= 89% of a GEMM tile and
@@ -303,22 +304,31 @@ corr_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, s
 }
 
 // ---------------------------------------------------------------------------------------------
-// fast backward (kernel_size 1, strides 1): one thread per input pixel keeps the D*D upstream
-// gradients in registers and loops channels.
+// fast backward (kernel_size 1, strides 1, max_displacement 4): one thread per input pixel keeps the 81 upstream
+// gradients of that pixel in registers; the other feature map goes through shared memory in 32 x 8 tiles (+ 4 pixels
+// of halo, zero padding applied by the loader) and chunks of 8 channels, so the 81 gathers per pixel and channel are LDS.
 //   gi1[n,c,y,x] = 1/C * sum_tc g[n,tc,y+s,x+s]       * f2[n,c,y+tj,x+ti]          (:151-241)
 //   gi2[n,c,y,x] = 1/C * sum_tc g[n,tc,y+s-tj,x+s-ti] * f1[n,c,y-tj,x-ti]          (:244-334)
-// with s = pad - md, zero outside the image / the output plane.
+// with s = pad - md, zero outside the image / the output plane.  (The first version gathered through L1 with the 81
+// gradients in a local array that ptxas spilled: 34 ms for the PWC level-2 map, 0.4 % of the roofline.)
 // ---------------------------------------------------------------------------------------------
-template <int DR, int WHICH>
-__global__ void __launch_bounds__(256)
-corr_backward_fast_kernel(const float *__restrict__ other, const float *__restrict__ gout, float *__restrict__ gi,
-                          int C, int H, int W, int s, int oh, int ow)
+namespace cbwd {
+constexpr int DR = 4, D = 9, TX = 32, TY = 8, CK = 8;
+constexpr int TW = TX + 2 * DR, TH = TY + 2 * DR;   // staged tile of the other map
+}  // namespace cbwd
+
+template <int WHICH>
+__global__ void __launch_bounds__(cbwd::TX *cbwd::TY, 2)
+corr_backward_tiled_kernel(const float *__restrict__ other, const float *__restrict__ gout, float *__restrict__ gi,
+                           int C, int H, int W, int s, int oh, int ow)
 {
-    constexpr int D = 2 * DR + 1;
-    const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
-    if (x >= W || y >= H) return;
+    using namespace cbwd;
+    __shared__ float tile[CK][TH][TW];
+    const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * TX + tx;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, x = x0 + tx, y = y0 + ty;
     const int n = blockIdx.z;
     const size_t HW = (size_t)H * W, plane = (size_t)oh * ow;
+    const bool inside = x < W && y < H;
     const float *g = gout + (size_t)n * D * D * plane;
     float gv[D * D];
 #pragma unroll
@@ -327,24 +337,31 @@ corr_backward_fast_kernel(const float *__restrict__ other, const float *__restri
         for (int b = 0; b < D; ++b) {
             const int tj = a - DR, ti = b - DR;
             const int oy = WHICH == 1 ? y + s : y + s - tj, ox = WHICH == 1 ? x + s : x + s - ti;
-            gv[a * D + b] = (oy >= 0 && oy < oh && ox >= 0 && ox < ow) ? __ldg(g + (size_t)(a * D + b) * plane + (size_t)oy * ow + ox) : 0.0f;
+            gv[a * D + b] = (inside && oy >= 0 && oy < oh && ox >= 0 && ox < ow) ? __ldg(g + (size_t)(a * D + b) * plane + (size_t)oy * ow + ox) : 0.0f;
         }
     const float nel = (float)C;
-    for (int c = 0; c < C; ++c) {
-        const float *pl = other + ((size_t)n * C + c) * HW;
-        float acc = 0.0f;
-#pragma unroll
-        for (int a = 0; a < D; ++a) {
-            const int yy = WHICH == 1 ? y + (a - DR) : y - (a - DR);
-            const bool yin = yy >= 0 && yy < H;
-#pragma unroll
-            for (int b = 0; b < D; ++b) {
-                const int xx = WHICH == 1 ? x + (b - DR) : x - (b - DR);
-                const float v = (yin && xx >= 0 && xx < W) ? __ldg(pl + (size_t)yy * W + xx) : 0.0f;
-                acc = fmaf(gv[a * D + b], v, acc);
-            }
+    for (int c0 = 0; c0 < C; c0 += CK) {
+        __syncthreads();   // the previous chunk has been consumed
+        for (int i = tid; i < CK * TH * TW; i += TX * TY) {
+            const int cc = i / (TH * TW), r = i - cc * (TH * TW), ry = r / TW, rx = r - ry * TW;
+            const int gy = y0 - DR + ry, gx = x0 - DR + rx;
+            const bool ok = c0 + cc < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+            tile[cc][ry][rx] = ok ? __ldg(other + ((size_t)n * C + c0 + cc) * HW + (size_t)gy * W + gx) : 0.0f;
         }
-        st_stream(gi + ((size_t)n * C + c) * HW + (size_t)y * W + x, acc / nel);
+        __syncthreads();
+        const int nc = min(CK, C - c0);
+        for (int cc = 0; cc < nc; ++cc) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int a = 0; a < D; ++a)
+#pragma unroll
+                for (int b = 0; b < D; ++b) {
+                    // gi1: f2[y + tj, x + ti] -> tile row ty + a, col tx + b;  gi2: f1[y - tj, x - ti] -> row ty + 8 - a, col tx + 8 - b
+                    const float v = WHICH == 1 ? tile[cc][ty + a][tx + b] : tile[cc][ty + 2 * DR - a][tx + 2 * DR - b];
+                    acc = fmaf(gv[a * D + b], v, acc);
+                }
+            if (inside) st_stream(gi + ((size_t)n * C + c0 + cc) * HW + (size_t)y * W + x, acc / nel);
+        }
     }
 }
 
@@ -534,8 +551,8 @@ VFIDKR_API int vfidkr_correlation_backward(const float *input1, const float *inp
     cudaStream_t s = (cudaStream_t)stream;
     if (k == 1 && s1 == 1 && s2 == 1 && md == 4 && pad >= md) {
         dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), B);
-        corr_backward_fast_kernel<4, 1><<<grid, block, 0, s>>>(input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow);
-        corr_backward_fast_kernel<4, 2><<<grid, block, 0, s>>>(input1, gradoutput, gradinput2, C, H, W, pad - md, cs.oh, cs.ow);
+        corr_backward_tiled_kernel<1><<<grid, block, 0, s>>>(input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow);
+        corr_backward_tiled_kernel<2><<<grid, block, 0, s>>>(input1, gradoutput, gradinput2, C, H, W, pad - md, cs.oh, cs.ow);
         note_launch(2);
     } else {
         if ((long long)B * C > 65535) return VFIDKR_ERR_ARG;
