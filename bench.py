@@ -637,6 +637,24 @@ def op_table(torch, V, device, path):
                                                               ptr(gx), ptr(o1), ptr(o2), ptr(o3), ptr(o4), Bx, 3, Hx, Wx, 4, sp), iters=20), 436, pxx)
         del Ix, flx, ftx, offx, depx, gx, o1, o2, o3, o4
         torch.cuda.empty_cache()
+    # SeparableConv at F = 51 (the reference's own test size, test_module.py:903-907) is arithmetic-bound:
+    # the row carries the fp32 rate next to the (irrelevant) byte rate.  3*C*F*F multiply-adds per output pixel forward,
+    # three times that backward.
+    Bs, Hs, Ws, Fs = 8, 256, 448, 51
+    Hos, Wos = Hs - Fs + 1, Ws - Fs + 1
+    Is = torch.rand(Bs, 3, Hs, Ws, device=device)
+    vs = torch.rand(Bs, Fs, Hos, Wos, device=device) / Fs
+    hs = torch.rand(Bs, Fs, Hos, Wos, device=device) / Fs
+    os_, gs = torch.empty(Bs, 3, Hos, Wos, device=device), torch.randn(Bs, 3, Hos, Wos, device=device)
+    g1s, g2s, g3s = torch.empty_like(Is), torch.empty_like(vs), torch.empty_like(hs)
+    pxs = Bs * Hos * Wos
+    add("SeparableConv_fwd_F51_B8_256x448", timeit(lambda: _lib.call("vfidkr_separableconv_forward", ptr(Is), ptr(vs), ptr(hs), ptr(os_),
+                                                                      Bs, 3, Hs, Ws, Fs, sp)), 4 * (2 * 3 + 2 * Fs), pxs)
+    rows[-1]["fp32_TFLOPs"] = 3 * 3 * Fs * Fs * pxs / (rows[-1]["ms"] * 1e-3) / 1e12
+    add("SeparableConv_bwd_F51_B8_256x448", timeit(lambda: _lib.call("vfidkr_separableconv_backward", ptr(Is), ptr(vs), ptr(hs), ptr(gs),
+                                                                      ptr(g1s), ptr(g2s), ptr(g3s), Bs, 3, Hs, Ws, Fs, sp)), 4 * (3 * 3 + 4 * Fs), pxs)
+    rows[-1]["fp32_TFLOPs"] = 3 * 3 * 3 * Fs * Fs * pxs / (rows[-1]["ms"] * 1e-3) / 1e12
+    del Is, vs, hs, os_, gs, g1s, g2s, g3s
     with open(path, "w") as f:
         for r in rows:
             f.write(json.dumps(r) + "\n")

@@ -263,7 +263,8 @@ def test_interpolation_requires_three_channels(lib):
 
 
 # ------------------------------------------------------------------------------ SeparableConv(Flow)
-@pytest.mark.parametrize("B,H,W,F", [(1, 128, 128, 51), (2, 20, 33, 5), (1, 9, 9, 9)])
+@pytest.mark.parametrize("B,H,W,F", [(1, 128, 128, 51), (2, 20, 33, 5), (1, 9, 9, 9), (2, 70, 150, 11), (1, 40, 90, 4),
+                                     (1, 150, 140, 120)])   # several ragged tiles; odd widths; F too large for the tiled kernels
 def test_separableconv(lib, oracle, B, H, W, F):
     r = U.rng(1500)
     C, Ho, Wo = 3, H - F + 1, W - F + 1

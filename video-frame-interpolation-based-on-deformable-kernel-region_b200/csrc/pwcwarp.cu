@@ -85,7 +85,7 @@ pwcwarp_forward_kernel(const float *__restrict__ x, const float *__restrict__ fl
 }
 
 // gx[corner] += gout * mask * weight;  gflo = (W / (W - 1)) * d(sample)/d(ix), (H / (H - 1)) * d(sample)/d(iy)
-__global__ void __launch_bounds__(BX *BY, 4)
+__global__ void __launch_bounds__(BX *BY, 3)
 pwcwarp_backward_kernel(const float *__restrict__ x, const float *__restrict__ flo, const float *__restrict__ gout,
                         float *__restrict__ gx, float *__restrict__ gflo, int C, int H, int W)
 {
