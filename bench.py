@@ -654,7 +654,10 @@ def op_table(torch, V, device, path):
     add("SeparableConv_bwd_F51_B8_256x448", timeit(lambda: _lib.call("vfidkr_separableconv_backward", ptr(Is), ptr(vs), ptr(hs), ptr(gs),
                                                                       ptr(g1s), ptr(g2s), ptr(g3s), Bs, 3, Hs, Ws, Fs, sp)), 4 * (3 * 3 + 4 * Fs), pxs)
     rows[-1]["fp32_TFLOPs"] = 3 * 3 * 3 * Fs * Fs * pxs / (rows[-1]["ms"] * 1e-3) / 1e12
-    del Is, vs, hs, os_, gs, g1s, g2s, g3s
+    fls = torch.empty(Bs, 2, Hos, Wos, device=device)
+    add("SeparableConvFlow_fwd_F51_B8_206x398", timeit(lambda: _lib.call("vfidkr_separableconvflow_forward", ptr(vs), ptr(hs), ptr(fls),
+                                                                          Bs, Hos, Wos, Fs, sp), iters=20), 4 * (2 * Fs + 2), pxs)
+    del Is, vs, hs, os_, gs, g1s, g2s, g3s, fls
     with open(path, "w") as f:
         for r in rows:
             f.write(json.dumps(r) + "\n")

@@ -100,7 +100,26 @@ if a.op == "fi_bench":
     d = bench.build_inputs(torch, dev, seed=1004)
     fi = V.FilterInterpolationModule()
     ops["fi_bench"] = lambda: (fi(d["frame0"], d["flow0"], d["filter0"]), fi(d["frame1"], d["flow1"], d["filter1"]))
-if a.op.startswith("corr"):
+if a.op == "sepconv":
+    # SeparableConv forward + backward at the op table's shape (8 x 3 x 256 x 448, F = 51)
+    Bs, Hs, Ws, Fs = 8, 256, 448, 51
+    Is = torch.rand(Bs, 3, Hs, Ws, device=dev)
+    vs = torch.rand(Bs, Fs, Hs - Fs + 1, Ws - Fs + 1, device=dev) / Fs
+    hs = torch.rand_like(vs) / Fs
+    os_, gs = torch.empty(Bs, 3, Hs - Fs + 1, Ws - Fs + 1, device=dev), torch.randn(Bs, 3, Hs - Fs + 1, Ws - Fs + 1, device=dev)
+    g1s, g2s, g3s = torch.empty_like(Is), torch.empty_like(vs), torch.empty_like(hs)
+    ops["sepconv"] = lambda: (_lib.call("vfidkr_separableconv_forward", ptr(Is), ptr(vs), ptr(hs), ptr(os_), Bs, 3, Hs, Ws, Fs, sp),
+                              _lib.call("vfidkr_separableconv_backward", ptr(Is), ptr(vs), ptr(hs), ptr(gs), ptr(g1s), ptr(g2s), ptr(g3s),
+                                        Bs, 3, Hs, Ws, Fs, sp))
+if a.op == "corr_bwd":
+    f1 = torch.randn(B, 32, H // 4, W // 4, device=dev)
+    f2 = torch.randn_like(f1)
+    go = torch.randn(B, 81, H // 4, W // 4, device=dev)
+    ga, gb = torch.empty_like(f1), torch.empty_like(f2)
+    ops["corr_bwd"] = lambda: _lib.call("vfidkr_correlation_backward", ptr(f1), ptr(f2), ptr(go), ptr(ga), ptr(gb), B, 32, H // 4, W // 4,
+                                        4, 1, 4, 1, 1, 1, sp)
+    fn = ops["corr_bwd"]
+elif a.op.startswith("corr"):
     Cc, s = {"corr_l2": (32, 4), "corr_l3": (64, 8), "corr_l4": (96, 16), "corr_l5": (128, 32), "corr_l6": (196, 64)}[a.op]
     f1 = torch.randn(B, Cc, H // s, W // s, device=dev)
     f2 = torch.randn_like(f1)

@@ -454,23 +454,32 @@ __global__ void __launch_bounds__(256)
 sepconvflow_forward_kernel(const float *__restrict__ in2, const float *__restrict__ in3, float *__restrict__ flow,
                            size_t HWo, size_t total, int F)
 {
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = idx / HWo, po = idx - b * HWo;
+    // one thread per (pixel, flow channel); the grid covers the map exactly (no grid-stride tail)
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = blockIdx.y;   // channel 0 <- input3 (x), channel 1 <- input2 (y)
+    const size_t b = idx / HWo, po = idx - b * HWo;
+    const float *src = (ch == 0 ? in3 : in2) + b * F * HWo + po;
+    float num = 0.f, den = 0.f;
+    int k = 0;
+    for (; k + 8 <= F; k += 8) {
+        float t[8];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {   // channel 0 <- input3 (x), channel 1 <- input2 (y)
-            const float *src = (ch == 0 ? in3 : in2) + b * F * HWo + po;
-            float num = 0.f, den = 0.f;
-            for (int k = 0; k < F; ++k) {
-                const float t = ld_stream(src + (size_t)k * HWo);
-                num += (float)k * t;   // :61
-                den += t;              // :62
-            }
-            // flow_y / sum_weights - ((float)(filter_size)-1.0)/2.0 is evaluated in double (:66)
-            const float val = (float)((double)(num / den) - ((double)(float)F - 1.0) / 2.0);
-            st_stream(flow + (b * 2 + ch) * HWo + po, fabsf(den) > 0.0f ? val : -2000.0f);
+        for (int j = 0; j < 8; ++j) t[j] = ld_stream(src + (size_t)(k + j) * HWo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            num += (float)(k + j) * t[j];   // :61
+            den += t[j];                    // :62
         }
     }
+    for (; k < F; ++k) {
+        const float t = ld_stream(src + (size_t)k * HWo);
+        num += (float)k * t;
+        den += t;
+    }
+    // flow_y / sum_weights - ((float)(filter_size)-1.0)/2.0 is evaluated in double (:66)
+    const float val = (float)((double)(num / den) - ((double)(float)F - 1.0) / 2.0);
+    st_stream(flow + (b * 2 + ch) * HWo + po, fabsf(den) > 0.0f ? val : -2000.0f);
 }
 
 // gi[k] = g * (k / S - num / S^2) where |S| > 0, else 0 (:131-169)
@@ -570,8 +579,8 @@ VFIDKR_API int vfidkr_separableconvflow_forward(const float *input2, const float
 {
     if (B <= 0 || Ho <= 0 || Wo <= 0 || F <= 0 || !input2 || !input3 || !flow_output) return VFIDKR_ERR_ARG;
     const size_t HWo = (size_t)Ho * Wo, total = (size_t)B * HWo;
-    const unsigned nb = (unsigned)min((size_t)sm_count() * 8, (total + 255) / 256);
-    sepconvflow_forward_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(input2, input3, flow_output, HWo, total, F);
+    if ((total + 255) / 256 > 0x7fffffffull) return VFIDKR_ERR_ARG;
+    sepconvflow_forward_kernel<<<dim3((unsigned)((total + 255) / 256), 2), 256, 0, (cudaStream_t)stream>>>(input2, input3, flow_output, HWo, total, F);
     note_launch();
     return check_launch("separableconvflow forward");
 }
