@@ -74,12 +74,16 @@ __device__ __forceinline__ void sepconv_chunk(const float *__restrict__ s_img, c
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int k = 0; k < XC; ++k) h[q][k] = (FULL || k < nk) ? __ldg(hz + (size_t)(xc + k) * HWo + po[q]) : 0.0f;
+    // vertical taps are requested one image row ahead (two CTAs of 8 warps per SM do not hide an L2 round trip)
+    float vn[4] = {__ldg(v + po[0]), __ldg(v + po[1]), 0.0f, 0.0f};
     for (int r = 0; r <= F; ++r) {   // image row row0 + r: vertical tap r of the upper pixels, r - 1 of the lower ones
         float vy[4];
-        vy[0] = r < F ? __ldg(v + (size_t)r * HWo + po[0]) : 0.0f;
-        vy[1] = r < F ? __ldg(v + (size_t)r * HWo + po[1]) : 0.0f;
-        vy[2] = r > 0 ? __ldg(v + (size_t)(r - 1) * HWo + po[2]) : 0.0f;
-        vy[3] = r > 0 ? __ldg(v + (size_t)(r - 1) * HWo + po[3]) : 0.0f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) vy[q] = vn[q];
+        vn[0] = r + 1 < F ? __ldg(v + (size_t)(r + 1) * HWo + po[0]) : 0.0f;
+        vn[1] = r + 1 < F ? __ldg(v + (size_t)(r + 1) * HWo + po[1]) : 0.0f;
+        vn[2] = r < F ? __ldg(v + (size_t)r * HWo + po[2]) : 0.0f;
+        vn[3] = r < F ? __ldg(v + (size_t)r * HWo + po[3]) : 0.0f;
         float I[3][XC + 2];
 #pragma unroll
         for (int cc = 0; cc < 3; ++cc) {
@@ -213,6 +217,14 @@ __device__ __forceinline__ void sepconv_filtergrad_chunk(const float *__restrict
             h[q][k] = (FULL || k < nk) ? __ldg(hz + (size_t)(xc + k) * HWo + po[q]) : 0.0f;
             g3[q][k] = 0.0f;
         }
+    // vertical taps and the carried gradinput2 sums are requested one image row ahead
+    float vn[4], on[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const bool lv = valid[q] && (q >> 1) == 0;
+        vn[q] = lv ? __ldg(v + po[q]) : 0.0f;
+        on[q] = (lv && !first_chunk) ? gi2[po[q]] : 0.0f;
+    }
     for (int r = 0; r <= F; ++r) {   // image row row0 + r: vertical tap r of the upper pixels, r - 1 of the lower ones
         float vy[4], old[4];
         bool live[4];
@@ -220,9 +232,12 @@ __device__ __forceinline__ void sepconv_filtergrad_chunk(const float *__restrict
         for (int q = 0; q < 4; ++q) {
             const int y = r - (q >> 1);
             live[q] = valid[q] && y >= 0 && y < F;
-            const size_t at = (size_t)(live[q] ? y : 0) * HWo + po[q];
-            vy[q] = live[q] ? __ldg(v + at) : 0.0f;
-            old[q] = (live[q] && !first_chunk) ? gi2[at] : 0.0f;
+            vy[q] = vn[q];
+            old[q] = on[q];
+            const bool lvn = valid[q] && y + 1 >= 0 && y + 1 < F;
+            const size_t at = (size_t)(lvn ? y + 1 : 0) * HWo + po[q];
+            vn[q] = lvn ? __ldg(v + at) : 0.0f;
+            on[q] = (lvn && !first_chunk) ? gi2[at] : 0.0f;
         }
         float s2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -362,13 +377,20 @@ __device__ __forceinline__ void sepconv_imagegrad_chunk(float *__restrict__ s_ac
     for (int q = 0; q < 4; ++q)
 #pragma unroll
         for (int k = 0; k < XC; ++k) h[q][k] = (FULL || k < nk) ? __ldg(hz + (size_t)(xc + k) * HWo + po[q]) : 0.0f;
+    auto tap = [&](int q, int r) {   // vertical tap of pixel q that meets image row row0 + r (0 when there is none)
+        const int y = r - (q >> 1);
+        const bool live = valid[q] && y >= 0 && y < F;
+        return live ? __ldg(v + (size_t)(live ? y : 0) * HWo + po[q]) : 0.0f;
+    };
+    float vn[4];   // requested one image row ahead
+#pragma unroll
+    for (int q = 0; q < 4; ++q) vn[q] = tap(q, 0);
     for (int r = 0; r <= F; ++r) {
         float vy[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const int y = r - (q >> 1);
-            const bool live = valid[q] && y >= 0 && y < F;
-            vy[q] = live ? __ldg(v + (size_t)(live ? y : 0) * HWo + po[q]) : 0.0f;
+            vy[q] = vn[q];
+            vn[q] = tap(q, r + 1);
         }
         float col[3][XC + 2];
 #pragma unroll
