@@ -365,6 +365,147 @@ corr_backward_tiled_kernel(const float *__restrict__ other, const float *__restr
     }
 }
 
+// Register-tiled backward.  corr_backward_tiled_kernel above issues one shared-memory load per multiply-add (the 81
+// upstream gradients of ONE pixel in registers, the feature taps from the tile) and is bound by the shared-memory
+// pipe at ~11 % of the HBM roofline.  Here a thread owns 4 neighbouring pixels x 8 channels (32 accumulators); per
+// displacement row it loads the 9 x 4 upstream gradients once (9 LDS.128, shared by its 8 channels) and a 12-float
+// feature window per channel (3 LDS.128) for 36 multiply-adds: 33 LDS.128 per 288 FMAs instead of 288 LDS.32.
+// The upstream gradients of the tile are staged once per CTA, PRE-SHIFTED per displacement for the gradient of the
+// second input (plane d holds gradoutput[d] at (y - tj, x - ti)), so both gradients read them at [d][row][4 * g];
+// 32 channels of the other feature map are staged per pass.  The sum over the 81 displacements runs in the same order
+// as in corr_backward_tiled_kernel.  Tiles of 32 x 4 pixels, 128 threads, 100 KB of shared memory: two CTAs per SM, so
+// that one stages while the other computes.
+namespace cbr {
+constexpr int DR = 4, D = 9, TX = 32, TY = 4, PX = 4, CKT = 8, NG = 4, CPASS = CKT * NG, NT = (TX / PX) * TY * NG;
+constexpr int TW = TX + 2 * DR, TH = TY + 2 * DR;
+constexpr int F_FLOATS = CPASS * TH * TW;
+// row pitch of a staged gradoutput plane: for the second gradient plane d starts at the 16-byte aligned column
+// x0 + 4 * floor(-ti / 4), four columns wider than the tile, and the thread picks its window at -ti mod 4
+__host__ __device__ constexpr int go_pitch(int which) { return which == 1 ? TX : TX + 4; }
+constexpr size_t smem_bytes(int which) { return (size_t)(D * D * TY * go_pitch(which) + F_FLOATS) * sizeof(float); }
+}  // namespace cbr
+
+// vec: bit 0 = 16-byte stores, bit 1 = 16-byte staging of the feature tile, bit 2 = 16-byte staging of gradoutput
+template <int WHICH>
+__global__ void __launch_bounds__(cbr::NT, 2)
+corr_backward_regtile_kernel(const float *__restrict__ other, const float *__restrict__ gout, float *__restrict__ gi,
+                             int C, int H, int W, int s, int oh, int ow, int vec)
+{
+    using namespace cbr;
+    constexpr int GOP = go_pitch(WHICH);
+    extern __shared__ __align__(16) float smem_f[];
+    float *sgo = smem_f;                          // [81][TY][GOP]
+    float *sf = smem_f + D * D * TY * GOP;        // [CPASS][TH][TW]
+    const int tid = threadIdx.x;
+    const int g = tid % (TX / PX), ry = (tid / (TX / PX)) % TY, cg = tid / ((TX / PX) * TY);
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, n = blockIdx.z;
+    const size_t HW = (size_t)H * W, plane = (size_t)oh * ow;
+    const int vec_store = vec & 1;
+
+    {   // upstream gradients of the tile, all 81 planes; where there is no source the entry is zero.  Entries of
+        // pixels outside the image are never used for a stored result.
+        const float *gsrc = gout + (size_t)n * D * D * plane;
+        if (vec & 4) {   // 16-byte groups: W, ow and s are multiples of 4, so a group is all in or all out
+            for (int i = tid; i < D * D * TY * (GOP / 4); i += NT) {
+                const int d = i / (TY * (GOP / 4)), r = i - d * (TY * (GOP / 4)), sy = r / (GOP / 4), sx = 4 * (r - sy * (GOP / 4));
+                const int tj = d / D - DR, bb = d % D;
+                const int oy = WHICH == 1 ? y0 + sy + s : y0 + sy + s - tj;
+                const int ox = WHICH == 1 ? x0 + sx + s : x0 + sx + s + 4 - 4 * ((bb + 3) / 4);   // 4 * floor((4 - b) / 4) = 4, 0, -4
+                const bool ok = oy >= 0 && oy < oh && ox >= 0 && ox < ow;
+                cp_async_16(sgo + (d * TY + sy) * GOP + sx, ok ? gsrc + (size_t)d * plane + (size_t)oy * ow + ox : gsrc, ok);
+            }
+        } else {
+            for (int i = tid; i < D * D * TY * GOP; i += NT) {
+                const int d = i / (TY * GOP), r = i - d * (TY * GOP), sy = r / GOP, sx = r - sy * GOP;
+                const int tj = d / D - DR, bb = d % D;
+                const int oy = WHICH == 1 ? y0 + sy + s : y0 + sy + s - tj;
+                const int ox = WHICH == 1 ? x0 + sx + s : x0 + sx + s + 4 - 4 * ((bb + 3) / 4);
+                const bool ok = oy >= 0 && oy < oh && ox >= 0 && ox < ow;
+                cp_async_4(sgo + i, ok ? gsrc + (size_t)d * plane + (size_t)oy * ow + ox : gsrc, ok);
+            }
+        }
+    }
+    const float nel = (float)C;
+    for (int c0 = 0; c0 < C; c0 += CPASS) {
+        if (c0 > 0) __syncthreads();   // the previous pass has been consumed
+        if (vec & 2) {   // W % 4 == 0 and x0 - DR a multiple of 4: a group of four is all inside the image or all outside
+            for (int i = tid; i < CPASS * TH * (TW / 4); i += NT) {
+                const int ch = i / (TH * (TW / 4)), r2 = i - ch * (TH * (TW / 4)), r = r2 / (TW / 4), cx = 4 * (r2 - r * (TW / 4));
+                const int gy = y0 - DR + r, gx = x0 - DR + cx;
+                const bool ok = c0 + ch < C && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                cp_async_16(sf + (ch * TH + r) * TW + cx, ok ? other + ((size_t)n * C + c0 + ch) * HW + (size_t)gy * W + gx : other, ok);
+            }
+        } else {
+            for (int ch = 0; ch < CPASS; ++ch) {
+                const bool chok = c0 + ch < C;
+                const float *src = other + ((size_t)n * C + (chok ? c0 + ch : 0)) * HW;
+                for (int i = tid; i < TH * TW; i += NT) {
+                    const int r = i / TW, cx = i - r * TW, gy = y0 - DR + r, gx = x0 - DR + cx;
+                    const bool ok = chok && gy >= 0 && gy < H && gx >= 0 && gx < W;
+                    cp_async_4(sf + ch * (TH * TW) + i, ok ? src + (size_t)gy * W + gx : other, ok);
+                }
+            }
+        }
+        cp_async_commit();
+        cp_async_wait<0>();
+        __syncthreads();
+
+        float acc[CKT][PX];
+#pragma unroll
+        for (int ch = 0; ch < CKT; ++ch)
+#pragma unroll
+            for (int p = 0; p < PX; ++p) acc[ch][p] = 0.0f;
+#pragma unroll 1
+        for (int a = 0; a < D; ++a) {
+            float gq[D][PX];
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+                const float *gp = sgo + ((a * D + b) * TY + ry) * GOP + PX * g;
+                const float4 t = *reinterpret_cast<const float4 *>(gp);
+                if (WHICH == 1 || (4 - b) % 4 == 0) {
+                    gq[b][0] = t.x; gq[b][1] = t.y; gq[b][2] = t.z; gq[b][3] = t.w;
+                } else {   // window at column offset o = (4 - b) mod 4 of the aligned plane: two aligned loads
+                    const float4 u = *reinterpret_cast<const float4 *>(gp + 4);
+                    const float w8[8] = {t.x, t.y, t.z, t.w, u.x, u.y, u.z, u.w};
+                    const int o = ((4 - b) % 4 + 4) % 4;
+#pragma unroll
+                    for (int p = 0; p < PX; ++p) gq[b][p] = w8[o + p];
+                }
+            }
+            // gi1: f2[y + tj, x + ti] -> tile row ry + a, column px + b;  gi2: f1[y - tj, x - ti] -> row ry + 8 - a, column px + 8 - b
+            const float *frow = sf + (cg * CKT) * (TH * TW) + (WHICH == 1 ? ry + a : ry + 2 * DR - a) * TW + PX * g;
+#pragma unroll
+            for (int ch = 0; ch < CKT; ++ch) {
+                const float4 f0 = *reinterpret_cast<const float4 *>(frow + ch * (TH * TW));
+                const float4 f1 = *reinterpret_cast<const float4 *>(frow + ch * (TH * TW) + 4);
+                const float4 f2 = *reinterpret_cast<const float4 *>(frow + ch * (TH * TW) + 8);
+                const float fv[12] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w, f2.x, f2.y, f2.z, f2.w};
+#pragma unroll
+                for (int b = 0; b < D; ++b)
+#pragma unroll
+                    for (int p = 0; p < PX; ++p)
+                        acc[ch][p] = fmaf(gq[b][p], fv[WHICH == 1 ? p + b : p + 2 * DR - b], acc[ch][p]);
+            }
+        }
+        const int y = y0 + ry, x = x0 + PX * g;
+        if (y < H) {
+#pragma unroll
+            for (int ch = 0; ch < CKT; ++ch) {
+                const int c = c0 + cg * CKT + ch;
+                if (c >= C) break;
+                float *dst = gi + ((size_t)n * C + c) * HW + (size_t)y * W + x;
+                if (vec_store && x + PX <= W) {
+                    st_stream4(dst, make_float4(acc[ch][0] / nel, acc[ch][1] / nel, acc[ch][2] / nel, acc[ch][3] / nel));
+                } else {
+#pragma unroll
+                    for (int p = 0; p < PX; ++p)
+                        if (x + p < W) st_stream(dst + p, acc[ch][p] / nel);
+                }
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // generic backward: restates the reference formulas, one thread per (n, c, y, x); stride1 must be 1
 // for the reference itself to stay in bounds, other strides follow the same index arithmetic with
@@ -550,9 +691,22 @@ VFIDKR_API int vfidkr_correlation_backward(const float *input1, const float *inp
     if (cs.oh <= 0 || cs.ow <= 0) return VFIDKR_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
     if (k == 1 && s1 == 1 && s2 == 1 && md == 4 && pad >= md) {
-        dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), B);
-        corr_backward_tiled_kernel<1><<<grid, block, 0, s>>>(input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow);
-        corr_backward_tiled_kernel<2><<<grid, block, 0, s>>>(input1, gradoutput, gradinput2, C, H, W, pad - md, cs.oh, cs.ow);
+        dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), B), grid_r(ceil_div(W, cbr::TX), ceil_div(H, cbr::TY), B);
+        const bool big_smem =
+            cudaFuncSetAttribute(corr_backward_regtile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbr::smem_bytes(1)) == cudaSuccess &&
+            cudaFuncSetAttribute(corr_backward_regtile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbr::smem_bytes(2)) == cudaSuccess;
+        if (big_smem && ceil_div(H, cbr::TY) <= 65535u) {
+            const bool w4 = W % 4 == 0;
+            const int vgo = (w4 && cs.ow % 4 == 0 && (pad - md) % 4 == 0 && aligned16(gradoutput)) ? 4 : 0;
+            const int v1 = ((w4 && aligned16(gradinput1)) ? 1 : 0) | ((w4 && aligned16(input2)) ? 2 : 0) | vgo;
+            const int v2 = ((w4 && aligned16(gradinput2)) ? 1 : 0) | ((w4 && aligned16(input1)) ? 2 : 0) | vgo;
+            corr_backward_regtile_kernel<1><<<grid_r, cbr::NT, cbr::smem_bytes(1), s>>>(input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow, v1);
+            corr_backward_regtile_kernel<2><<<grid_r, cbr::NT, cbr::smem_bytes(2), s>>>(input1, gradoutput, gradinput2, C, H, W, pad - md, cs.oh, cs.ow, v2);
+        } else {
+            (void)cudaGetLastError();
+            corr_backward_tiled_kernel<1><<<grid, block, 0, s>>>(input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow);
+            corr_backward_tiled_kernel<2><<<grid, block, 0, s>>>(input1, gradoutput, gradinput2, C, H, W, pad - md, cs.oh, cs.ow);
+        }
         note_launch(2);
     } else {
         if ((long long)B * C > 65535) return VFIDKR_ERR_ARG;

@@ -194,6 +194,12 @@ __device__ __forceinline__ void cp_async_4(void *smem_dst, const void *gmem_src,
                  "r"(valid ? 4u : 0u)
                  : "memory");
 }
+__device__ __forceinline__ void cp_async_16(void *smem_dst, const void *gmem_src, bool valid)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src),
+                 "r"(valid ? 16u : 0u)
+                 : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
