@@ -370,19 +370,19 @@ corr_backward_tiled_kernel(const float *__restrict__ other, const float *__restr
 // pipe at ~11 % of the HBM roofline.  Here a thread owns 4 neighbouring pixels x 8 channels (32 accumulators); per
 // displacement row it loads the 9 x 4 upstream gradients once (9 LDS.128, shared by its 8 channels) and a 12-float
 // feature window per channel (3 LDS.128) for 36 multiply-adds: 33 LDS.128 per 288 FMAs instead of 288 LDS.32.
-// The upstream gradients of the tile are staged once per CTA, PRE-SHIFTED per displacement for the gradient of the
-// second input (plane d holds gradoutput[d] at (y - tj, x - ti)), so both gradients read them at [d][row][4 * g];
-// 32 channels of the other feature map are staged per pass.  The sum over the 81 displacements runs in the same order
-// as in corr_backward_tiled_kernel.  Tiles of 32 x 4 pixels, 128 threads, 100 KB of shared memory: two CTAs per SM, so
-// that one stages while the other computes.
+// A CTA owns a 32 x 8 pixel tile and stages 32 channels of the other feature map per pass (80 KB); the upstream
+// gradients stream through a two-slot ring, one displacement row (9 planes) at a time, copied asynchronously while
+// the previous row is being used.  For the gradient of the second input the planes are staged PRE-SHIFTED (plane d
+// holds gradoutput[d] at (y - tj, x - ti), its columns starting at the 16-byte aligned x0 + 4 * floor(-ti / 4)), so
+// that both gradients read aligned 16-byte windows.  The sum over the 81 displacements runs in the same order as in
+// corr_backward_tiled_kernel.  256 threads, ~100 KB of shared memory: two CTAs per SM.
 namespace cbr {
-constexpr int DR = 4, D = 9, TX = 32, TY = 4, PX = 4, CKT = 8, NG = 4, CPASS = CKT * NG, NT = (TX / PX) * TY * NG;
+constexpr int DR = 4, D = 9, TX = 32, TY = 8, PX = 4, CKT = 8, NG = 4, CPASS = CKT * NG, NT = (TX / PX) * TY * NG;
 constexpr int TW = TX + 2 * DR, TH = TY + 2 * DR;
 constexpr int F_FLOATS = CPASS * TH * TW;
-// row pitch of a staged gradoutput plane: for the second gradient plane d starts at the 16-byte aligned column
-// x0 + 4 * floor(-ti / 4), four columns wider than the tile, and the thread picks its window at -ti mod 4
 __host__ __device__ constexpr int go_pitch(int which) { return which == 1 ? TX : TX + 4; }
-constexpr size_t smem_bytes(int which) { return (size_t)(D * D * TY * go_pitch(which) + F_FLOATS) * sizeof(float); }
+__host__ __device__ constexpr int go_slot(int which) { return D * TY * go_pitch(which); }   // one displacement row
+constexpr size_t smem_bytes(int which) { return (size_t)(2 * go_slot(which) + F_FLOATS) * sizeof(float); }
 }  // namespace cbr
 
 // vec: bit 0 = 16-byte stores, bit 1 = 16-byte staging of the feature tile, bit 2 = 16-byte staging of gradoutput
@@ -392,42 +392,44 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
                              int C, int H, int W, int s, int oh, int ow, int vec)
 {
     using namespace cbr;
-    constexpr int GOP = go_pitch(WHICH);
+    constexpr int GOP = go_pitch(WHICH), SLOT = go_slot(WHICH);
     extern __shared__ __align__(16) float smem_f[];
-    float *sgo = smem_f;                          // [81][TY][GOP]
-    float *sf = smem_f + D * D * TY * GOP;        // [CPASS][TH][TW]
+    float *sgo = smem_f;                 // [2][9][TY][GOP]
+    float *sf = smem_f + 2 * SLOT;       // [CPASS][TH][TW]
     const int tid = threadIdx.x;
     const int g = tid % (TX / PX), ry = (tid / (TX / PX)) % TY, cg = tid / ((TX / PX) * TY);
     const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, n = blockIdx.z;
     const size_t HW = (size_t)H * W, plane = (size_t)oh * ow;
     const int vec_store = vec & 1;
+    const float *gsrc = gout + (size_t)n * D * D * plane;
 
-    {   // upstream gradients of the tile, all 81 planes; where there is no source the entry is zero.  Entries of
-        // pixels outside the image are never used for a stored result.
-        const float *gsrc = gout + (size_t)n * D * D * plane;
+    // upstream gradients of the tile for displacement row a (9 planes) into ring slot a & 1; zero where there is no
+    // source.  Entries of pixels outside the image are never used for a stored result.
+    auto stage_go = [&](int a) {
+        float *dst = sgo + (a & 1) * SLOT;
+        const int tj = a - DR;
         if (vec & 4) {   // 16-byte groups: W, ow and s are multiples of 4, so a group is all in or all out
-            for (int i = tid; i < D * D * TY * (GOP / 4); i += NT) {
-                const int d = i / (TY * (GOP / 4)), r = i - d * (TY * (GOP / 4)), sy = r / (GOP / 4), sx = 4 * (r - sy * (GOP / 4));
-                const int tj = d / D - DR, bb = d % D;
+            for (int i = tid; i < D * TY * (GOP / 4); i += NT) {
+                const int bb = i / (TY * (GOP / 4)), r = i - bb * (TY * (GOP / 4)), sy = r / (GOP / 4), sx = 4 * (r - sy * (GOP / 4));
                 const int oy = WHICH == 1 ? y0 + sy + s : y0 + sy + s - tj;
                 const int ox = WHICH == 1 ? x0 + sx + s : x0 + sx + s + 4 - 4 * ((bb + 3) / 4);   // 4 * floor((4 - b) / 4) = 4, 0, -4
                 const bool ok = oy >= 0 && oy < oh && ox >= 0 && ox < ow;
-                cp_async_16(sgo + (d * TY + sy) * GOP + sx, ok ? gsrc + (size_t)d * plane + (size_t)oy * ow + ox : gsrc, ok);
+                cp_async_16(dst + (bb * TY + sy) * GOP + sx, ok ? gsrc + (size_t)(a * D + bb) * plane + (size_t)oy * ow + ox : gsrc, ok);
             }
         } else {
-            for (int i = tid; i < D * D * TY * GOP; i += NT) {
-                const int d = i / (TY * GOP), r = i - d * (TY * GOP), sy = r / GOP, sx = r - sy * GOP;
-                const int tj = d / D - DR, bb = d % D;
+            for (int i = tid; i < SLOT; i += NT) {
+                const int bb = i / (TY * GOP), r = i - bb * (TY * GOP), sy = r / GOP, sx = r - sy * GOP;
                 const int oy = WHICH == 1 ? y0 + sy + s : y0 + sy + s - tj;
                 const int ox = WHICH == 1 ? x0 + sx + s : x0 + sx + s + 4 - 4 * ((bb + 3) / 4);
                 const bool ok = oy >= 0 && oy < oh && ox >= 0 && ox < ow;
-                cp_async_4(sgo + i, ok ? gsrc + (size_t)d * plane + (size_t)oy * ow + ox : gsrc, ok);
+                cp_async_4(dst + i, ok ? gsrc + (size_t)(a * D + bb) * plane + (size_t)oy * ow + ox : gsrc, ok);
             }
         }
-    }
+    };
+
     const float nel = (float)C;
     for (int c0 = 0; c0 < C; c0 += CPASS) {
-        if (c0 > 0) __syncthreads();   // the previous pass has been consumed
+        // (the previous pass ended with a barrier: the feature tile and both ring slots are free)
         if (vec & 2) {   // W % 4 == 0 and x0 - DR a multiple of 4: a group of four is all inside the image or all outside
             for (int i = tid; i < CPASS * TH * (TW / 4); i += NT) {
                 const int ch = i / (TH * (TW / 4)), r2 = i - ch * (TH * (TW / 4)), r = r2 / (TW / 4), cx = 4 * (r2 - r * (TW / 4));
@@ -446,9 +448,8 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
                 }
             }
         }
+        stage_go(0);
         cp_async_commit();
-        cp_async_wait<0>();
-        __syncthreads();
 
         float acc[CKT][PX];
 #pragma unroll
@@ -457,10 +458,19 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
             for (int p = 0; p < PX; ++p) acc[ch][p] = 0.0f;
 #pragma unroll 1
         for (int a = 0; a < D; ++a) {
+            if (a + 1 < D) {
+                stage_go(a + 1);   // its slot was last read in iteration a - 1, which ended with a barrier
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncthreads();
+            const float *go_a = sgo + (a & 1) * SLOT;
             float gq[D][PX];
 #pragma unroll
             for (int b = 0; b < D; ++b) {
-                const float *gp = sgo + ((a * D + b) * TY + ry) * GOP + PX * g;
+                const float *gp = go_a + (b * TY + ry) * GOP + PX * g;
                 const float4 t = *reinterpret_cast<const float4 *>(gp);
                 if (WHICH == 1 || (4 - b) % 4 == 0) {
                     gq[b][0] = t.x; gq[b][1] = t.y; gq[b][2] = t.z; gq[b][3] = t.w;
@@ -486,6 +496,7 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
                     for (int p = 0; p < PX; ++p)
                         acc[ch][p] = fmaf(gq[b][p], fv[WHICH == 1 ? p + b : p + 2 * DR - b], acc[ch][p]);
             }
+            __syncthreads();   // slot a & 1 (and, after the last row, the feature tile) may be overwritten
         }
         const int y = y0 + ry, x = x0 + PX * g;
         if (y < H) {
