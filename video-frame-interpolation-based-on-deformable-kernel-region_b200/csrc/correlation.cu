@@ -386,14 +386,19 @@ constexpr size_t smem_bytes(int which) { return (size_t)(2 * go_slot(which) + F_
 }  // namespace cbr
 
 // vec: bit 0 = 16-byte stores, bit 1 = 16-byte staging of the feature tile, bit 2 = 16-byte staging of gradoutput
-template <int WHICH>
+// TMA = true (everything 16-byte aligned): one elected thread issues box loads of the feature tile and of each
+// displacement row (one box of 9 planes for the first gradient, 9 shifted single-plane boxes for the second) and the
+// threads wait on mbarriers; otherwise all threads stage with cp.async.
+template <int WHICH, bool TMA>
 __global__ void __launch_bounds__(cbr::NT, 2)
-corr_backward_regtile_kernel(const float *__restrict__ other, const float *__restrict__ gout, float *__restrict__ gi,
+corr_backward_regtile_kernel(const __grid_constant__ CUtensorMap map_f, const __grid_constant__ CUtensorMap map_g,
+                             const float *__restrict__ other, const float *__restrict__ gout, float *__restrict__ gi,
                              int C, int H, int W, int s, int oh, int ow, int vec)
 {
     using namespace cbr;
     constexpr int GOP = go_pitch(WHICH), SLOT = go_slot(WHICH);
-    extern __shared__ __align__(16) float smem_f[];
+    extern __shared__ __align__(128) float smem_f[];
+    __shared__ uint64_t bars[3];   // ring slots 0 / 1, feature tile
     float *sgo = smem_f;                 // [2][9][TY][GOP]
     float *sf = smem_f + 2 * SLOT;       // [CPASS][TH][TW]
     const int tid = threadIdx.x;
@@ -405,8 +410,29 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
 
     // upstream gradients of the tile for displacement row a (9 planes) into ring slot a & 1; zero where there is no
     // source.  Entries of pixels outside the image are never used for a stored result.
-    auto stage_go = [&](int a) {
-        float *dst = sgo + (a & 1) * SLOT;
+    if (TMA) {
+        if (tid == 0) {
+            prefetch_tensormap(&map_f);
+            prefetch_tensormap(&map_g);
+            for (int i = 0; i < 3; ++i) mbar_init(&bars[i], 1);
+            fence_mbar_init();
+        }
+        __syncthreads();
+    }
+    auto issue_go = [&](int item, int a) {   // thread 0, TMA path: displacement row a into ring slot item & 1
+        uint64_t *bar = &bars[item & 1];
+        float *dst = sgo + (item & 1) * SLOT;
+        mbar_arrive_expect_tx(bar, SLOT * sizeof(float));
+        if (WHICH == 1) {
+            tma_load_4d(dst, &map_g, bar, x0 + s, y0 + s, a * D, n);
+        } else {
+#pragma unroll
+            for (int bb = 0; bb < D; ++bb)
+                tma_load_4d(dst + bb * TY * GOP, &map_g, bar, x0 + s + 4 - 4 * ((bb + 3) / 4), y0 + s - (a - DR), a * D + bb, n);
+        }
+    };
+    auto stage_go = [&](int item, int a) {
+        float *dst = sgo + (item & 1) * SLOT;
         const int tj = a - DR;
         if (vec & 4) {   // 16-byte groups: W, ow and s are multiples of 4, so a group is all in or all out
             for (int i = tid; i < D * TY * (GOP / 4); i += NT) {
@@ -428,9 +454,16 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
     };
 
     const float nel = (float)C;
-    for (int c0 = 0; c0 < C; c0 += CPASS) {
+    int item = 0, pass = 0;   // displacement rows staged so far (ring position / mbarrier phase), channel passes
+    for (int c0 = 0; c0 < C; c0 += CPASS, ++pass) {
         // (the previous pass ended with a barrier: the feature tile and both ring slots are free)
-        if (vec & 2) {   // W % 4 == 0 and x0 - DR a multiple of 4: a group of four is all inside the image or all outside
+        if (TMA) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&bars[2], F_FLOATS * sizeof(float));
+                tma_load_4d(sf, &map_f, &bars[2], x0 - DR, y0 - DR, c0, n);   // rows / columns / channels outside: zero
+                issue_go(item, 0);
+            }
+        } else if (vec & 2) {   // W % 4 == 0 and x0 - DR a multiple of 4: a group of four is all inside the image or all outside
             for (int i = tid; i < CPASS * TH * (TW / 4); i += NT) {
                 const int ch = i / (TH * (TW / 4)), r2 = i - ch * (TH * (TW / 4)), r = r2 / (TW / 4), cx = 4 * (r2 - r * (TW / 4));
                 const int gy = y0 - DR + r, gx = x0 - DR + cx;
@@ -448,8 +481,10 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
                 }
             }
         }
-        stage_go(0);
-        cp_async_commit();
+        if (!TMA) {
+            stage_go(item, 0);
+            cp_async_commit();
+        }
 
         float acc[CKT][PX];
 #pragma unroll
@@ -457,16 +492,23 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
 #pragma unroll
             for (int p = 0; p < PX; ++p) acc[ch][p] = 0.0f;
 #pragma unroll 1
-        for (int a = 0; a < D; ++a) {
-            if (a + 1 < D) {
-                stage_go(a + 1);   // its slot was last read in iteration a - 1, which ended with a barrier
-                cp_async_commit();
-                cp_async_wait<1>();
+        for (int a = 0; a < D; ++a, ++item) {
+            // the next row goes into the slot last read in iteration a - 1, which ended with a barrier
+            if (TMA) {
+                if (tid == 0 && a + 1 < D) issue_go(item + 1, a + 1);
+                if (a == 0) mbar_wait(&bars[2], (uint32_t)(pass & 1));
+                mbar_wait(&bars[item & 1], (uint32_t)((item >> 1) & 1));
             } else {
-                cp_async_wait<0>();
+                if (a + 1 < D) {
+                    stage_go(item + 1, a + 1);
+                    cp_async_commit();
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                __syncthreads();
             }
-            __syncthreads();
-            const float *go_a = sgo + (a & 1) * SLOT;
+            const float *go_a = sgo + (item & 1) * SLOT;
             float gq[D][PX];
 #pragma unroll
             for (int b = 0; b < D; ++b) {
@@ -496,7 +538,7 @@ corr_backward_regtile_kernel(const float *__restrict__ other, const float *__res
                     for (int p = 0; p < PX; ++p)
                         acc[ch][p] = fmaf(gq[b][p], fv[WHICH == 1 ? p + b : p + 2 * DR - b], acc[ch][p]);
             }
-            __syncthreads();   // slot a & 1 (and, after the last row, the feature tile) may be overwritten
+            __syncthreads();   // this slot (and, after the last row, the feature tile) may be overwritten
         }
         const int y = y0 + ry, x = x0 + PX * g;
         if (y < H) {
@@ -703,16 +745,24 @@ VFIDKR_API int vfidkr_correlation_backward(const float *input1, const float *inp
     cudaStream_t s = (cudaStream_t)stream;
     if (k == 1 && s1 == 1 && s2 == 1 && md == 4 && pad >= md) {
         dim3 block(32, 8), grid(ceil_div(W, 32), ceil_div(H, 8), B), grid_r(ceil_div(W, cbr::TX), ceil_div(H, cbr::TY), B);
+        const bool w4 = W % 4 == 0;
+        const int vgo = (w4 && cs.ow % 4 == 0 && (pad - md) % 4 == 0 && aligned16(gradoutput)) ? 4 : 0;
+        const int v1 = ((w4 && aligned16(gradinput1)) ? 1 : 0) | ((w4 && aligned16(input2)) ? 2 : 0) | vgo;
+        const int v2 = ((w4 && aligned16(gradinput2)) ? 1 : 0) | ((w4 && aligned16(input1)) ? 2 : 0) | vgo;
+        CUtensorMap mf1, mf2, mg1, mg2;
+        memset(&mf1, 0, sizeof(mf1)); memset(&mf2, 0, sizeof(mf2)); memset(&mg1, 0, sizeof(mg1)); memset(&mg2, 0, sizeof(mg2));
+        const bool tma1 = (v1 & 6) == 6 && encode_tensor_map_4d(&mf1, input2, W, H, C, B, cbr::TW, cbr::TH, cbr::CPASS) &&
+                          encode_tensor_map_4d(&mg1, gradoutput, cs.ow, cs.oh, 81, B, cbr::go_pitch(1), cbr::TY, cbr::D);
+        const bool tma2 = (v2 & 6) == 6 && encode_tensor_map_4d(&mf2, input1, W, H, C, B, cbr::TW, cbr::TH, cbr::CPASS) &&
+                          encode_tensor_map_4d(&mg2, gradoutput, cs.ow, cs.oh, 81, B, cbr::go_pitch(2), cbr::TY, 1);
+        auto k1 = tma1 ? corr_backward_regtile_kernel<1, true> : corr_backward_regtile_kernel<1, false>;
+        auto k2 = tma2 ? corr_backward_regtile_kernel<2, true> : corr_backward_regtile_kernel<2, false>;
         const bool big_smem =
-            cudaFuncSetAttribute(corr_backward_regtile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbr::smem_bytes(1)) == cudaSuccess &&
-            cudaFuncSetAttribute(corr_backward_regtile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbr::smem_bytes(2)) == cudaSuccess;
+            cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbr::smem_bytes(1)) == cudaSuccess &&
+            cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cbr::smem_bytes(2)) == cudaSuccess;
         if (big_smem && ceil_div(H, cbr::TY) <= 65535u) {
-            const bool w4 = W % 4 == 0;
-            const int vgo = (w4 && cs.ow % 4 == 0 && (pad - md) % 4 == 0 && aligned16(gradoutput)) ? 4 : 0;
-            const int v1 = ((w4 && aligned16(gradinput1)) ? 1 : 0) | ((w4 && aligned16(input2)) ? 2 : 0) | vgo;
-            const int v2 = ((w4 && aligned16(gradinput2)) ? 1 : 0) | ((w4 && aligned16(input1)) ? 2 : 0) | vgo;
-            corr_backward_regtile_kernel<1><<<grid_r, cbr::NT, cbr::smem_bytes(1), s>>>(input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow, v1);
-            corr_backward_regtile_kernel<2><<<grid_r, cbr::NT, cbr::smem_bytes(2), s>>>(input1, gradoutput, gradinput2, C, H, W, pad - md, cs.oh, cs.ow, v2);
+            k1<<<grid_r, cbr::NT, cbr::smem_bytes(1), s>>>(mf1, mg1, input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow, v1);
+            k2<<<grid_r, cbr::NT, cbr::smem_bytes(2), s>>>(mf2, mg2, input1, gradoutput, gradinput2, C, H, W, pad - md, cs.oh, cs.ow, v2);
         } else {
             (void)cudaGetLastError();
             corr_backward_tiled_kernel<1><<<grid, block, 0, s>>>(input2, gradoutput, gradinput1, C, H, W, pad - md, cs.oh, cs.ow);
