@@ -8,7 +8,7 @@
 //     direct kernel is the load per multiply-add.  The tiled kernels stage the image region of a 64 x 16 pixel tile
 //     in shared memory, give a thread a 2 x 2 block of pixels and hold the horizontal taps in registers, so that one
 //     8-byte shared-memory access feeds eight multiply-adds (forward, filter gradients) or carries eight terms
-//     (image gradient).  Measured at 8 x 3 x 256 x 448, F = 51: forward 1.37 -> 0.65 ms, backward 8.2 -> 2.4 ms.
+//     (image gradient).  Measured at 8 x 3 x 256 x 448, F = 51: forward 1.37 -> 0.56 ms, backward 8.2 -> 1.9 ms.
 //   * gradinput2 / gradinput3 use no atomics (thread-private sums; the reference issues 2*C*F*F atomicAdds per pixel,
 //     :124-127); gradinput1 is summed per tile in shared memory and added to the image with ~9 atomics per element
 //     (the reference: F*F per element, :122-123).  The direct kernels (F too large for the shared-memory region) use
