@@ -453,7 +453,10 @@ corr_backward_regtile_kernel(const __grid_constant__ CUtensorMap map_f, const __
         }
     };
 
-    const float nel = (float)C;
+    // sum / nelems as the reference writes it; for a power-of-two channel count the reciprocal multiply is bit-identical
+    const float nel = (float)C, rnel = 1.0f / nel;
+    const bool pow2 = (C & (C - 1)) == 0;
+    auto scaled = [&](float v) { return pow2 ? v * rnel : v / nel; };
     int item = 0, pass = 0;   // displacement rows staged so far (ring position / mbarrier phase), channel passes
     for (int c0 = 0; c0 < C; c0 += CPASS, ++pass) {
         // (the previous pass ended with a barrier: the feature tile and both ring slots are free)
@@ -548,11 +551,11 @@ corr_backward_regtile_kernel(const __grid_constant__ CUtensorMap map_f, const __
                 if (c >= C) break;
                 float *dst = gi + ((size_t)n * C + c) * HW + (size_t)y * W + x;
                 if (vec_store && x + PX <= W) {
-                    st_stream4(dst, make_float4(acc[ch][0] / nel, acc[ch][1] / nel, acc[ch][2] / nel, acc[ch][3] / nel));
+                    st_stream4(dst, make_float4(scaled(acc[ch][0]), scaled(acc[ch][1]), scaled(acc[ch][2]), scaled(acc[ch][3])));
                 } else {
 #pragma unroll
                     for (int p = 0; p < PX; ++p)
-                        if (x + p < W) st_stream(dst + p, acc[ch][p] / nel);
+                        if (x + p < W) st_stream(dst + p, scaled(acc[ch][p]));
                 }
             }
         }
