@@ -62,13 +62,12 @@ namespace sct {
 constexpr int TWO = 64, THO = 16, NT = 256, XC = 8;
 }
 
-template <bool FULL>
+template <int XC, bool FULL>
 __device__ __forceinline__ void sepconv_chunk(const float *__restrict__ s_img, const float *__restrict__ v,
                                               const float *__restrict__ hz, const size_t (&po)[4], size_t HWo,
                                               int F, int RH, int pitch, int row0, int col0, int xc, int nk, int nc,
                                               float (&acc)[4][3])
 {
-    using namespace sct;
     float h[4][XC];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -143,8 +142,9 @@ sepconv_forward_tiled_kernel(const float *__restrict__ in1, const float *__restr
         for (int q = 0; q < 4; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.0f;
         int xc = 0;
         for (; xc + XC <= F; xc += XC)
-            sepconv_chunk<true>(s_img, v, hz, po, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, XC, nc, acc);
-        if (xc < F) sepconv_chunk<false>(s_img, v, hz, po, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, F - xc, nc, acc);
+            sepconv_chunk<XC, true>(s_img, v, hz, po, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, XC, nc, acc);
+        if (F - xc > XC / 2) sepconv_chunk<XC, false>(s_img, v, hz, po, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, F - xc, nc, acc);
+        else if (xc < F) sepconv_chunk<XC / 2, false>(s_img, v, hz, po, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, F - xc, nc, acc);   // short tail: half the columns
 #pragma unroll
         for (int q = 0; q < 4; ++q)
 #pragma unroll
@@ -200,7 +200,7 @@ namespace scb {
 constexpr int XC = 8, XH = 4;   // columns per chunk (taps held in registers); columns per shared-memory step
 }
 
-template <bool FULL>
+template <int XC, bool FULL>
 __device__ __forceinline__ void sepconv_filtergrad_chunk(const float *__restrict__ s_img, const float *__restrict__ v,
                                                          const float *__restrict__ hz, float *__restrict__ gi2,
                                                          float *__restrict__ gi3, const size_t (&po)[4],
@@ -208,7 +208,7 @@ __device__ __forceinline__ void sepconv_filtergrad_chunk(const float *__restrict
                                                          int row0, int col0, int xc, int nk, const float (&g)[4][3],
                                                          bool first_chunk, bool first_pass)
 {
-    using namespace scb;
+    constexpr int XH = scb::XH;
     float h[4][XC], g3[4][XC];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -319,10 +319,13 @@ sepconv_backward_filters_tiled_kernel(const float *__restrict__ in1, const float
 
         int xc = 0;
         for (; xc + scb::XC <= F; xc += scb::XC)
-            sepconv_filtergrad_chunk<true>(s_img, v, hz, o2, o3, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc,
+            sepconv_filtergrad_chunk<scb::XC, true>(s_img, v, hz, o2, o3, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc,
                                            scb::XC, g, c0 == 0 && xc == 0, c0 == 0);
-        if (xc < F)
-            sepconv_filtergrad_chunk<false>(s_img, v, hz, o2, o3, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc,
+        if (F - xc > scb::XC / 2)
+            sepconv_filtergrad_chunk<scb::XC, false>(s_img, v, hz, o2, o3, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc,
+                                            F - xc, g, c0 == 0 && xc == 0, c0 == 0);
+        else if (xc < F)
+            sepconv_filtergrad_chunk<scb::XC / 2, false>(s_img, v, hz, o2, o3, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc,
                                             F - xc, g, c0 == 0 && xc == 0, c0 == 0);
     }
 }
@@ -365,13 +368,12 @@ sepconv_backward_image_kernel(const float *__restrict__ in2, const float *__rest
 // warps own distinct rows as long as they work on the same r, which the barrier per row guarantees.  The region is
 // then added to gradinput1 with one atomic per element: ~9 tiles overlap on an image pixel, against the reference's
 // F*F atomics per channel and pixel (:122-123).  gradinput1 is zeroed by the launcher.
-template <bool FULL>
+template <int XC, bool FULL>
 __device__ __forceinline__ void sepconv_imagegrad_chunk(float *__restrict__ s_acc, const float *__restrict__ v,
                                                         const float *__restrict__ hz, const size_t (&po)[4],
                                                         const bool (&valid)[4], size_t HWo, int F, int RH, int pitch,
                                                         int row0, int col0, int xc, int nk, const float (&g)[4][3])
 {
-    constexpr int XC = sct::XC;
     float h[4][XC];
 #pragma unroll
     for (int q = 0; q < 4; ++q)
@@ -458,9 +460,11 @@ sepconv_backward_image_tiled_kernel(const float *__restrict__ in2, const float *
 
         int xc = 0;
         for (; xc + XC <= F; xc += XC)
-            sepconv_imagegrad_chunk<true>(s_acc, v, hz, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, XC, g);
-        if (xc < F)
-            sepconv_imagegrad_chunk<false>(s_acc, v, hz, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, F - xc, g);
+            sepconv_imagegrad_chunk<XC, true>(s_acc, v, hz, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, XC, g);
+        if (F - xc > XC / 2)
+            sepconv_imagegrad_chunk<XC, false>(s_acc, v, hz, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, F - xc, g);
+        else if (xc < F)
+            sepconv_imagegrad_chunk<XC / 2, false>(s_acc, v, hz, po, valid, HWo, F, RH, pitch, 2 * ty, 2 * lane, xc, F - xc, g);
         __syncthreads();
         for (int row = ty; row < nc * RH; row += NT / 32) {
             const int cc = row / RH, gy = h0 + row - cc * RH;
