@@ -148,6 +148,9 @@ int vfidkr_interpolation_backward(const float *input1, const float *input2, cons
  * input1 [B,C,H,W]; input2 (vertical) / input3 (horizontal) [B,F,H-F+1,W-F+1].
  * replaces separableconv_cuda.SeparableConvLayer_gpu_forward / _gpu_backward
  * (separableconv_cuda.cc:10-176, C == 3 enforced at :21; kernels separableconv_cuda_kernel.cu:29-135)
+ * backward: every element of the three gradients is written; gradinput1 is cleared on the stream by the library
+ * and summed with atomics (about 9 per element for filter sizes that use the shared-memory tiled kernels), so its
+ * low bits depend on the order of arrival, as the reference's do (F*F atomics per element there).
  */
 int vfidkr_separableconv_forward(const float *input1, const float *input2, const float *input3, float *output,
                                  int B, int C, int H, int W, int filter_size, vfidkr_stream_t stream);
