@@ -657,7 +657,10 @@ def op_table(torch, V, device, path):
     fls = torch.empty(Bs, 2, Hos, Wos, device=device)
     add("SeparableConvFlow_fwd_F51_B8_206x398", timeit(lambda: _lib.call("vfidkr_separableconvflow_forward", ptr(vs), ptr(hs), ptr(fls),
                                                                           Bs, Hos, Wos, Fs, sp), iters=20), 4 * (2 * Fs + 2), pxs)
-    del Is, vs, hs, os_, gs, g1s, g2s, g3s, fls
+    gfl = torch.randn(Bs, 2, Hos, Wos, device=device)
+    add("SeparableConvFlow_bwd_F51_B8_206x398", timeit(lambda: _lib.call("vfidkr_separableconvflow_backward", ptr(vs), ptr(hs), ptr(gfl),
+                                                                          ptr(g2s), ptr(g3s), Bs, Hos, Wos, Fs, sp), iters=20), 4 * (4 * Fs + 2), pxs)
+    del Is, vs, hs, os_, gs, g1s, g2s, g3s, fls, gfl
     with open(path, "w") as f:
         for r in rows:
             f.write(json.dumps(r) + "\n")

@@ -514,27 +514,36 @@ sepconvflow_backward_kernel(const float *__restrict__ in2, const float *__restri
                             const float *__restrict__ gflow, float *__restrict__ gi2, float *__restrict__ gi3,
                             size_t HWo, size_t total, int F)
 {
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t b = idx / HWo, po = idx - b * HWo;
+    // one thread per (pixel, flow channel); the grid covers the map exactly
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int ch = blockIdx.y;
+    const size_t b = idx / HWo, po = idx - b * HWo;
+    const float *src = (ch == 0 ? in3 : in2) + b * F * HWo + po;
+    float *dst = (ch == 0 ? gi3 : gi2) + b * F * HWo + po;
+    const float g = ld_stream(gflow + (b * 2 + ch) * HWo + po);
+    float num = 0.f, den = 0.f;
+    int k = 0;
+    for (; k + 8 <= F; k += 8) {
+        float t[8];
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            const float *src = (ch == 0 ? in3 : in2) + b * F * HWo + po;
-            float *dst = (ch == 0 ? gi3 : gi2) + b * F * HWo + po;
-            float num = 0.f, den = 0.f;
-            for (int k = 0; k < F; ++k) {
-                const float t = __ldg(src + (size_t)k * HWo);
-                num += (float)k * t;
-                den += t;
-            }
-            if (fabsf(den) > 0.0f) {
-                const float g = ld_stream(gflow + (b * 2 + ch) * HWo + po);
-                const float offset = num / (den * den);   // :138
-                for (int k = 0; k < F; ++k) st_stream(dst + (size_t)k * HWo, g * ((float)k / den - offset));   // :140-143
-            } else {
-                for (int k = 0; k < F; ++k) st_stream(dst + (size_t)k * HWo, 0.0f);
-            }
+        for (int j = 0; j < 8; ++j) t[j] = ld_stream(src + (size_t)(k + j) * HWo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            num += (float)(k + j) * t[j];
+            den += t[j];
         }
+    }
+    for (; k < F; ++k) {
+        const float t = ld_stream(src + (size_t)k * HWo);
+        num += (float)k * t;
+        den += t;
+    }
+    if (fabsf(den) > 0.0f) {
+        const float offset = num / (den * den);   // :138
+        for (int k2 = 0; k2 < F; ++k2) st_stream(dst + (size_t)k2 * HWo, g * ((float)k2 / den - offset));   // :140-143
+    } else {
+        for (int k2 = 0; k2 < F; ++k2) st_stream(dst + (size_t)k2 * HWo, 0.0f);
     }
 }
 
@@ -618,8 +627,8 @@ VFIDKR_API int vfidkr_separableconvflow_backward(const float *input2, const floa
     if (B <= 0 || Ho <= 0 || Wo <= 0 || F <= 0) return VFIDKR_ERR_ARG;
     if (!input2 || !input3 || !gradflow_output || !gradinput2 || !gradinput3) return VFIDKR_ERR_ARG;
     const size_t HWo = (size_t)Ho * Wo, total = (size_t)B * HWo;
-    const unsigned nb = (unsigned)min((size_t)sm_count() * 8, (total + 255) / 256);
-    sepconvflow_backward_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(input2, input3, gradflow_output, gradinput2, gradinput3, HWo, total, F);
+    if ((total + 255) / 256 > 0x7fffffffull) return VFIDKR_ERR_ARG;
+    sepconvflow_backward_kernel<<<dim3((unsigned)((total + 255) / 256), 2), 256, 0, (cudaStream_t)stream>>>(input2, input3, gradflow_output, gradinput2, gradinput3, HWo, total, F);
     note_launch();
     return check_launch("separableconvflow backward");
 }
