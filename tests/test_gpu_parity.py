@@ -600,7 +600,7 @@ def test_fi_ori_many_channel_kernel(lib, oracle, monkeypatch, B, C, H, W, fk):
     assert U.max_err(host(a), host(b).astype(np.float64)) < 2e-6
 
 
-# ------------------------------------------------------------------------------ BASELINE configs 3 and 5 at full size
+# ------------------------------------------------------------------------------ BASELINE configs 2, 3 and 5 at full size
 def test_config3_training_step_dkr_and_projections_batch16(lib, oracle):
     """BASELINE config 3 beyond the "_ori" warp: fwd+bwd of the 4-input DKR warp, FlowProjection (fillhole = 0)
     and DepthFlowProjection at B = 16, 256x448, against the oracle; upstream gradient = the output."""
@@ -629,6 +629,46 @@ def test_config3_training_step_dkr_and_projections_batch16(lib, oracle):
         U.assert_close(host(tf.grad), gi1, U.RTOL_ATOMIC, "projection gradinput1")
         if depth is not None:
             U.assert_close(host(td.grad), gi2, U.RTOL_ATOMIC, "projection gradinput2 (depth)")
+
+
+def test_config2_forward_chain_256x448(lib, oracle):
+    """BASELINE config 2 (one forward at the Vimeo-90K shape, 256x448, batch 1) restricted to the path: the operators
+    of one forward pass in network order -- PWC correlations at the five pyramid levels in both directions
+    (PWCNet.py:72), the flow warp between levels (PWCNet.py:159-199), depth-aware projection of both flows with hole
+    filling (networks/DAIN.py:306-330, inference), adaptive warping of both frames by the PROJECTED flows, in the "_ori"
+    and the deformable-kernel-region form (DAIN.py:536-573), and the blend.  The convolutions between them are out of
+    scope, so features, depths, filters and offsets are synthetic; every stage is checked against the oracle run on the
+    same upstream tensors the GPU stage consumed."""
+    r = U.rng(1002)
+    B, H, W = 1, 256, 448
+    corr = lib.Correlation(4, 1, 4, 1, 1, 1)
+    for C, s in ((196, 64), (128, 32), (96, 16), (64, 8), (32, 4)):
+        a, b = U.image(r, B, C, H // s, W // s, "normal"), U.image(r, B, C, H // s, W // s, "normal")
+        for x, y in ((a, b), (b, a)):
+            U.assert_close(host(corr(cu(x), cu(y))), oracle.correlation_forward(x, y, 4, 1, 4, 1, 1), U.RTOL_FWD, f"correlation C={C}")
+    feat, flo = U.image(r, B, 32, H // 4, W // 4, "normal"), (U.flow(r, B, H // 4, W // 4, "gauss") * 0.25).astype(np.float32)
+    U.assert_close(host(lib.pwc_warp(cu(feat), cu(flo))), oracle.pwc_warp_forward(feat, flo), U.RTOL_FWD, "PWC warp")
+
+    frames = [U.image(r, B, 3, H, W) for _ in range(2)]
+    flows = [(0.5 * U.flow(r, B, H, W, "gauss")).astype(np.float32) for _ in range(2)]   # time step 0.5
+    depths = [U.depth_inv(r, B, H, W) for _ in range(2)]
+    filts = [U.filt(r, B, 4, H, W) for _ in range(2)]
+    offs = [U.offsets(r, B, 4, H, W, 0.45) for _ in range(2)]
+    proj = []
+    for fl, d in zip(flows, depths):
+        p = lib.DepthFlowProjectionModule(False)(cu(fl), cu(d))      # requires_grad = False: holes are filled
+        ref, _ = oracle.flowprojection_forward(fl, d, 1)
+        U.assert_close(host(p), ref, U.RTOL_ATOMIC, "depth-aware projection with hole filling")
+        proj.append(p)
+    warped = []
+    for I, p, ft, off in zip(frames, proj, filts, offs):
+        w = lib.FilterInterpolationModule()(cu(I), p, cu(ft))
+        U.assert_close(host(w), oracle.fi_forward("ori", I, host(p), ft), U.RTOL_FWD, "adaptive warp by the projected flow")
+        wd = lib.FilterInterpolationModule("dkr")(cu(I), p, cu(ft), cu(off))
+        U.assert_close(host(wd), oracle.fi_forward("dkr", I, host(p), ft, off), U.RTOL_FWD, "DKR warp by the projected flow")
+        warped.append(w)
+    out = lib.filter_interpolate_blend(cu(frames[0]), cu(frames[1]), proj[0], proj[1], cu(filts[0]), cu(filts[1]))
+    U.assert_close(host(out), 0.5 * host(warped[0]).astype(np.float64) + 0.5 * host(warped[1]).astype(np.float64), U.RTOL_FWD, "blended frame")
 
 
 def test_config5_4k_pair_properties(lib, oracle, monkeypatch):
