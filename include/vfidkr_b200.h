@@ -11,9 +11,21 @@
  *   - All tensors are float32, NCHW, contiguous (the reference asserts is_contiguous() in
  *     Python, e.g. FilterInterpolationLayer.py:16-18, and checks W-stride == 1 in C++,
  *     filterinterpolation_cuda.cc:579-581).
- *   - The caller owns every buffer; the library never allocates and never synchronises.
- *     Work is enqueued on `stream` (the reference uses at::cuda::getCurrentCUDAStream(),
- *     filterinterpolation_cuda.cc:590).
+ *   - float32 ONLY.  The reference dispatches float and double (AT_DISPATCH_FLOATING_TYPES in
+ *     every launcher, e.g. filterinterpolation_cuda_kernel.cu:3155) and half in the correlation
+ *     (correlation_cuda_kernel.cu:386), although every intermediate in its kernels is `float`;
+ *     VFIDKR itself only ever passes float32.  The Python front-end raises TypeError on any
+ *     other dtype instead of converting silently.
+ *   - The caller owns every INPUT and OUTPUT buffer and the library never synchronises; work is
+ *     enqueued on `stream` (the reference uses at::cuda::getCurrentCUDAStream(),
+ *     filterinterpolation_cuda.cc:590).  Some entry points need device SCRATCH memory (the
+ *     projections' splat image, the correlation's split-K partial volumes and row-padded
+ *     copies, the strip kernels' work queue): it is taken from a library-private, stream-ordered
+ *     memory pool (cudaMallocFromPoolAsync on `stream`, freed on `stream` before the call
+ *     returns) -- the counterpart of the rbot1/rbot2 scratch tensors the reference's
+ *     correlation resizes inside C++ (correlation_cuda.cc:34-40).  The pool keeps at most
+ *     VFIDKR_SCRATCH_RETAIN_MB (default 1024) MiB cached between calls; vfidkr_trim_scratch()
+ *     returns everything to the device.  The process-wide default pool is not touched.
  *   - Unlike the reference, outputs need NOT be zero-filled by the caller: every element
  *     of every output/gradient buffer is written (accumulation targets are cleared on the
  *     stream by the library itself).
@@ -47,6 +59,13 @@ int vfidkr_abi_version(void);
 unsigned long long vfidkr_launch_count(void);
 /* Text of the last CUDA error seen by the calling thread ("" if none). */
 const char *vfidkr_last_error(void);
+/* TEST HOOK (no reference counterpart): force the implementation of the FilterInterpolation forwards --
+ * 0 = automatic (production), 1 = strip kernels, 2 = tile kernel, 3 = direct kernels -- so that the parity tests
+ * can hold every implementation to the oracle.  Process-wide; returns the previous setting, -1 on a bad value. */
+int vfidkr_debug_force_forward_path(int path);
+/* Return the scratch memory the library's private pool has cached on the current device to the device
+ * (see "Common contract"; blocks still in use by enqueued work are not affected).  No reference counterpart. */
+int vfidkr_trim_scratch(void);
 
 /* ---- FilterInterpolation: adaptive warping with per-pixel F x F filters ------------------
  * input1 [B,C,H,W] image/features   input2 [B,2,H,W] flow (x,y)   input3 [B,F*F,H,W] filter

@@ -5,11 +5,13 @@
  * file; it is the checker used by tests/, __graft_entry__.smoke() and bench.py's
  * cpu_baseline / --impl reference legs.
  *
- * PARITY STATUS: "parity unpinned by reference fixtures" -- the reference ships no golden
- * vectors, no known-answer tests and no CPU implementation for this path (SURVEY.md section 4,
- * section 8c), and its CUDA extensions cannot be imported or built unmodified in this image.
- * The restatement is therefore pinned by (i) the known-answer identities of SURVEY.md section 8c
- * (tests/test_oracle_kat.py) and (ii) finite-difference gradient checks of the float64 forward.
+ * PARITY STATUS: PINNED against the reference itself.  The reference ships no golden vectors, no
+ * known-answer tests and no CPU implementation for this path, but its CUDA
+ * extensions compile unmodified for sm_100a (oracle/build_ref.py -> oracle/_ref/*.so); their outputs on
+ * the seeded cases of tests/golden_cases.py are committed as tests/golden/*.npz (oracle/make_golden.py)
+ * and tests/test_golden.py::test_oracle_reproduces_reference_kernels holds this file to them.  On top:
+ * the known-answer identities of SURVEY.md section 8c (tests/test_oracle_kat.py) and finite-difference
+ * gradient checks of the float64 forward.
  *
  * Conventions:
  *   - every input is float32, NCHW, contiguous -- the same bytes the GPU sees;

@@ -42,3 +42,12 @@ def lib():
     B.build_library()
     import vfidkr_b200
     return vfidkr_b200
+
+
+@pytest.fixture(autouse=True)
+def _forward_path_is_automatic_again():
+    """A test that pins a FilterInterpolation forward implementation must not leak the setting into the next one."""
+    yield
+    mod = sys.modules.get("vfidkr_b200")
+    if mod is not None and getattr(mod._lib, "_lib", None) is not None:
+        mod.debug_force_forward_path(None)

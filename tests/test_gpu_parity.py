@@ -390,9 +390,9 @@ def test_fi_ori_tma_and_direct_paths_agree(lib, oracle, monkeypatch):
     r = U.rng(1900)
     for (B, C, H, W) in [(2, 3, 37, 132), (1, 3, 256, 448), (3, 5, 9, 68), (1, 196, 8, 64)]:
         I, fl, ft = U.image(r, B, C, H, W), U.flow(r, B, H, W, "stress"), U.filt(r, B, 4, H, W)
-        monkeypatch.setenv("VFIDKR_FORCE_DIRECT", "1")
+        lib.debug_force_forward_path("direct")
         a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
-        monkeypatch.setenv("VFIDKR_FORCE_DIRECT", "0")
+        lib.debug_force_forward_path(None)
         b = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
         # same arithmetic, slightly different FMA grouping: agree to fp32 rounding, and each with the oracle
         assert U.max_err(host(a), host(b).astype(np.float64)) < 2e-6, (B, C, H, W)
@@ -455,11 +455,11 @@ def test_fi_ori_strip_kernel(lib, oracle, monkeypatch, B, C, H, W, fk):
     I = U.image(r, B, C, H, W)
     fl = big_flow(r, B, H, W, fk) if fk in ("uniform_motion", "shear", "wild", "jump_back") else U.flow(r, B, H, W, fk)
     ft = U.filt(r, B, 4, H, W, "uniform")
-    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "strip")
+    lib.debug_force_forward_path("strip")
     a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
-    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    lib.debug_force_forward_path("direct")
     b = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
-    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    lib.debug_force_forward_path(None)
     ref = oracle.fi_forward("ori", I, fl, ft)
     U.assert_close(host(a), ref, U.RTOL_FWD, f"strip kernel vs oracle ({fk})")
     U.assert_close(host(b), ref, U.RTOL_FWD, f"direct kernel vs oracle ({fk})")
@@ -503,9 +503,9 @@ def test_fi_dkr_strip_kernel(lib, oracle, monkeypatch, variant, B, C, H, W, fk, 
     args = (I, fl, off) if variant == "nofilterwithdeforconv" else (I, fl, ft, off)
     run = lambda: lib.FilterInterpolationModule(variant)(*map(cu, args))
     a = run()
-    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    lib.debug_force_forward_path("direct")
     b = run()
-    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    lib.debug_force_forward_path(None)
     ref = oracle.fi_forward(variant, *args)
     # an offset of exactly +-amp can land a sample on a pixel boundary where the two paths round the fraction
     # identically (same fp32 index arithmetic), so both must match the oracle at the forward tolerance
@@ -534,9 +534,9 @@ def test_fi_strip_window_is_not_reused_across_work_items(lib, monkeypatch, varia
     off = (torch.rand(B, 32, H, W, device="cuda", generator=g) - 0.5) * 0.9
     args = (I, fl, ft) if variant == "ori" else (I, fl, ft, off)
     mod = lib.FilterInterpolationModule() if variant == "ori" else lib.FilterInterpolationModule(variant)
-    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    lib.debug_force_forward_path("direct")
     ref = mod(*args)
-    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    lib.debug_force_forward_path(None)
     for _ in range(4):   # the item-to-CTA assignment is dynamic: several draws
         out = mod(*args)
         assert (out - ref).abs().max().item() < 3e-6
@@ -591,9 +591,9 @@ def test_fi_ori_many_channel_kernel(lib, oracle, monkeypatch, B, C, H, W, fk):
     fl = big_flow(r, B, H, W, fk) if fk in ("uniform_motion", "shear", "wild", "jump_back") else U.flow(r, B, H, W, fk)
     ft = U.filt(r, B, 4, H, W, "uniform")
     a = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
-    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    lib.debug_force_forward_path("direct")
     b = lib.FilterInterpolationModule()(cu(I), cu(fl), cu(ft))
-    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    lib.debug_force_forward_path(None)
     ref = oracle.fi_forward("ori", I, fl, ft)
     U.assert_close(host(a), ref, U.RTOL_FWD, f"many-channel kernel vs oracle ({fk})")
     U.assert_close(host(b), ref, U.RTOL_FWD, f"direct kernel vs oracle ({fk})")
@@ -681,9 +681,9 @@ def test_config5_4k_pair_properties(lib, oracle, monkeypatch):
     fl = torch.nn.functional.interpolate(lo, scale_factor=8, mode="bilinear", align_corners=False).contiguous()
     ft = torch.softmax(torch.randn(B, 16, H, W, device="cuda", generator=g), 1)
     out = lib.FilterInterpolationModule()(I, fl, ft)
-    monkeypatch.setenv("VFIDKR_FI_FWD_PATH", "direct")
+    lib.debug_force_forward_path("direct")
     ref = lib.FilterInterpolationModule()(I, fl, ft)
-    monkeypatch.delenv("VFIDKR_FI_FWD_PATH")
+    lib.debug_force_forward_path(None)
     assert (out - ref).abs().max().item() < 3e-6
     assert out.min().item() >= -1e-6 and out.max().item() <= 1 + 1e-6        # convex filter, convex blend
     # oracle on the first 64 rows: a pixel's window may reach below the band, so only rows whose windows stay inside count

@@ -41,18 +41,23 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu(lib):
 
 
 def test_reference_import_lines_resolve_to_this_package(lib):
-    names = lib.install_reference_aliases(overwrite=True)
-    assert "my_package.FilterInterpolation" in names
-    from my_package.FilterInterpolation import FilterInterpolationModule          # networks/DAIN.py:11
-    from my_package.FlowProjection import FlowProjectionModule                    # networks/DAIN.py:12
-    from my_package.DepthFlowProjection import DepthFlowProjectionModule          # networks/DAIN.py:13
-    from PWCNet.correlation_package_pytorch1_0.correlation import Correlation     # PWCNet/PWCNet.py:15
-    assert FilterInterpolationModule is lib.FilterInterpolationModule
-    assert FlowProjectionModule is lib.FlowProjectionModule
-    assert DepthFlowProjectionModule is lib.DepthFlowProjectionModule
-    assert Correlation is lib.Correlation
-    for k in [k for k in sys.modules if k == "my_package" or k.startswith("my_package.") or k.startswith("PWCNet")]:
-        del sys.modules[k]
+    """The four operator import lines of the reference's networks (more in tests/test_dropin_network.py, which
+    imports the reference's real networks through the aliases)."""
+    names = lib.install_reference_aliases()
+    try:
+        assert "my_package.FilterInterpolation" in names
+        from my_package.FilterInterpolation import FilterInterpolationModule          # networks/DAIN.py:11
+        from my_package.FlowProjection import FlowProjectionModule                    # networks/DAIN.py:12
+        from my_package.DepthFlowProjection import DepthFlowProjectionModule          # networks/DAIN.py:13
+        from PWCNet.correlation_package_pytorch1_0.correlation import Correlation     # PWCNet/PWCNet.py:15
+        assert FilterInterpolationModule is lib.FilterInterpolationModule
+        assert FlowProjectionModule is lib.FlowProjectionModule
+        assert DepthFlowProjectionModule is lib.DepthFlowProjectionModule
+        assert Correlation is lib.Correlation
+    finally:
+        lib.compat.remove_reference_aliases()
+        for k in [k for k in sys.modules if k.startswith("PWCNet")]:
+            del sys.modules[k]
 
 
 def test_module_signatures_match_the_reference(lib):

@@ -19,7 +19,7 @@ flows = {
 }
 
 def run(path, fl, img=I):
-    os.environ["VFIDKR_FI_FWD_PATH"] = path
+    V.debug_force_forward_path(path)
     return fi(img, fl, ft)
 
 for name, fl in flows.items():

@@ -15,7 +15,9 @@ def check_input(t: torch.Tensor, name: str) -> None:
         raise RuntimeError(f"{name} must be a CUDA tensor: vfidkr_b200 has no CPU fallback")
     if t.dtype != torch.float32:
         raise TypeError(f"{name} must be float32 (got {t.dtype})")
-    assert t.is_contiguous(), f"{name} must be contiguous"
+    if not t.is_contiguous():
+        # the reference asserts; an assert disappears under `python -O`, and the C ABI takes dense NCHW pointers
+        raise ValueError(f"{name} must be contiguous (dense NCHW): call .contiguous() first")
 
 
 def ptr(t) -> c_void_p:

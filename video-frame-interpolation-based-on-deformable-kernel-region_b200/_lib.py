@@ -57,6 +57,8 @@ _SIGNATURES = {
     "vfidkr_correlation_forward": [_P] * 3 + [_I] * 10 + [_P],
     "vfidkr_correlation_backward": [_P] * 5 + [_I] * 10 + [_P],
     "vfidkr_abi_version": [],
+    "vfidkr_trim_scratch": [],
+    "vfidkr_debug_force_forward_path": [_I],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vfidkr_launch_count", "vfidkr_last_error"])
 
@@ -93,6 +95,22 @@ def call(name: str, *args) -> None:
     if err != VFIDKR_OK:
         detail = lib.vfidkr_last_error().decode(errors="replace") if err == VFIDKR_ERR_CUDA else "argument rejected"
         raise VfidkrError(f"{name} failed with status {err}: {detail}")
+
+
+_PATHS = {None: 0, "auto": 0, "strip": 1, "tile": 2, "direct": 3}
+
+
+def debug_force_forward_path(path) -> int:
+    """TEST HOOK: pin the FilterInterpolation forward implementation (None/"auto", "strip", "tile", "direct")."""
+    prev = load().vfidkr_debug_force_forward_path(_PATHS[path])
+    if prev < 0:
+        raise VfidkrError("vfidkr_debug_force_forward_path rejected the value")
+    return prev
+
+
+def trim_scratch() -> None:
+    """Give the scratch memory cached by the library's private pool back to the device."""
+    call("vfidkr_trim_scratch")
 
 
 def launch_count() -> int:

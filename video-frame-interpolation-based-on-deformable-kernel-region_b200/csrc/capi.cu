@@ -1,7 +1,11 @@
 // capi.cu -- library info entry points and shared host helpers
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
 
 #include "common.cuh"
 #include "tma.cuh"
@@ -33,6 +37,70 @@ int sm_count()
         cached[dev] = n;
     }
     return cached[dev];
+}
+
+// ---- environment switches, read once ------------------------------------------------------------------------
+const char *env_once(const char *name)
+{
+    static std::mutex mu;
+    static std::map<std::string, std::string> seen;     // value, or "\x01" for "unset"
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = seen.find(name);
+    if (it == seen.end()) {
+        const char *v = std::getenv(name);
+        it = seen.emplace(name, v ? std::string(v) : std::string("\x01")).first;
+    }
+    return it->second == "\x01" ? nullptr : it->second.c_str();
+}
+
+// ---- library-private stream-ordered scratch pool -------------------------------------------------------------
+// One cudaMemPool_t per device, created on first use.  Blocks freed with cudaFreeAsync stay cached in the pool up to
+// the release threshold (VFIDKR_SCRATCH_RETAIN_MB, default 1024 MiB; the same few sizes come back every step), the
+// rest goes back to the device at the next synchronisation point.  The process-wide default pool (and with it the
+// host framework's own view of free memory) is not reconfigured.
+static constexpr int MAX_DEVICES = 64;
+static cudaMemPool_t g_pool[MAX_DEVICES];
+static std::atomic<int> g_pool_state[MAX_DEVICES];    // 0 = none, 1 = ready, -1 = creation failed (use the default pool)
+static std::mutex g_pool_mu;
+
+static cudaMemPool_t scratch_pool(int dev)
+{
+    if (dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    int st = g_pool_state[dev].load(std::memory_order_acquire);
+    if (st == 0) {
+        std::lock_guard<std::mutex> lock(g_pool_mu);
+        st = g_pool_state[dev].load(std::memory_order_relaxed);
+        if (st == 0) {
+            cudaMemPoolProps props;
+            memset(&props, 0, sizeof props);
+            props.allocType = cudaMemAllocationTypePinned;
+            props.handleTypes = cudaMemHandleTypeNone;
+            props.location.type = cudaMemLocationTypeDevice;
+            props.location.id = dev;
+            cudaMemPool_t pool = nullptr;
+            if (cudaMemPoolCreate(&pool, &props) == cudaSuccess) {
+                unsigned long long keep = 1024ull << 20;
+                if (const char *v = env_once("VFIDKR_SCRATCH_RETAIN_MB")) keep = strtoull(v, nullptr, 10) << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+                g_pool[dev] = pool;
+                st = 1;
+            } else {
+                st = -1;
+            }
+            (void)cudaGetLastError();
+            g_pool_state[dev].store(st, std::memory_order_release);
+        }
+    }
+    return st == 1 ? g_pool[dev] : nullptr;
+}
+
+int stream_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+    if (cudaMemPool_t pool = scratch_pool(dev))
+        return set_error(cudaMallocFromPoolAsync(p, bytes, pool, s), "scratch (cudaMallocFromPoolAsync)");
+    return set_error(cudaMallocAsync(p, bytes, s), "scratch (cudaMallocAsync)");
 }
 
 // ---- TMA tensor-map encoding through the driver entry point (no link-time dependency on libcuda) ----
@@ -124,3 +192,10 @@ VFIDKR_API unsigned long long vfidkr_launch_count(void)
     return vfidkr::g_launches.load(std::memory_order_relaxed);
 }
 VFIDKR_API const char *vfidkr_last_error(void) { return vfidkr::t_error; }
+VFIDKR_API int vfidkr_trim_scratch(void)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= vfidkr::MAX_DEVICES) return VFIDKR_ERR_CUDA;
+    if (vfidkr::g_pool_state[dev].load(std::memory_order_acquire) != 1) return VFIDKR_OK;
+    return vfidkr::set_error(cudaMemPoolTrimTo(vfidkr::g_pool[dev], 0), "trim scratch pool");
+}

@@ -15,8 +15,11 @@ void note_launch(int n = 1);              // relaxed launch counter (capi.cu)
 int  check_launch(const char *what);      // cudaGetLastError -> VFIDKR_OK / VFIDKR_ERR_CUDA
 int  set_error(cudaError_t e, const char *what);
 int  sm_count();                          // cached multiprocessor count of the current device
-// stream-ordered scratch memory from the device's default pool (projection.cu): no synchronisation, cached by the pool
+// stream-ordered scratch memory from a library-private pool (capi.cu): no synchronisation, cached by the pool up to
+// VFIDKR_SCRATCH_RETAIN_MB; release with cudaFreeAsync on the same stream.  The device's default pool is left alone.
 int  stream_scratch_alloc(void **p, size_t bytes, cudaStream_t s);
+// environment switch read once per process (test hooks must not cost a getenv per launch)
+const char *env_once(const char *name);
 
 static inline unsigned ceil_div(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

@@ -479,7 +479,10 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
     const int nseg = choose_segments(B, tiles_x, tiles_y, sms), segt = (tiles_y + nseg - 1) / nseg;
     const long long items = (long long)B * tiles_x * nseg;
     auto kernel = fi_forward_ori_strip_kernel<CG>;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<CG>());
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<CG>()) != cudaSuccess) {
+        (void)cudaGetLastError();   // smaller shared-memory carve-out (MIG, ...): let the caller run the generic kernels
+        return -1;
+    }
     const int nblk = (int)std::min<long long>(sms, items);
     void *counter = nullptr;   // the global work counter: 4 bytes of stream-ordered scratch, zeroed on the stream
     int e = stream_scratch_alloc(&counter, sizeof(int), s);

@@ -424,7 +424,10 @@ static int launch_dkr(const float *in1, const float *in2, const float *filt, con
     const int nseg = choose_segments(B, tiles_x, tiles_y, sms), segt = (tiles_y + nseg - 1) / nseg;
     const long long items = (long long)B * tiles_x * nseg;
     auto kernel = fi_forward_dkr_strip_kernel<V, CG>;
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkr_smem_bytes<CG>());
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dkr_smem_bytes<CG>()) != cudaSuccess) {
+        (void)cudaGetLastError();   // let the caller run the per-pixel kernels
+        return -1;
+    }
     const int nblk = (int)std::min<long long>(sms, items);
     kernel<<<nblk, NTHREADS, dkr_smem_bytes<CG>(), s>>>(mfilt, moff, mimg, in1, in2, out, H, W, tiles_x, tiles_y, nseg, segt,
                                                        (int)items, FastDiv((unsigned)tiles_x), FastDiv((unsigned)nseg));

@@ -22,6 +22,7 @@
 #include "tma.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdlib>
 
 namespace vfidkr {
@@ -39,19 +40,21 @@ constexpr int BX = 32, BY = 8;  // thread block = 32 x 8 output pixels
 
 // The "_ori" forward has three implementations: strip (rolling shared-memory window, fi_strip.cu), tile
 // (TMA-streamed taps, gathers through L1) and direct.  The launcher picks the first that applies.  The tests
-// check that all of them agree by forcing one with VFIDKR_FI_FWD_PATH=strip|tile|direct (VFIDKR_FORCE_DIRECT=1
-// is the older spelling of "direct"); never needed in production.
+// check that all of them agree by forcing one through vfidkr_debug_force_forward_path() (a process-wide test
+// hook: one relaxed atomic load per launch).  The environment variable VFIDKR_FI_FWD_PATH=strip|tile|direct
+// sets its initial value and is read ONCE, at the first launch; never needed in production.
 enum { PATH_AUTO = 0, PATH_STRIP, PATH_TILE, PATH_DIRECT };
+std::atomic<int> g_forced_path{-1};   // -1: environment not consulted yet
 inline int forced_forward_path()
 {
-    const char *d = std::getenv("VFIDKR_FORCE_DIRECT");
-    if (d && d[0] == '1') return PATH_DIRECT;
-    const char *e = std::getenv("VFIDKR_FI_FWD_PATH");
-    if (!e) return PATH_AUTO;
-    if (e[0] == 's') return PATH_STRIP;
-    if (e[0] == 't') return PATH_TILE;
-    if (e[0] == 'd') return PATH_DIRECT;
-    return PATH_AUTO;
+    int v = g_forced_path.load(std::memory_order_relaxed);
+    if (v >= 0) return v;
+    v = PATH_AUTO;
+    if (const char *e = env_once("VFIDKR_FI_FWD_PATH"))
+        v = e[0] == 's' ? PATH_STRIP : e[0] == 't' ? PATH_TILE : e[0] == 'd' ? PATH_DIRECT : PATH_AUTO;
+    int expected = -1;
+    g_forced_path.compare_exchange_strong(expected, v, std::memory_order_relaxed);
+    return g_forced_path.load(std::memory_order_relaxed);
 }
 
 // resident blocks per SM the register allocator must leave room for
@@ -598,6 +601,13 @@ int launch_backward(const float *in1, const float *in2, const float *in3, const 
 }  // namespace vfidkr
 
 using namespace vfidkr;
+
+VFIDKR_API int vfidkr_debug_force_forward_path(int path)
+{
+    if (path < PATH_AUTO || path > PATH_DIRECT) return -1;
+    (void)forced_forward_path();      // consult the environment first, so that it cannot override this call later
+    return g_forced_path.exchange(path, std::memory_order_relaxed);
+}
 
 VFIDKR_API int vfidkr_filterinterpolation_forward_ori(const float *i1, const float *i2, const float *i3, float *out,
                                                       int B, int C, int H, int W, int F, vfidkr_stream_t s)

@@ -11,7 +11,7 @@
 //     spreads it -- same sums, 1 atomic instead of 12, which is what bounds this op (the L2 retires roughly
 //     one RED request per clock per slice, whatever its width);
 //   * the scratch image (16 B per pixel) is stream-ordered memory from the device's default pool
-//     (cudaMallocAsync: no synchronisation, cached after the first call);
+//     (library-private stream-ordered pool, capi.cu: no synchronisation, cached after the first call);
 //   * the accumulation planes are cleared by the library on the stream (no caller zero-fill);
 //   * the backward is a pure gather with register accumulation and a single store per output
 //     (the reference does eight / sixteen read-modify-writes of its own pixel).
@@ -437,23 +437,6 @@ mindepth_backward_kernel(const float *__restrict__ flow, const float *__restrict
 }
 
 }  // namespace
-
-// stream-ordered scratch from the device's default memory pool; the pool keeps the block cached between calls
-int stream_scratch_alloc(void **p, size_t bytes, cudaStream_t s)
-{
-    static thread_local int configured_for = -1;
-    int dev = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && dev != configured_for) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;   // never trim: the same few sizes come back every step
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        (void)cudaGetLastError();
-        configured_for = dev;
-    }
-    return set_error(cudaMallocAsync(p, bytes, s), "scratch (cudaMallocAsync)");
-}
 
 namespace {
 
