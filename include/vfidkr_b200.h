@@ -228,15 +228,17 @@ int vfidkr_mindepthflowprojection_backward(const float *input1, const float *inp
                                            const float *gradoutput, float *gradinput1, float *gradinput2,
                                            int B, int H, int W, vfidkr_stream_t stream);
 
-/* ---- PWCDCNet.warp (PWCNet/PWCNet.py:159-199): grid + flow, grid_sample (bilinear, zero padding, default
- * align_corners = False on an align_corners = True style normalisation -- the reference's quirk, kept) and the validity
- * mask (grid_sample of ones, thresholded at 0.9999), output = sample * mask.  Not a native symbol of the reference: it
- * replaces two grid_sample launches and five elementwise kernels of PyTorch code.  x [B,C,H,W], flow [B,2,H,W].
+/* ---- PWCDCNet.warp (PWCNet/PWCNet.py:159-199): grid + flow, normalised with 2 v / max(size - 1, 1) - 1 (:178-179),
+ * grid_sample (bilinear, zero padding) and the validity mask (grid_sample of ones, thresholded at 0.9999),
+ * output = sample * mask.  align_corners != 0: grid_sample as in the reference's pinned torch 1.0.1
+ * (environment.yaml:88,104), ix = x + fx -- the exact warp; align_corners == 0: what the same source line computes on
+ * torch >= 1.3 (ix = (x + fx) W / (W - 1) - 0.5).  Not a native symbol of the reference: it replaces two grid_sample
+ * launches and five elementwise kernels of PyTorch code.  x [B,C,H,W], flow [B,2,H,W].
  * The backward returns d/dx (scattered, cleared by the library) and d/dflow; the mask carries no gradient. ---- */
 int vfidkr_pwcwarp_forward(const float *x, const float *flow, float *output, int B, int C, int H, int W,
-                           vfidkr_stream_t stream);
+                           int align_corners, vfidkr_stream_t stream);
 int vfidkr_pwcwarp_backward(const float *x, const float *flow, const float *gradoutput, float *gradx, float *gradflow,
-                            int B, int C, int H, int W, vfidkr_stream_t stream);
+                            int B, int C, int H, int W, int align_corners, vfidkr_stream_t stream);
 
 /* ---- frame I/O boundary of the demo drivers (demo_MiddleBury.py:276-364; not native in the reference: numpy + torch
  * ReplicationPad2d there).  frames: uint8 [B,H,W,3] (HWC) on the device.  padded: float32 [B,3,Hp,Wp] with

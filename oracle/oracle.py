@@ -207,12 +207,14 @@ def correlation_backward(input1, input2, gradoutput, pad=4, k=1, md=4, s1=1, s2=
 
 # ---------------------------------------------------------------------------------------------------------------
 # PWCDCNet.warp (PWCNet/PWCNet.py:159-199).  The sampling itself is torch.nn.functional.grid_sample, a third-party
-# dependency of the reference (pinned at torch 1.4 in environment.yaml; default mode bilinear / zeros / align_corners =
-# False).  Its published algorithm (aten/src/ATen/native/GridSampler.h, cuda/GridSampler.cu) is restated here in numpy:
+# dependency of the reference, pinned at torch 1.0.1 (environment.yaml:88 `pytorch=1.0.1`, :104 `torch==1.0.1.post2`):
+# bilinear / zeros and -- there being no align_corners argument before torch 1.3 -- the align_corners=True rule
+# ix = ((nx + 1) / 2) * (W - 1).  Its published algorithm (aten/src/ATen/native/GridSampler.h, cuda/GridSampler.cu) is
+# restated here in numpy, both unnormalisation rules (align_corners=False is what the same line computes on torch >= 1.3):
 # coordinate arithmetic in float32 in the reference's operation order, value accumulation in float64.
-# Pinned against torch's own CPU grid_sample in tests/test_oracle_kat.py.
+# Pinned against torch's own CPU grid_sample, both modes, in tests/test_oracle_kat.py.
 # ---------------------------------------------------------------------------------------------------------------
-def _pwc_geometry(flo, H, W):
+def _pwc_geometry(flo, H, W, align_corners=True):
     f32 = np.float32
     xs = np.arange(W, dtype=f32)[None, None, :]
     ys = np.arange(H, dtype=f32)[None, :, None]
@@ -220,8 +222,12 @@ def _pwc_geometry(flo, H, W):
     vy = (ys + flo[:, 1]).astype(f32)
     nx = ((f32(2.0) * vx).astype(f32) / f32(max(W - 1, 1))).astype(f32) - f32(1.0)       # PWCNet.py:178
     ny = ((f32(2.0) * vy).astype(f32) / f32(max(H - 1, 1))).astype(f32) - f32(1.0)       # :179
-    ix = ((((nx + f32(1.0)).astype(f32) * f32(W)).astype(f32) - f32(1.0)).astype(f32) / f32(2.0)).astype(f32)
-    iy = ((((ny + f32(1.0)).astype(f32) * f32(H)).astype(f32) - f32(1.0)).astype(f32) / f32(2.0)).astype(f32)
+    if align_corners:
+        ix = (((nx + f32(1.0)).astype(f32) / f32(2.0)).astype(f32) * f32(W - 1)).astype(f32)
+        iy = (((ny + f32(1.0)).astype(f32) / f32(2.0)).astype(f32) * f32(H - 1)).astype(f32)
+    else:
+        ix = ((((nx + f32(1.0)).astype(f32) * f32(W)).astype(f32) - f32(1.0)).astype(f32) / f32(2.0)).astype(f32)
+        iy = ((((ny + f32(1.0)).astype(f32) * f32(H)).astype(f32) - f32(1.0)).astype(f32) / f32(2.0)).astype(f32)
     x0f, y0f = np.floor(ix), np.floor(iy)
     x1f, y1f = (x0f + f32(1.0)).astype(f32), (y0f + f32(1.0)).astype(f32)
     wts = [((x1f - ix).astype(f32) * (y1f - iy).astype(f32)).astype(f32), ((ix - x0f).astype(f32) * (y1f - iy).astype(f32)).astype(f32),
@@ -238,10 +244,10 @@ def _pwc_geometry(flo, H, W):
     return corners, inb, [w_.astype(np.float64) for w_ in wts], mask, tx, ty
 
 
-def pwc_warp_forward(x, flo):
+def pwc_warp_forward(x, flo, align_corners=True):
     x, flo = _f32(x), _f32(flo)
     B, C, H, W = x.shape
-    corners, inb, wts, mask, _, _ = _pwc_geometry(flo, H, W)
+    corners, inb, wts, mask, _, _ = _pwc_geometry(flo, H, W, align_corners)
     out = np.zeros((B, C, H, W), np.float64)
     bi = np.arange(B)[:, None, None]
     for (cy, cx), ok, w_ in zip(corners, inb, wts):
@@ -251,10 +257,10 @@ def pwc_warp_forward(x, flo):
     return out * mask[:, None]
 
 
-def pwc_warp_backward(x, flo, gradoutput):
+def pwc_warp_backward(x, flo, gradoutput, align_corners=True):
     x, flo, g = _f32(x), _f32(flo), _f32(gradoutput).astype(np.float64)
     B, C, H, W = x.shape
-    corners, inb, wts, mask, tx, ty = _pwc_geometry(flo, H, W)
+    corners, inb, wts, mask, tx, ty = _pwc_geometry(flo, H, W, align_corners)
     gm = g * mask[:, None]
     gx = np.zeros((B, C, H, W), np.float64)
     bi = np.broadcast_to(np.arange(B)[:, None, None], (B, H, W))
@@ -269,7 +275,8 @@ def pwc_warp_backward(x, flo, gradoutput):
     v0, v1, v2, v3 = vals
     gix = (gm * ((v1 - v0) * (1 - ty)[:, None] + (v3 - v2) * ty[:, None])).sum(1)
     giy = (gm * ((v2 - v0) * (1 - tx)[:, None] + (v3 - v1) * tx[:, None])).sum(1)
-    gflo = np.stack([gix * (W / max(W - 1, 1)), giy * (H / max(H - 1, 1))], 1)
+    sx, sy = ((W - 1), (H - 1)) if align_corners else (W, H)
+    gflo = np.stack([gix * (sx / max(W - 1, 1)), giy * (sy / max(H - 1, 1))], 1)
     return gx, gflo
 
 

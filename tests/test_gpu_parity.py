@@ -780,8 +780,9 @@ def test_fi_blend_writes_into_a_channel_slice(lib):
 
 
 # ------------------------------------------------------------------------------ PWCDCNet.warp
+@pytest.mark.parametrize("ac", [True, False])
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 64, 112), (1, 128, 18, 31), (3, 5, 17, 23), (1, 2, 1, 9), (1, 196, 8, 14)])
-def test_pwc_warp(lib, oracle, B, C, H, W):
+def test_pwc_warp(lib, oracle, B, C, H, W, ac):
     """pwc_warp (PWCNet/PWCNet.py:159-199: grid + flow, grid_sample with the reference's normalisation quirk, validity
     mask) forward and backward against the numpy restatement, and against PyTorch's own grid_sample on the GPU."""
     r = U.rng(3200 + H + W)
@@ -790,11 +791,11 @@ def test_pwc_warp(lib, oracle, B, C, H, W):
     flo[:, :, 0, 0] = 0.0
     flo[:, 0, -1, -1] = 3.0 * W
     tx, tf = cu(x).requires_grad_(), cu(flo).requires_grad_()
-    out = lib.pwc_warp(tx, tf)
-    U.assert_close(host(out), oracle.pwc_warp_forward(x, flo), U.RTOL_FWD, "pwc warp forward")
+    out = lib.pwc_warp(tx, tf, align_corners=ac)
+    U.assert_close(host(out), oracle.pwc_warp_forward(x, flo, ac), U.RTOL_FWD, "pwc warp forward")
     g = r.standard_normal((B, C, H, W)).astype(np.float32)
     out.backward(cu(g))
-    gx, gf = oracle.pwc_warp_backward(x, flo, g)
+    gx, gf = oracle.pwc_warp_backward(x, flo, g, ac)
     U.assert_close(host(tx.grad), gx, U.RTOL_ATOMIC, "pwc warp grad x")
     U.assert_close(host(tf.grad), gf, U.RTOL_ATOMIC, "pwc warp grad flow")
     # the reference's own code path on the same device
@@ -803,8 +804,8 @@ def test_pwc_warp(lib, oracle, B, C, H, W):
         yy = torch.arange(H, device="cuda").view(1, 1, H, 1).expand(B, 1, H, W)
         vg = torch.cat((xx, yy), 1).float() + cu(flo)
         vg = torch.stack([2.0 * vg[:, 0] / max(W - 1, 1) - 1.0, 2.0 * vg[:, 1] / max(H - 1, 1) - 1.0], 1).permute(0, 2, 3, 1)
-        o = torch.nn.functional.grid_sample(cu(x), vg, align_corners=False)
-        m = torch.nn.functional.grid_sample(torch.ones_like(o), vg, align_corners=False)
+        o = torch.nn.functional.grid_sample(cu(x), vg, align_corners=ac)
+        m = torch.nn.functional.grid_sample(torch.ones_like(o), vg, align_corners=ac)
         m[m < 0.9999] = 0
         m[m > 0] = 1
         assert (out.detach() - o * m).abs().max().item() <= 1e-5 * max(1.0, float(np.abs(x).max()))

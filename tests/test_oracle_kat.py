@@ -380,8 +380,9 @@ def test_correlation_gradients_match_finite_differences(oracle, pad, k, md, s1, 
 
 
 # ------------------------------------------------------------------------------ PWCDCNet.warp
-def _reference_pwc_warp(x, flo):
-    """PWCNet/PWCNet.py:159-199 as written (without the pre-allocated grid and .cuda()), on CPU tensors."""
+def _reference_pwc_warp(x, flo, align_corners):
+    """PWCNet/PWCNet.py:159-199 as written (without the pre-allocated grid and .cuda()), on CPU tensors.
+    align_corners=True is grid_sample of the reference's pinned torch 1.0.1, False the default since torch 1.3."""
     import torch
     B, C, H, W = x.size()
     xx = torch.arange(0, W).view(1, -1).repeat(H, 1).view(1, 1, H, W).repeat(B, 1, 1, 1)
@@ -389,14 +390,15 @@ def _reference_pwc_warp(x, flo):
     vgrid = torch.cat((xx, yy), 1).to(x.dtype) + flo
     vgrid = torch.stack([2.0 * vgrid[:, 0] / max(W - 1, 1) - 1.0, 2.0 * vgrid[:, 1] / max(H - 1, 1) - 1.0], 1)
     vgrid = vgrid.permute(0, 2, 3, 1)
-    output = torch.nn.functional.grid_sample(x, vgrid, align_corners=False)     # the default since torch 1.3
-    mask = torch.nn.functional.grid_sample(torch.ones_like(x), vgrid, align_corners=False).detach().clone()
+    output = torch.nn.functional.grid_sample(x, vgrid, align_corners=align_corners)
+    mask = torch.nn.functional.grid_sample(torch.ones_like(x), vgrid, align_corners=align_corners).detach().clone()
     mask[mask < 0.9999] = 0
     mask[mask > 0] = 1
     return output * mask
 
 
-def test_pwc_warp_oracle_is_pinned_to_torch_grid_sample(oracle):
+@pytest.mark.parametrize("ac", [True, False])
+def test_pwc_warp_oracle_is_pinned_to_torch_grid_sample(oracle, ac):
     """The numpy restatement of PWCDCNet.warp against the reference's own code path run on torch's CPU grid_sample
     (float32 for the values the reference computes, float64 autograd for the gradients)."""
     import torch
@@ -406,8 +408,8 @@ def test_pwc_warp_oracle_is_pinned_to_torch_grid_sample(oracle):
         flo = (r.standard_normal((B, 2, H, W)) * 3).astype(np.float32)
         flo[:, :, 0, 0] = 0.0                      # exact-integer landing
         flo[:, 0, -1, -1] = 50.0                   # far outside
-        ref = _reference_pwc_warp(torch.from_numpy(x), torch.from_numpy(flo)).numpy()
-        got = oracle.pwc_warp_forward(x, flo)
+        ref = _reference_pwc_warp(torch.from_numpy(x), torch.from_numpy(flo), ac).numpy()
+        got = oracle.pwc_warp_forward(x, flo, ac)
         assert np.abs(got - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
         # gradients: float64 torch autograd on float32-representable inputs (away from knife edges the index
         # arithmetic agrees between float32 and float64)
@@ -415,15 +417,33 @@ def test_pwc_warp_oracle_is_pinned_to_torch_grid_sample(oracle):
         tx = torch.from_numpy(x).double().requires_grad_()
         tf = torch.from_numpy(flo_s).double().requires_grad_()
         g = r.standard_normal((B, C, H, W))
-        _reference_pwc_warp(tx, tf).backward(torch.from_numpy(g))
+        _reference_pwc_warp(tx, tf, ac).backward(torch.from_numpy(g))
         # the oracle's float32 geometry must select the same corners: skip shapes where W - 1 makes 1/8-pixel offsets inexact
-        gx, gf = oracle.pwc_warp_backward(x, flo_s, g.astype(np.float32))
+        gx, gf = oracle.pwc_warp_backward(x, flo_s, g.astype(np.float32), ac)
         g32 = g.astype(np.float32).astype(np.float64)
         tx2 = torch.from_numpy(x).double().requires_grad_()
         tf2 = torch.from_numpy(flo_s).double().requires_grad_()
-        _reference_pwc_warp(tx2, tf2).backward(torch.from_numpy(g32))
+        _reference_pwc_warp(tx2, tf2, ac).backward(torch.from_numpy(g32))
         assert np.abs(gx - tx2.grad.numpy()).max() <= 1e-4 * max(1.0, np.abs(gx).max())
         assert np.abs(gf - tf2.grad.numpy()).max() <= 1e-4 * max(1.0, np.abs(gf).max())
+
+
+def test_pwc_warp_with_the_pinned_torch_rule_is_an_exact_warp(oracle):
+    """torch 1.0.1's grid_sample (align_corners=True) on the reference's normalisation samples exactly at x + flow:
+    zero flow is the identity with a full mask, an integer flow is a pure shift (the ADVICE finding of round 1: the
+    align_corners=False rule instead shifts by up to half a pixel and masks row 0 / column 0 at zero flow)."""
+    r = U.rng(3150)
+    x = r.standard_normal((1, 3, 9, 17)).astype(np.float32)
+    z = np.zeros((1, 2, 9, 17), np.float32)
+    assert np.abs(oracle.pwc_warp_forward(x, z, True) - x).max() <= 1e-5
+    modern = oracle.pwc_warp_forward(x, z, False)
+    assert not modern[:, :, 0, :].any() and not modern[:, :, :, 0].any()          # the masked border of the modern rule
+    f = z.copy()
+    f[:, 0] = 2.0
+    f[:, 1] = -1.0
+    out = oracle.pwc_warp_forward(x, f, True)
+    assert np.abs(out[:, :, 1:, :-2] - x[:, :, :-1, 2:]).max() <= 1e-5
+    assert not out[:, :, 0, :].any() and not out[:, :, :, -2:].any()              # sampled outside the plane
 
 
 def test_mindepth_oracle_known_answers(oracle):

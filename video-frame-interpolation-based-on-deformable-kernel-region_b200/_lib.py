@@ -41,8 +41,8 @@ _SIGNATURES = {
     "vfidkr_frame_padding": [_I, ctypes.POINTER(_I)],
     "vfidkr_frames_u8_to_padded_f32": [_P, _P, _I, _I, _I, _P],
     "vfidkr_padded_f32_to_frames_u8": [_P, _P, _I, _I, _I, _P],
-    "vfidkr_pwcwarp_forward": [_P] * 3 + [_I] * 4 + [_P],
-    "vfidkr_pwcwarp_backward": [_P] * 5 + [_I] * 4 + [_P],
+    "vfidkr_pwcwarp_forward": [_P] * 3 + [_I] * 5 + [_P],
+    "vfidkr_pwcwarp_backward": [_P] * 5 + [_I] * 5 + [_P],
     "vfidkr_flowprojection_forward": [_P] * 3 + [_I] * 4 + [_P],
     "vfidkr_flowprojection_backward": [_P] * 4 + [_I] * 3 + [_P],
     "vfidkr_depthflowprojection_forward": [_P] * 4 + [_I] * 4 + [_P],

@@ -2,12 +2,16 @@
 //
 // Behaviour follows PWCNet/PWCNet.py:159-199: vgrid = pixel grid + flow, normalised as
 //   nx = 2 * (x + fx) / max(W - 1, 1) - 1          (the align_corners = True style normalisation, :178-179)
-// and sampled with torch.nn.functional.grid_sample in its default mode (bilinear, zero padding, align_corners = False),
-// whose published algorithm (PyTorch, aten/src/ATen/native/GridSampler.h: grid_sampler_unnormalize, and
-// cuda/GridSampler.cu: grid_sampler_2d_kernel) is
-//   ix = ((nx + 1) * W - 1) / 2,  corners floor(ix), floor(ix) + 1,  weights (ix_se - ix) * (iy_se - iy) ...,
-//   a corner outside the plane contributes nothing.
-// The mismatch of the two conventions is the reference's and is kept: ix = (x + fx) * W / (W - 1) - 0.5.  The mask is
+// and sampled with torch.nn.functional.grid_sample (bilinear, zero padding), whose published algorithm (PyTorch,
+// aten/src/ATen/native/GridSampler.h: grid_sampler_unnormalize, and cuda/GridSampler.cu: grid_sampler_2d_kernel) is
+//   align_corners = True :  ix = ((nx + 1) / 2) * (W - 1)          = x + fx: an exact warp
+//   align_corners = False:  ix = ((nx + 1) * W - 1) / 2            = (x + fx) * W / (W - 1) - 0.5
+//   corners floor(ix), floor(ix) + 1,  weights (ix_se - ix) * (iy_se - iy) ...,  a corner outside the plane contributes nothing.
+// The reference's environment pins torch 1.0.1 (environment.yaml:88,104), whose grid_sample has no align_corners argument
+// and behaves as align_corners = True -- the exact warp the PWC-Net weights were trained with; `align_corners = 1` is
+// therefore the default of the Python front-end.  Run on torch >= 1.3 the same source line silently becomes
+// align_corners = False (features shifted by up to half a pixel, first row / column masked at zero flow);
+// `align_corners = 0` reproduces that, for callers who need today's behaviour of the unmodified file.  The mask is
 // the same sampling of an all-ones tensor, set to 0 below 0.9999 and to 1 otherwise (:193-194); output = sample * mask.
 // All coordinate arithmetic is float32 in the reference's operation order; the mask carries no gradient.
 // One thread per pixel computes the geometry once and loops over the channels (the reference runs two grid_sample
@@ -28,14 +32,18 @@ struct WarpGeom {
     float mask;                    // 0 or 1
 };
 
+template <bool AC>
 __device__ __forceinline__ WarpGeom warp_geom(int w_i, int h_i, float fx, float fy, int W, int H)
 {
     WarpGeom g;
     const float vx = __fadd_rn((float)w_i, fx), vy = __fadd_rn((float)h_i, fy);                        // :176
     const float nx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vx), (float)max(W - 1, 1)), 1.0f);           // :178
     const float ny = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, vy), (float)max(H - 1, 1)), 1.0f);           // :179
-    const float ix = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(nx, 1.0f), (float)W), 1.0f), 2.0f);      // grid_sampler_unnormalize
-    const float iy = __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(ny, 1.0f), (float)H), 1.0f), 2.0f);
+    // grid_sampler_unnormalize
+    const float ix = AC ? __fmul_rn(__fdiv_rn(__fadd_rn(nx, 1.0f), 2.0f), (float)(W - 1))
+                        : __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(nx, 1.0f), (float)W), 1.0f), 2.0f);
+    const float iy = AC ? __fmul_rn(__fdiv_rn(__fadd_rn(ny, 1.0f), 2.0f), (float)(H - 1))
+                        : __fdiv_rn(__fsub_rn(__fmul_rn(__fadd_rn(ny, 1.0f), (float)H), 1.0f), 2.0f);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
     // the saturating conversion keeps wild coordinates (and NaN -> 0 weights are NaN anyway) out of int overflow
     g.x0 = (int)fmaxf(fminf(fx0, 1e9f), -1e9f);
@@ -59,6 +67,7 @@ __device__ __forceinline__ WarpGeom warp_geom(int w_i, int h_i, float fx, float 
     return g;
 }
 
+template <bool AC>
 __global__ void __launch_bounds__(BX *BY, 6)
 pwcwarp_forward_kernel(const float *__restrict__ x, const float *__restrict__ flo, float *__restrict__ out, int C, int H, int W)
 {
@@ -68,7 +77,7 @@ pwcwarp_forward_kernel(const float *__restrict__ x, const float *__restrict__ fl
     const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
     const float fx = ld_stream(flo + ((size_t)b * 2 + 0) * HW + pix);
     const float fy = ld_stream(flo + ((size_t)b * 2 + 1) * HW + pix);
-    const WarpGeom g = warp_geom(w_i, h_i, fx, fy, W, H);
+    const WarpGeom g = warp_geom<AC>(w_i, h_i, fx, fy, W, H);
     const float *img = x + (size_t)b * C * HW;
     float *o = out + (size_t)b * C * HW + pix;
     const int a = g.y0 * W + g.x0;   // only dereferenced where the in_* flags allow
@@ -85,6 +94,7 @@ pwcwarp_forward_kernel(const float *__restrict__ x, const float *__restrict__ fl
 }
 
 // gx[corner] += gout * mask * weight;  gflo = (W / (W - 1)) * d(sample)/d(ix), (H / (H - 1)) * d(sample)/d(iy)
+template <bool AC>
 __global__ void __launch_bounds__(BX *BY, 3)
 pwcwarp_backward_kernel(const float *__restrict__ x, const float *__restrict__ flo, const float *__restrict__ gout,
                         float *__restrict__ gx, float *__restrict__ gflo, int C, int H, int W)
@@ -95,7 +105,7 @@ pwcwarp_backward_kernel(const float *__restrict__ x, const float *__restrict__ f
     const size_t HW = (size_t)H * W, pix = (size_t)h_i * W + w_i;
     const float fx = ld_stream(flo + ((size_t)b * 2 + 0) * HW + pix);
     const float fy = ld_stream(flo + ((size_t)b * 2 + 1) * HW + pix);
-    const WarpGeom g = warp_geom(w_i, h_i, fx, fy, W, H);
+    const WarpGeom g = warp_geom<AC>(w_i, h_i, fx, fy, W, H);
     float gix = 0.0f, giy = 0.0f;
     if (g.mask != 0.0f) {
         const float *img = x + (size_t)b * C * HW;
@@ -129,9 +139,9 @@ pwcwarp_backward_kernel(const float *__restrict__ x, const float *__restrict__ f
             }
         }
     }
-    // ix = (x + fx) * W / max(W - 1, 1) - 0.5
-    st_stream(gflo + ((size_t)b * 2 + 0) * HW + pix, gix * ((float)W / (float)max(W - 1, 1)));
-    st_stream(gflo + ((size_t)b * 2 + 1) * HW + pix, giy * ((float)H / (float)max(H - 1, 1)));
+    // d(ix)/d(fx): ix = (x + fx) * (W - 1) / max(W - 1, 1)  or  (x + fx) * W / max(W - 1, 1) - 0.5
+    st_stream(gflo + ((size_t)b * 2 + 0) * HW + pix, gix * ((float)(AC ? W - 1 : W) / (float)max(W - 1, 1)));
+    st_stream(gflo + ((size_t)b * 2 + 1) * HW + pix, giy * ((float)(AC ? H - 1 : H) / (float)max(H - 1, 1)));
 }
 
 }  // namespace
@@ -140,18 +150,19 @@ pwcwarp_backward_kernel(const float *__restrict__ x, const float *__restrict__ f
 using namespace vfidkr;
 
 VFIDKR_API int vfidkr_pwcwarp_forward(const float *x, const float *flow, float *output, int B, int C, int H, int W,
-                                      vfidkr_stream_t stream)
+                                      int align_corners, vfidkr_stream_t stream)
 {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || B > 65535 || !x || !flow || !output) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 30)) return VFIDKR_ERR_ARG;
     dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
-    pwcwarp_forward_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(x, flow, output, C, H, W);
+    if (align_corners) pwcwarp_forward_kernel<true><<<grid, block, 0, (cudaStream_t)stream>>>(x, flow, output, C, H, W);
+    else               pwcwarp_forward_kernel<false><<<grid, block, 0, (cudaStream_t)stream>>>(x, flow, output, C, H, W);
     note_launch();
     return check_launch("pwc warp forward");
 }
 
 VFIDKR_API int vfidkr_pwcwarp_backward(const float *x, const float *flow, const float *gradoutput, float *gradx,
-                                       float *gradflow, int B, int C, int H, int W, vfidkr_stream_t stream)
+                                       float *gradflow, int B, int C, int H, int W, int align_corners, vfidkr_stream_t stream)
 {
     if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || B > 65535 || !x || !flow || !gradoutput || !gradx || !gradflow) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 30)) return VFIDKR_ERR_ARG;
@@ -159,7 +170,8 @@ VFIDKR_API int vfidkr_pwcwarp_backward(const float *x, const float *flow, const 
     const int e = set_error(cudaMemsetAsync(gradx, 0, sizeof(float) * (size_t)B * C * H * W, s), "clear gradx");
     if (e) return e;
     dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
-    pwcwarp_backward_kernel<<<grid, block, 0, s>>>(x, flow, gradoutput, gradx, gradflow, C, H, W);
+    if (align_corners) pwcwarp_backward_kernel<true><<<grid, block, 0, s>>>(x, flow, gradoutput, gradx, gradflow, C, H, W);
+    else               pwcwarp_backward_kernel<false><<<grid, block, 0, s>>>(x, flow, gradoutput, gradx, gradflow, C, H, W);
     note_launch();
     return check_launch("pwc warp backward");
 }
