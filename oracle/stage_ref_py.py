@@ -21,7 +21,9 @@ OUT = HERE / "_ref" / "reference_py"
 
 # what `import networks` pulls in (networks/DAIN.py:1-21, networks/DAIN_slowmotion.py:1-13)
 TREES = ["networks", "S2D_models", "Resblock", "MegaDepth", "my_package"]   # my_package: its Python layers only
-FILES = ["Stack.py", "PWCNet/__init__.py", "PWCNet/PWCNet.py"]
+FILES = ["Stack.py", "PWCNet/__init__.py", "PWCNet/PWCNet.py",
+         # the reference's own correlation wrapper, imported by PWCNet/PWCNet.py:15 when the aliases are NOT installed (run A)
+         "PWCNet/correlation_package_pytorch1_0/__init__.py", "PWCNet/correlation_package_pytorch1_0/correlation.py"]
 
 
 def available() -> bool:

@@ -51,3 +51,16 @@ def _forward_path_is_automatic_again():
     mod = sys.modules.get("vfidkr_b200")
     if mod is not None and getattr(mod._lib, "_lib", None) is not None:
         mod.debug_force_forward_path(None)
+
+
+def pytest_terminal_summary(terminalreporter):
+    """Which comparisons needed the absolute floor of the per-element criterion (tests/util.py)."""
+    try:
+        import util as U
+    except Exception:
+        return
+    if U.NEEDS_FLOOR:
+        terminalreporter.write_line(f"[parity] {len(U.NEEDS_FLOOR)} comparisons hold |d| <= rtol*|ref| + floor only thanks to the "
+                                    "absolute floor (elements tiny against the tensor's scale); worst pure-relative factors:")
+        for k, v in sorted(U.NEEDS_FLOOR.items(), key=lambda kv: -kv[1])[:12]:
+            terminalreporter.write_line(f"[parity]   {k}: x{v:.1f}")
