@@ -133,14 +133,18 @@ projection_splat_kernel(const FlowSource fs, int b0, const float *__restrict__ d
 constexpr int FIN_ROWS = 8, FIN_WARPS = 4, FIN_UNROLL = 4;   // short segments: one frame per launch must still fill 148 SMs
 
 // raw loads of one row: this lane's cell and (lane 0 only) the cell left of the block
+// CG: the scratch image was written earlier in the SAME launch by other SMs (fused pipeline kernel below): read it
+// through L2 only (ld.global.cg) -- L1 and the read-only path are not coherent and may still hold the lines of the
+// frame that used this buffer before.
+template <bool CG = false>
 __device__ __forceinline__ void load_row(const float4 *__restrict__ Srow, int x, int W, int lane, bool valid,
                                          float4 &cur, float4 &edge)
 {
     cur = make_float4(0.f, 0.f, 0.f, 0.f);
     edge = cur;
     if (valid) {
-        if (x < W) cur = __ldcs(Srow + x);
-        if (lane == 0 && x > 0 && x < W) edge = __ldg(Srow + x - 1);
+        if (x < W) cur = CG ? __ldcg(Srow + x) : __ldcs(Srow + x);
+        if (lane == 0 && x > 0 && x < W) edge = CG ? __ldcg(Srow + x - 1) : __ldg(Srow + x - 1);
     }
 }
 // horizontal half of the box: wx(x,0) * S[x] + S[x-1]
@@ -208,44 +212,83 @@ projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count
 // here the walks run over the source bitmaps written by the box pass: a word covers 32 columns, a byte 8 rows, so a hole
 // n pixels wide costs n / 32 (n / 8) loads per direction instead of n, and the nearest source inside a word is a
 // clz / ffs.  Each scan returns the distance to the nearest source (0: none before the edge of the plane).
+template <bool CG, typename T>
+__device__ __forceinline__ unsigned ldm(const T *p) { return CG ? (unsigned)__ldcg(p) : (unsigned)__ldg(p); }
+template <bool CG = false>
 __device__ __forceinline__ int scan_left(const unsigned *__restrict__ rm, int x)
 {
     int wi = x >> 5;
-    unsigned m = __ldg(rm + wi) & ((1u << (x & 31)) - 1u);
+    unsigned m = ldm<CG>(rm + wi) & ((1u << (x & 31)) - 1u);
     for (;;) {
         if (m) return x - ((wi << 5) + 31 - __clz(m));
         if (--wi < 0) return 0;
-        m = __ldg(rm + wi);
+        m = ldm<CG>(rm + wi);
     }
 }
+template <bool CG = false>
 __device__ __forceinline__ int scan_right(const unsigned *__restrict__ rm, int x, int WW)
 {
     int wi = x >> 5;
-    unsigned m = __ldg(rm + wi) & ~((2u << (x & 31)) - 1u);   // bits above x (none when x & 31 == 31)
+    unsigned m = ldm<CG>(rm + wi) & ~((2u << (x & 31)) - 1u);   // bits above x (none when x & 31 == 31)
     for (;;) {
         if (m) return (wi << 5) + __ffs(m) - 1 - x;
         if (++wi >= WW) return 0;
-        m = __ldg(rm + wi);
+        m = ldm<CG>(rm + wi);
     }
 }
+template <bool CG = false>
 __device__ __forceinline__ int scan_up(const unsigned char *__restrict__ cm, int y, int W)
 {
     int bi = y >> 3;
-    unsigned m = __ldg(cm + (size_t)bi * W) & ((1u << (y & 7)) - 1u);
+    unsigned m = ldm<CG>(cm + (size_t)bi * W) & ((1u << (y & 7)) - 1u);
     for (;;) {
         if (m) return y - ((bi << 3) + 31 - __clz(m));
         if (--bi < 0) return 0;
-        m = __ldg(cm + (size_t)bi * W);
+        m = ldm<CG>(cm + (size_t)bi * W);
     }
 }
+template <bool CG = false>
 __device__ __forceinline__ int scan_down(const unsigned char *__restrict__ cm, int y, int W, int HB)
 {
     int bi = y >> 3;
-    unsigned m = __ldg(cm + (size_t)bi * W) & 0xffu & ~((2u << (y & 7)) - 1u);
+    unsigned m = ldm<CG>(cm + (size_t)bi * W) & 0xffu & ~((2u << (y & 7)) - 1u);
     for (;;) {
         if (m) return (bi << 3) + __ffs(m) - 1 - y;
         if (++bi >= HB) return 0;
-        m = __ldg(cm + (size_t)bi * W);
+        m = ldm<CG>(cm + (size_t)bi * W);
+    }
+}
+
+// One hole (:175-232): the nearest source pixel in each of the four axis directions, found on the bitmaps; the hole
+// becomes the mean of those that exist.  cnb / ob / rm / cm: count plane, the two output planes, row and column bitmaps of
+// ONE frame.  CG: everything was written earlier in the same launch by other SMs -> L2-coherent loads.
+template <bool CG>
+__device__ __forceinline__ void fill_one(const float *__restrict__ cnb, float *__restrict__ ob, const unsigned *__restrict__ rm,
+                                         const unsigned char *__restrict__ cm, int x, int y, int H, int W)
+{
+    auto ld = [](const float *p) { return CG ? __ldcg(p) : __ldg(p); };
+    const size_t HW = (size_t)H * W;
+    const int WW = (W + 31) >> 5, HB = (H + 7) >> 3;
+    const float *cn = cnb + (size_t)y * W + x;
+    const int dl = scan_left<CG>(rm + (size_t)y * WW, x);
+    const int dr = scan_right<CG>(rm + (size_t)y * WW, x, WW);
+    const int du = scan_up<CG>(cm + x, y, W);
+    const int dd = scan_down<CG>(cm + x, y, W, HB);
+    // the counts the reference's loops end on (0 when a scan ran off the plane)
+    const float lt = dl ? ld(cn - dl) : 0.0f, rt = dr ? ld(cn + dr) : 0.0f;
+    const float ut = du ? ld(cn - (long long)du * W) : 0.0f, dt = dd ? ld(cn + (long long)dd * W) : 0.0f;
+    if (lt + rt + ut + dt <= 0.0f) return;
+    const float l = lt > 0.0f ? 1.f : 0.f, r = rt > 0.0f ? 1.f : 0.f;
+    const float u = ut > 0.0f ? 1.f : 0.f, d = dt > 0.0f ? 1.f : 0.f;
+    const float den = l + r + u + d;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        float *o = ob + (size_t)ch * HW + (size_t)y * W + x;
+        // the sources are non-hole pixels, final since the averaging pass and never written here (plain loads in the
+        // three-kernel path: no read-only path for a buffer this kernel also writes)
+        const float v = CG ? l * __ldcg(o - dl) + r * __ldcg(o + dr) + u * __ldcg(o - (long long)du * W) + d * __ldcg(o + (long long)dd * W)
+                           : l * o[-dl] + r * o[dr] + u * o[-(long long)du * W] + d * o[(long long)dd * W];
+        *o = v / den;
     }
 }
 
@@ -278,26 +321,8 @@ projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ 
     const int n = s_n;
     for (int q = tid; q < n; q += BX * BY) {
         const int t = s_list[q];
-        const int x = blockIdx.x * BX + (t & (BX - 1)), y = blockIdx.y * BY + t / BX;
-        const float *cn = cnb + (size_t)y * W + x;
-        const int dl = scan_left(rowmask + ((size_t)b * H + y) * WW, x);
-        const int dr = scan_right(rowmask + ((size_t)b * H + y) * WW, x, WW);
-        const int du = scan_up(colmask + (size_t)b * HB * W + x, y, W);
-        const int dd = scan_down(colmask + (size_t)b * HB * W + x, y, W, HB);
-        // the counts the reference's loops end on (0 when a scan ran off the plane)
-        const float lt = dl ? __ldg(cn - dl) : 0.0f, rt = dr ? __ldg(cn + dr) : 0.0f;
-        const float ut = du ? __ldg(cn - (long long)du * W) : 0.0f, dt = dd ? __ldg(cn + (long long)dd * W) : 0.0f;
-        if (lt + rt + ut + dt <= 0.0f) continue;
-        const float l = lt > 0.0f ? 1.f : 0.f, r = rt > 0.0f ? 1.f : 0.f;
-        const float u = ut > 0.0f ? 1.f : 0.f, d = dt > 0.0f ? 1.f : 0.f;
-        const float den = l + r + u + d;
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            float *o = out + ((size_t)b * 2 + ch) * HW + (size_t)y * W + x;
-            // plain loads: the sources are non-hole pixels, final since the averaging pass and never written here
-            const float v = l * o[-dl] + r * o[dr] + u * o[-(long long)du * W] + d * o[(long long)dd * W];
-            *o = v / den;
-        }
+        fill_one<false>(cnb, out + (size_t)b * 2 * HW, rowmask + (size_t)b * H * WW, colmask + (size_t)b * HB * W,
+                        blockIdx.x * BX + (t & (BX - 1)), blockIdx.y * BY + t / BX, H, W);
     }
 }
 
