@@ -228,6 +228,68 @@ def test_flowprojection_count_is_bit_exact(lib, oracle):
     assert np.array_equal(host(count).astype(np.float64), cnt)
 
 
+PIPE_SHAPES = [(2, 37, 29, "stress"), (3, 97, 131, "stress"), (8, 256, 448, "gauss"), (5, 64, 200, "smooth"),
+               (2, 1, 1, "unit"), (4, 9, 33, "unit"), (7, 40, 96, "gauss")]
+
+
+@pytest.mark.parametrize("B,H,W,fk", PIPE_SHAPES)
+@pytest.mark.parametrize("with_depth", [False, True])
+def test_projection_pipeline_and_three_kernel_paths(lib, oracle, B, H, W, fk, with_depth):
+    """The fused pipeline kernel (splat workers and box-pass / hole-filling workers on different frames of the batch,
+    per-frame counters, three rotating scratch images) against the oracle and against the three-kernel path, with and
+    without hole filling: batches shorter and longer than the image rotation, ragged shapes, holes."""
+    from vfidkr_b200 import _lib
+    from vfidkr_b200._common import ptr, stream_ptr
+    r = U.rng(1350 + B + H)
+    fl = U.flow(r, B, H, W, fk)
+    d = U.depth_inv(r, B, H, W) if with_depth else None
+    tf, td = cu(fl), (cu(d) if with_depth else None)
+    sp = stream_ptr(tf.device)
+    res = {}
+    for path in ("kernels", "pipeline"):
+        lib.debug_force_projection_path(path)
+        for fill in (0, 1):
+            cnt, out = torch.full((B, 1, H, W), -7.0, device="cuda"), torch.full((B, 2, H, W), -7.0, device="cuda")
+            before = lib.launch_count()
+            if with_depth:
+                _lib.call("vfidkr_depthflowprojection_forward", ptr(tf), ptr(td), ptr(cnt), ptr(out), B, H, W, fill, sp)
+            else:
+                _lib.call("vfidkr_flowprojection_forward", ptr(tf), ptr(cnt), ptr(out), B, H, W, fill, sp)
+            torch.cuda.synchronize()
+            launches = lib.launch_count() - before
+            assert launches == (1 + fill if path == "pipeline" else 2 + fill), (path, launches)
+            res[path, fill] = (host(out), host(cnt))
+    lib.debug_force_projection_path(None)
+    for fill in (0, 1):
+        ref, rc = oracle.flowprojection_forward(fl, d, fill)
+        for path in ("kernels", "pipeline"):
+            out, cnt = res[path, fill]
+            U.assert_close(out, ref, U.RTOL_ATOMIC, f"projection {path} fillhole={fill}")
+            if with_depth:
+                U.assert_close(cnt, rc, U.RTOL_ATOMIC, f"projection {path} count fillhole={fill}")
+            else:
+                assert np.array_equal(cnt.astype(np.float64), rc), f"{path}: FlowProjection counts are exact integers"
+        # the two implementations add the same fp32 terms per cell, in hardware order: equal to rounding
+        assert U.max_err(res["pipeline", fill][0], res["kernels", fill][0].astype(np.float64)) <= 2e-6
+
+
+def test_projection_pipeline_is_repeatable_back_to_back(lib):
+    """Back-to-back launches on one stream reuse the cached scratch block (dirty images, stale counters): every launch
+    must clear what it needs itself."""
+    r = U.rng(1399)
+    B, H, W = 6, 120, 168
+    fl, d = cu(U.flow(r, B, H, W, "stress")), cu(U.depth_inv(r, B, H, W))
+    lib.debug_force_projection_path("pipeline")
+    mod = lib.DepthFlowProjectionModule(False)
+    first = mod(fl, d).clone()
+    for _ in range(5):
+        other = mod(cu(U.flow(r, B, H, W, "gauss")), d)      # different data through the same scratch
+        again = mod(fl, d)
+        assert torch.isfinite(other).all()
+        assert (again - first).abs().max().item() <= 2e-5 * first.abs().max().item()
+    lib.debug_force_projection_path(None)
+
+
 def test_projection_known_answers_on_gpu(lib):
     z = torch.zeros(1, 2, 6, 7, device="cuda")
     out = lib.FlowProjectionModule(False)(z)

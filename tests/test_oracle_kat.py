@@ -477,3 +477,34 @@ def test_mindepth_oracle_known_answers(oracle):
     g = np.ones((1, 2, H, W), np.float32)
     gi1, gi2 = oracle.mindepth_backward(flo, dep, cnt.astype(np.float32), g)
     assert gi1[0, 0, 0, 1] == -1.0 and gi1[0, 0, 0, 2] == 0.0 and not gi2.any()
+
+
+# ------------------------------------------------------------------------------ PyTorch-CPU fp32 baseline (bench.py leg)
+def test_torch_cpu_baseline_matches_the_oracle(oracle):
+    """oracle/torch_cpu.py -- the vectorised PyTorch-CPU fp32 path bench.py times as the second CPU baseline
+     -- computes what the float64 oracle computes (fp32 tolerance; atomically ordered sums 1e-4)."""
+    import torch
+    from oracle import torch_cpu as T
+    r = U.rng(3300)
+    B, C, H, W = 2, 3, 23, 37
+    I, ft = U.image(r, B, C, H, W), U.filt(r, B, 4, H, W)
+    for fk in ("gauss", "stress"):
+        fl = U.flow(r, B, H, W, fk)
+        got = T.fi_ori_forward(torch.from_numpy(I), torch.from_numpy(fl), torch.from_numpy(ft)).numpy()
+        U.assert_close(got, oracle.fi_forward("ori", I, fl, ft), 2e-5, f"torch-CPU FilterInterpolation ({fk})")
+        d = U.depth_inv(r, B, H, W)
+        for depth in (None, d):
+            for fill in (0, 1):
+                out, cnt = T.flowprojection_forward(torch.from_numpy(fl), None if depth is None else torch.from_numpy(depth), fill)
+                ref, rc = oracle.flowprojection_forward(fl, depth, fill)
+                U.assert_close(out.numpy(), ref, U.RTOL_ATOMIC, f"torch-CPU projection ({fk}, depth={depth is not None}, fill={fill})")
+                U.assert_close(cnt.numpy(), rc, U.RTOL_ATOMIC, "torch-CPU projection count")
+    # wide holes: constant shift leaves whole columns / rows empty
+    fl = np.zeros((1, 2, 9, 14), np.float32)
+    fl[:, 0] = 3.0
+    fl[:, 1, 4:] = -2.0
+    out, _ = T.flowprojection_forward(torch.from_numpy(fl), None, 1)
+    U.assert_close(out.numpy(), oracle.flowprojection_forward(fl, None, 1)[0], U.RTOL_ATOMIC, "torch-CPU hole filling")
+    f1, f2 = U.image(r, 2, 8, 12, 20, "normal"), U.image(r, 2, 8, 12, 20, "normal")
+    U.assert_close(T.correlation_forward(torch.from_numpy(f1), torch.from_numpy(f2)).numpy(),
+                   oracle.correlation_forward(f1, f2, 4, 1, 4, 1, 1), 2e-5, "torch-CPU correlation")

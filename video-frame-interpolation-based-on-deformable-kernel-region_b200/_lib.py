@@ -59,6 +59,7 @@ _SIGNATURES = {
     "vfidkr_abi_version": [],
     "vfidkr_trim_scratch": [],
     "vfidkr_debug_force_forward_path": [_I],
+    "vfidkr_debug_force_projection_path": [_I],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vfidkr_launch_count", "vfidkr_last_error"])
 
@@ -105,6 +106,14 @@ def debug_force_forward_path(path) -> int:
     prev = load().vfidkr_debug_force_forward_path(_PATHS[path])
     if prev < 0:
         raise VfidkrError("vfidkr_debug_force_forward_path rejected the value")
+    return prev
+
+
+def debug_force_projection_path(path) -> int:
+    """TEST HOOK: None/"auto", "kernels" (splat + box pass + hole filling launches) or "pipeline" (fused kernel)."""
+    prev = load().vfidkr_debug_force_projection_path({None: 0, "auto": 0, "kernels": 1, "pipeline": 2}[path])
+    if prev < 0:
+        raise VfidkrError("vfidkr_debug_force_projection_path rejected the value")
     return prev
 
 

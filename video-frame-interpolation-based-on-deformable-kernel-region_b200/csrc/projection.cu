@@ -16,6 +16,7 @@
 //   * the backward is a pure gather with register accumulation and a single store per output
 //     (the reference does eight / sixteen read-modify-writes of its own pixel).
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -326,6 +327,228 @@ projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused forward for batches: ONE persistent, cooperatively launched kernel pipelines the frames of the batch.
+//
+// The splat is bound by the rate at which L2 retires vector REDs, the box pass by L2 / DRAM bandwidth: different units,
+// so the two run CONCURRENTLY on different frames.  Half of the CTAs (one per SM) are splat workers, the other half
+// (one more per SM) are finish workers; each role walks the frames in order with a static share of the frame's tiles,
+// and the roles meet only through per-frame counters in global memory:
+//     splat(f)   needs the scratch image f % NB clean      (c_done[f - NB] == workers; the first NB images: see below)
+//     finish(f)  needs every splat worker done with f      (s_done[f] == workers)
+//     clear(f)   needs every finish worker done with f     (f_done[f] == workers) -- it is run one frame LATE, after
+//                finish(f + 1), when that condition has long been true: no worker ever waits at a barrier
+// so the splat workers run up to NB - 1 frames ahead and the RED unit never waits for a box pass.  NB = 3 scratch
+// images of 16 B per pixel rotate; at 1080p they and the streams around them live in the 126 MB L2, so the scratch
+// makes no DRAM round trip (the three-kernel path below moves 2.9x the algorithmic bytes).  Image 0 is cleared on the
+// stream before the launch, images 1 .. NB-1 by the finish workers while the first splat runs.
+// Holes are appended to ONE list for the batch by the box pass (one global atomic per 32 x 4 block that has any); a
+// second, small launch fills exactly those pixels.  (A first version filled the holes of frame f inside the pipeline,
+// behind a barrier of the finish workers: its chain of dependent L2 round trips -- barrier, bitmap scans, value loads --
+// cost 30-90 us PER FRAME with only one frame's holes in flight; measured 736 us against 421 us for three kernels.)
+// All cross-SM traffic inside the launch uses L2-coherent accesses (RED, ld.global.cg / st.global.cg): L1 is not
+// coherent and the images are reused.  The counters need every CTA resident: cudaLaunchCooperativeKernel guarantees it
+// (or fails -> three-kernel path).
+// ---------------------------------------------------------------------------------------------------------------
+namespace pipe {
+
+constexpr int NT = 512;            // threads per CTA, both roles
+constexpr int NB_MAX = 3;          // scratch images in rotation
+constexpr int SPLAT_UNROLL = 4;    // 32 x 16 pixel sub-tiles whose loads a splat worker keeps in flight
+constexpr int WARPS = NT / 32;
+
+struct FrameCtl { unsigned s_done, f_done, c_done, pad; };        // zeroed on the stream before the launch
+struct Ctl { unsigned pre_done, h_count, pad[2]; };                // images 1 .. NB-1 cleared; holes listed so far
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// every thread of the CTA calls these two
+__device__ __forceinline__ void cta_wait(const unsigned *flag, unsigned target)
+{
+    if (threadIdx.x == 0) {
+        unsigned ns = 32;
+        while (ld_acquire(flag) < target) { __nanosleep(ns); if (ns < 512) ns <<= 1; }
+        __threadfence();
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void cta_signal(unsigned *flag)
+{
+    __syncthreads();   // every thread's REDs / stores are issued ...
+    if (threadIdx.x == 0) { __threadfence(); atomicAdd(flag, 1u); }   // ... and ordered before the count (cumulative fence)
+}
+
+template <bool DEPTH>
+__device__ __forceinline__ void splat_frame(const FlowSource &fs, const float *__restrict__ depth_f, int frame,
+                                            float4 *__restrict__ S, int H, int W, int worker, int nworkers, const FastDiv div_tx)
+{
+    const int tiles_x = (W + 31) >> 5, ntiles = tiles_x * ((H + 15) >> 4);
+    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    for (int t0 = worker; t0 < ntiles; t0 += nworkers * SPLAT_UNROLL) {
+        float fx[SPLAT_UNROLL], fy[SPLAT_UNROLL], d[SPLAT_UNROLL];
+        int wi[SPLAT_UNROLL], hi[SPLAT_UNROLL];
+        bool ok[SPLAT_UNROLL];
+#pragma unroll
+        for (int k = 0; k < SPLAT_UNROLL; ++k) {   // every load of the group before the first RED
+            const int t = t0 + k * nworkers;
+            const int ty = div_tx.quot(min(t, ntiles - 1)), tx = min(t, ntiles - 1) - ty * tiles_x;
+            wi[k] = tx * 32 + lx; hi[k] = ty * 16 + ly;
+            ok[k] = t < ntiles && wi[k] < W && hi[k] < H;
+            fx[k] = fy[k] = 0.0f; d[k] = 1.0f;
+            if (ok[k]) {
+                load_flow(fs, frame, hi[k], wi[k], H, W, fx[k], fy[k]);
+                if (DEPTH) d[k] = ld_stream(depth_f + (size_t)hi[k] * W + wi[k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < SPLAT_UNROLL; ++k) {
+            if (!ok[k]) continue;
+            const Corners c = corners(wi[k], hi[k], fx[k], fy[k], W, H);
+            if (!c.in_range) continue;
+            const float vx = DEPTH ? -d[k] * fx[k] : -fx[k], vy = DEPTH ? -d[k] * fy[k] : -fy[k];
+            atomicAdd(S + (size_t)c.T * W + c.L, make_float4(vx, vy, d[k], 0.0f));   // REDG.F32x4
+        }
+    }
+}
+
+// box pass + averaging of one frame, the finish worker's share: warp items of 32 columns x 8 rows (the arithmetic of
+// projection_finish_kernel, same operation order).  With hole filling: bitmaps and the frame's hole list.
+__device__ __forceinline__ void finish_frame(const float4 *__restrict__ Sf, float *__restrict__ cn, float *__restrict__ ou,
+                                             unsigned *__restrict__ rowmask_f, unsigned char *__restrict__ colmask_f,
+                                             unsigned *__restrict__ hlist, unsigned *__restrict__ h_count, unsigned frame_base,
+                                             int H, int W, int gwarp, int nwarps, const FastDiv div_bw)
+{
+    const int lane = threadIdx.x & 31;
+    const int bw = (W + 31) >> 5, nitems = bw * ((H + FIN_ROWS - 1) / FIN_ROWS);
+    const size_t HW = (size_t)H * W;
+    float *ov = ou + HW;
+    for (int it = gwarp; it < nitems; it += nwarps) {
+        const int seg = div_bw.quot(it), x = (it - seg * bw) * 32 + lane;
+        const int y0 = seg * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
+        float4 c0, e0;
+        load_row<true>(Sf + (size_t)max(y0 - 1, 0) * W, x, W, lane, y0 > 0, c0, e0);
+        float4 prev = hsum_row(c0, e0, x, W, lane);
+        unsigned colbits = 0;
+#pragma unroll
+        for (int ybk = 0; ybk < FIN_ROWS; ybk += FIN_UNROLL) {
+            const int yb = y0 + ybk;
+            float4 cur[FIN_UNROLL], edge[FIN_UNROLL];
+            unsigned holes[FIN_UNROLL];
+#pragma unroll
+            for (int k = 0; k < FIN_UNROLL; ++k)
+                load_row<true>(Sf + (size_t)min(yb + k, H - 1) * W, x, W, lane, yb + k < y1, cur[k], edge[k]);
+#pragma unroll
+            for (int k = 0; k < FIN_UNROLL; ++k) {
+                const int y = yb + k;
+                const float4 h = hsum_row(cur[k], edge[k], x, W, lane);
+                const float w0 = (y == H - 1) ? 2.0f : 1.0f;
+                float su = w0 * h.x + prev.x, sv = w0 * h.y + prev.y;
+                const float sc = w0 * h.z + prev.z;
+                prev = h;
+                const bool live = y < y1 && x < W;
+                if (live) {
+                    if (sc > 0.0f) { su = su / sc; sv = sv / sc; }   // :130-134
+                    const size_t a = (size_t)y * W + x;
+                    __stcg(cn + a, sc); __stcg(ou + a, su); __stcg(ov + a, sv);
+                }
+                holes[k] = 0;
+                if (rowmask_f) {   // uniform
+                    const bool src = live && sc != 0.0f;
+                    const unsigned m = __ballot_sync(0xffffffffu, src);
+                    if (lane == 0 && y < y1) __stcg(rowmask_f + (size_t)y * bw + (x >> 5), m);
+                    colbits |= (src ? 1u : 0u) << (y - y0);
+                    holes[k] = __ballot_sync(0xffffffffu, live && !(sc > 0.0f));   // count <= 0 (:171)
+                }
+            }
+            if (rowmask_f) {   // the group's holes go to the frame's list: one global atomic per group that has any
+                unsigned total = 0;
+#pragma unroll
+                for (int k = 0; k < FIN_UNROLL; ++k) total += __popc(holes[k]);
+                if (total) {   // uniform
+                    unsigned base = 0;
+                    if (lane == 0) base = atomicAdd(h_count, total);
+                    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+                    for (int k = 0; k < FIN_UNROLL; ++k) {
+                        if (holes[k] >> lane & 1u)
+                            __stcg(hlist + base + __popc(holes[k] & ((1u << lane) - 1u)), frame_base + (unsigned)((yb + k) * W + x));
+                        base += __popc(holes[k]);
+                    }
+                }
+            }
+        }
+        if (rowmask_f && x < W) colmask_f[(size_t)seg * W + x] = (unsigned char)colbits;   // read after the frame's barrier (cg loads)
+    }
+}
+
+template <bool DEPTH>
+__global__ void __launch_bounds__(NT, 2)
+projection_pipeline_kernel(const FlowSource fs, const float *__restrict__ depth, float4 *__restrict__ S, int nbuf,
+                           float *__restrict__ count, float *__restrict__ out, unsigned *__restrict__ rowmask,
+                           unsigned char *__restrict__ colmask, unsigned *__restrict__ hlist, Ctl *__restrict__ ctl,
+                           FrameCtl *__restrict__ fctl, int B, int H, int W, const FastDiv div_tx, const FastDiv div_bw)
+{
+    const int workers = gridDim.x >> 1;
+    const bool splat_role = (int)blockIdx.x < workers;
+    const int worker = splat_role ? blockIdx.x : blockIdx.x - workers;
+    const size_t HW = (size_t)H * W;
+    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (splat_role) {
+        for (int f = 0; f < B; ++f) {
+            if (f >= nbuf) cta_wait(&fctl[f - nbuf].c_done, workers);
+            else if (f > 0) cta_wait(&ctl->pre_done, workers);
+            splat_frame<DEPTH>(fs, DEPTH ? depth + (size_t)f * HW : nullptr, f, S + (size_t)(f % nbuf) * HW, H, W, worker, workers, div_tx);
+            cta_signal(&fctl[f].s_done);
+        }
+        return;
+    }
+    // finish worker.  Prologue: scratch images 1 .. nbuf-1 (image 0 was cleared on the stream).
+    for (size_t i = HW + (size_t)worker * NT + threadIdx.x; i < (size_t)nbuf * HW; i += (size_t)workers * NT) __stcg(S + i, zero4);
+    cta_signal(&ctl->pre_done);
+    const int gwarp = worker * WARPS + (threadIdx.x >> 5), nwarps = workers * WARPS;
+    for (int f = 0; f < B; ++f) {
+        cta_wait(&fctl[f].s_done, workers);
+        finish_frame(S + (size_t)(f % nbuf) * HW, count + (size_t)f * HW, out + (size_t)f * 2 * HW,
+                     rowmask ? rowmask + (size_t)f * H * bw : nullptr, colmask ? colmask + (size_t)f * HB * W : nullptr,
+                     hlist, &ctl->h_count, (unsigned)((size_t)f * HW), H, W, gwarp, nwarps, div_bw);
+        cta_signal(&fctl[f].f_done);
+        // the image of the PREVIOUS frame goes back to the splat workers: every finish worker has long left it
+        const int fc = f - 1;
+        if (fc >= 0 && fc + nbuf < B) {
+            cta_wait(&fctl[fc].f_done, workers);
+            float4 *Sc = S + (size_t)(fc % nbuf) * HW;
+            for (size_t i = (size_t)worker * NT + threadIdx.x; i < HW; i += (size_t)workers * NT) __stcg(Sc + i, zero4);
+            cta_signal(&fctl[fc].c_done);
+        }
+    }
+}
+
+// Fills the holes the pipeline listed (entries: frame * H * W + pixel).  A separate launch: the bitmaps, counts and
+// outputs are final and the scans may use the read-only path.
+__global__ void __launch_bounds__(256)
+projection_fill_list_kernel(const float *__restrict__ count, float *__restrict__ out, const unsigned *__restrict__ rowmask,
+                            const unsigned char *__restrict__ colmask, const unsigned *__restrict__ hlist,
+                            const Ctl *__restrict__ ctl, int H, int W, const FastDiv div_w)
+{
+    const unsigned n = ctl->h_count;
+    const size_t HW = (size_t)H * W;
+    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3;
+    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
+        const unsigned p = __ldg(hlist + q);
+        const unsigned fr = p / (unsigned)HW, pix = p - fr * (unsigned)HW;     // one 32-bit division per hole
+        const int y = div_w.quot((int)pix), x = (int)pix - y * W;
+        fill_one<false>(count + (size_t)fr * HW, out + (size_t)fr * 2 * HW, rowmask + (size_t)fr * H * bw,
+                        colmask + (size_t)fr * HB * W, x, y, H, W);
+    }
+}
+
+}  // namespace pipe
+
 // backward gather (:266-297; depth :276-337)
 template <bool DEPTH>
 __global__ void __launch_bounds__(BX *BY)
@@ -465,6 +688,78 @@ mindepth_backward_kernel(const float *__restrict__ flow, const float *__restrict
 
 namespace {
 
+// ---- host side of the fused pipeline ------------------------------------------------------------------------
+std::atomic<int> g_projection_path{0};     // test hook: 0 = automatic, 1 = three-kernel path, 2 = fused pipeline
+inline int forced_projection_path() { return g_projection_path.load(std::memory_order_relaxed); }
+
+static int pipeline_grid(const void *kernel)
+{
+    int dev = 0, coop = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, pipe::NT, 0) != cudaSuccess || per_sm < 1) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    const int sms = sm_count();
+    return (per_sm >= 2 ? 2 * sms : sms) & ~1;      // one splat and one finish worker per SM when both fit
+}
+
+template <bool DEPTH>
+int projection_forward_pipelined(const FlowSource fs, const float *depth, float *count, float *out,
+                                 int B, int H, int W, int fillhole, cudaStream_t s)
+{
+    using namespace pipe;
+    auto kernel = projection_pipeline_kernel<DEPTH>;
+    const int grid = pipeline_grid((const void *)kernel);
+    const size_t HW = (size_t)H * W;
+    if (grid < 2 || (fillhole && (unsigned long long)B * HW >= (1ull << 32))) return -1;   // hole-list entries are 32-bit
+    const int nbuf = std::min(B, NB_MAX);
+    const size_t WW = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
+    // one stream-ordered block: [scratch images | row bitmaps | column bitmaps | hole list | counters]
+    const size_t s_bytes = sizeof(float4) * HW * nbuf;
+    const size_t rowmask_bytes = fillhole ? sizeof(unsigned) * B * H * WW : 0;
+    const size_t colmask_bytes = fillhole ? (((size_t)B * HB * W + 15) & ~(size_t)15) : 0;
+    const size_t hlist_bytes = fillhole ? sizeof(unsigned) * B * HW : 0;     // worst case: every pixel a hole
+    const size_t ctl_bytes = sizeof(Ctl) + sizeof(FrameCtl) * B;
+    void *mem = nullptr;
+    int e = stream_scratch_alloc(&mem, s_bytes + rowmask_bytes + colmask_bytes + hlist_bytes + ctl_bytes, s);
+    if (e) return e;
+    char *base = static_cast<char *>(mem);
+    float4 *S = reinterpret_cast<float4 *>(base);
+    unsigned *rowmask = fillhole ? reinterpret_cast<unsigned *>(base + s_bytes) : nullptr;
+    unsigned char *colmask = fillhole ? reinterpret_cast<unsigned char *>(base + s_bytes + rowmask_bytes) : nullptr;
+    unsigned *hlist = fillhole ? reinterpret_cast<unsigned *>(base + s_bytes + rowmask_bytes + colmask_bytes) : nullptr;
+    Ctl *ctl = reinterpret_cast<Ctl *>(base + s_bytes + rowmask_bytes + colmask_bytes + hlist_bytes);
+    FrameCtl *fctl = reinterpret_cast<FrameCtl *>(ctl + 1);
+    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * HW, s), "clear projection scratch image 0");
+    if (!e) e = set_error(cudaMemsetAsync(ctl, 0, ctl_bytes, s), "clear projection pipeline counters");
+    if (!e) {
+        FlowSource fsv = fs;
+        const float *depth_v = depth;
+        int nbuf_v = nbuf, Bv = B, Hv = H, Wv = W;
+        FastDiv div_tx((unsigned)((W + 31) >> 5)), div_bw((unsigned)((W + 31) >> 5));
+        void *args[] = {&fsv, &depth_v, &S, &nbuf_v, &count, &out, &rowmask, &colmask, &hlist, &ctl, &fctl, &Bv, &Hv, &Wv,
+                        &div_tx, &div_bw};
+        const cudaError_t le = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(NT), args, 0, s);
+        if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
+            (void)cudaGetLastError();
+            cudaFreeAsync(mem, s);
+            return -1;
+        }
+        e = set_error(le, "flow projection forward (pipelined)");
+        if (!e) { note_launch(); e = check_launch("flow projection forward (pipelined)"); }
+        if (!e && fillhole) {
+            // the list length lives on the device: a fixed grid strides over it
+            const unsigned nb = (unsigned)std::min<size_t>(((size_t)B * HW + 255) / 256, (size_t)sm_count() * 8);
+            projection_fill_list_kernel<<<nb, 256, 0, s>>>(count, out, rowmask, colmask, hlist, ctl, H, W, FastDiv((unsigned)W));
+            note_launch();
+            e = check_launch("flow projection hole filling (list)");
+        }
+    }
+    const int e2 = set_error(cudaFreeAsync(mem, s), "projection scratch (cudaFreeAsync)");
+    return e ? e : e2;
+}
+
 template <bool DEPTH>
 int projection_forward(const FlowSource fs, const float *depth, float *count, float *out,
                        int B, int H, int W, int fillhole, cudaStream_t s)
@@ -473,6 +768,10 @@ int projection_forward(const FlowSource fs, const float *depth, float *count, fl
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !flow || !count || !out || (DEPTH && !depth)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
+    if (B >= 2 && forced_projection_path() != 1) {
+        const int e = projection_forward_pipelined<DEPTH>(fs, depth, count, out, B, H, W, fillhole, s);
+        if (e >= 0) return e;     // -1: cooperative launch not possible here -> the three-kernel path below
+    }
     // Frames are processed in chunks whose scratch image (16 B per pixel) is at most SCRATCH_BYTES; two such buffers
     // alternate and the splat of one chunk clears the buffer of the next.  Keeping the scratch L2-RESIDENT (one 1080p
     // frame, 36 MB, per chunk) was measured: the splat's DRAM traffic fell from 731 MB to its 219 MB of input, its time
@@ -535,6 +834,13 @@ int projection_backward(const float *flow, const float *depth, const float *coun
 }  // namespace vfidkr
 
 using namespace vfidkr;
+
+VFIDKR_API int vfidkr_debug_force_projection_path(int path)
+{
+    if (path == 100) return pipeline_grid((const void *)pipe::projection_pipeline_kernel<true>);   // query: CTAs of the pipeline grid
+    if (path < 0 || path > 2) return -1;
+    return g_projection_path.exchange(path, std::memory_order_relaxed);
+}
 
 VFIDKR_API int vfidkr_flowprojection_forward(const float *input1, float *count, float *output,
                                              int B, int H, int W, int fillhole, vfidkr_stream_t s)
