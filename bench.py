@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the VFIDKR hot path on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--table PATH]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload 1080p_b8|4k_stream]
+                    [--no-check] [--table PATH]
 
 Workload (BASELINE.json configs[3], the largest single-GPU configuration; named in config.workload):
 one "step" is the hot path of a 1080p frame-pair inference batch, B = 8 pairs padded to 1152x1984
@@ -20,6 +21,11 @@ collective on the data path; NCCL only reduces the timing / unit counts.
            average duration measured with CUDA events inside the timed region, against the measured HBM copy peak.
 `cpu_baseline`  the float64 CPU oracle (a port: the reference has no CPU implementation of this path) on the
            host cores, on a bounded sample (one pair).
+`check`    before anything is timed, rank 0 runs ONE step on the reference's own kernels (oracle/_ref) on the same inputs
+           and compares all 14 outputs of the step (10 cost volumes, 2 projected flows, 2 warped frames) -- a fast kernel
+           whose results differ from the reference's is not done.  (oracle/_ref as the checker, never as the thing timed.)
+`--workload 4k_stream`  BASELINE config 5: a stream of 4K pairs (2176 x 3904 padded) dealt round-robin to the ranks, the
+           interpolated frames gathered to rank 0 with NCCL inside the timed region; strong scaling.
 `--impl reference`  the reference's OWN CUDA kernels -- oracle/_ref/*.so, the unmodified reference sources built
            for sm_100a by oracle/build_ref.py -- through the same step, called as the reference's Python layers call
            them (caller zero-fills every output).  If those modules or a GPU are absent: the CPU oracle port.
@@ -43,6 +49,18 @@ PAD_H, PAD_W = 1152, 1984                 # 1080p after the /128 replication pad
 PAIRS_PER_GPU = 8
 PWC_LEVELS = [(196, 64), (128, 32), (96, 16), (64, 8), (32, 4)]   # (channels, downscale) levels 6..2
 FI_BYTES_PER_PIXEL = 4 * (2 * 3 + 18)     # 96 B/px at C = 3
+METRIC = "interpolated Mpixel/s (1080p)"
+WORKLOAD = ("1080p_pair_inference_b8: 10x correlation fwd (5 PWC levels x 2 dirs) + 2x DepthFlowProjection fwd (fillhole) + "
+            "2x FilterInterpolation_ori fwd (C=3,F=4)")
+PAD_H_4K, PAD_W_4K, FRAME_PIXELS_4K = 2176, 3904, 3840 * 2160    # 4K after the /128 replication padding
+
+
+def workload_config(world: int) -> dict:
+    """`config` of the JSON line -- built ONCE, identical in both arms (the driver compares the two)."""
+    return {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "frame": "1920x1080 padded to 1152x1984",
+            "parallelism": f"pair-sharded x{world}, no data-path collective",
+            "l2": "inputs_exceed_l2 (one step streams > 4 GB, L2 is 126 MB)",
+            "flow": "synthetic scene flow: quarter-res smooth field + 6 moving rectangles + 0.25 px jitter, x4 bilinear (bench.py: scene_flow)"}
 FALLBACK_HBM_GBS = 6650.0                 # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
@@ -222,6 +240,81 @@ def run_step(V, mods, d, fi_events=None):
     return warped, (p0, p1), outs
 
 
+def reference_step(torch, mods, d, keep=False):
+    """The same step on the reference's own kernels (oracle/_ref), driven the way its Python layers drive them
+    (caller zero-fills every output: FilterInterpolationLayer.py:34, DepthFlowProjectionLayer.py:33-35; the correlation
+    resizes its own, correlation.py:24-31).  keep: also return the cost volumes and projections (for the check)."""
+    corr_m, dproj_m, fi_m = mods["correlation_cuda"], mods["depthflowprojection_cuda"], mods["filterinterpolation_cuda"]
+    outs, proj, warped = [], [], []
+    for lvl in range(len(PWC_LEVELS)):
+        a, b = d[f"feat{lvl}_0"], d[f"feat{lvl}_1"]
+        for x, y in ((a, b), (b, a)):
+            rb1, rb2, o = x.new_empty(0), y.new_empty(0), x.new_empty(0)
+            corr_m.forward(x, y, rb1, rb2, o, 4, 1, 4, 1, 1, 1)
+            if keep:
+                outs.append(o)
+    for k in (0, 1):
+        cnt = torch.zeros_like(d["depth"])
+        po = torch.zeros_like(d[f"rawflow{k}"])
+        dproj_m.DepthFlowProjectionLayer_gpu_forward(d[f"rawflow{k}"], d["depth"], cnt, po, 1)
+        if keep:
+            proj.append(po)
+    for k in (0, 1):
+        out = torch.zeros_like(d[f"frame{k}"])
+        fi_m.FilterInterpolationLayer_gpu_forward_ori(d[f"frame{k}"], d[f"flow{k}"], d[f"filter{k}"], out)
+        warped.append(out)
+    return warped, proj, outs
+
+
+def check_step(torch, V, mods, d):
+    """Rank 0, before timing: every output of one step against the reference's own kernels on the same inputs.
+    Both sides are fp32 and each is within the stated tolerance of the float64 oracle (tests/), so they may differ by
+    twice that: 2e-5 (cost volumes, warped frames), 2e-4 (projections: atomically ordered sums, discontinuous hole filling
+    at exact ties is the same arithmetic on both sides)."""
+    ref_mods = _reference_modules()
+    if ref_mods is None:
+        return {"ran": False, "why": "oracle/_ref modules not available"}
+    with torch.no_grad():
+        warped, proj, outs = run_step(V, mods, d)
+        rwarped, rproj, routs = reference_step(torch, ref_mods, d, keep=True)
+        torch.cuda.synchronize()
+
+        def err(a, b):
+            scale = b.abs().max().clamp_min(1e-30)
+            return float(((a - b).abs() / (b.abs() + scale)).max())
+
+        res = {"correlation": max(err(a, b) for a, b in zip(outs, routs)),
+               "depthflowprojection": max(err(a, b) for a, b in zip(proj, rproj)),
+               "filterinterpolation": max(err(a, b) for a, b in zip(warped, rwarped))}
+    tol = {"correlation": 2e-5, "depthflowprojection": 2e-4, "filterinterpolation": 2e-5}
+    ok = all(res[k] <= tol[k] for k in res)
+    del rwarped, rproj, routs
+    torch.cuda.empty_cache()
+    return {"ran": True, "ok": ok, "against": "oracle/_ref (the reference's kernels, same inputs, one step, 14 outputs)",
+            "max_normalised_error": res, "tolerance": tol}
+
+
+def h2d_ceiling(torch, device, world, dist, mib=1024, reps=4):
+    """What the box's host->device path delivers with every rank copying from pinned memory at once: GB/s summed over ranks."""
+    host = torch.empty(mib << 18, dtype=torch.float32, pin_memory=True)
+    dev = torch.empty_like(host, device=device)
+    dev.copy_(host, non_blocking=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(reps):
+        dev.copy_(host, non_blocking=True)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    nbytes = torch.tensor([float(reps * host.numel() * 4)], dtype=torch.float64, device=device)
+    reduce_timing(ms, nbytes)
+    del host, dev
+    return float(nbytes.item()) / (ms.item() * 1e-3) / 1e9
+
+
 def bench_ours(args):
     import torch
     import torch.distributed as dist
@@ -237,6 +330,7 @@ def bench_ours(args):
         dist.init_process_group("nccl", device_id=device)
 
     import vfidkr_b200 as V
+    numa_cpus = V.bind_to_gpu_numa_node(device)      # before any pinned allocation: first touch lands on the GPU's node
     mods = (V.Correlation(pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1),
             V.DepthFlowProjectionModule(requires_grad=False), V.FilterInterpolationModule())
 
@@ -247,6 +341,13 @@ def bench_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    check = None
+    if rank == 0 and not args.no_check:
+        try:
+            check = check_step(torch, V, mods, d)
+        except Exception as e:      # the checker must never take the measurement down with it
+            check = {"ran": False, "why": f"{type(e).__name__}: {e}"}
 
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
@@ -272,9 +373,31 @@ def bench_ours(args):
         fi_ms = [e[0].elapsed_time(e[1]) for step in ev for e in step]
         fi_avg_ms = sum(fi_ms) / len(fi_ms)
 
+        # ---- the dominant kernel on SURVEY 8d's stated flow distributions (outside the timed step; rank 0) ----
+        other_flows = {}
+        if rank == 0:
+            g = torch.Generator(device=device)
+            g.manual_seed(77)
+            B, H, W = PAIRS_PER_GPU, PAD_H, PAD_W
+            flows = {"up4": torch.nn.functional.interpolate((torch.randn((B, 2, H // 4, W // 4), generator=g, device=device) * 4).clamp_(-20, 20),
+                                                            scale_factor=4, mode="bilinear", align_corners=False).contiguous(),
+                     "iid": (torch.randn((B, 2, H, W), generator=g, device=device) * 4).clamp_(-20, 20)}
+            for name, fl in flows.items():
+                for _ in range(2):
+                    mods[2](d["frame0"], fl, d["filter0"])
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(5):
+                    mods[2](d["frame0"], fl, d["filter0"])
+                b.record()
+                torch.cuda.synchronize()
+                other_flows[name] = a.elapsed_time(b) / 5
+            del flows
+
         # ---- end to end: pinned host inputs -> device -> step -> frames back on the host ----
         e2e = None
         if not args.no_e2e:
+            ceiling = h2d_ceiling(torch, device, world, dist)
             hd = build_inputs(torch, device, seed=2004 + rank, pinned_host=True)
             h2d = sum(t.numel() * 4 for t in hd.values())
             host_out = torch.empty((2, PAIRS_PER_GPU, 3, PAD_H, PAD_W), dtype=torch.float32, pin_memory=True)
@@ -299,9 +422,14 @@ def bench_ours(args):
             e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
             e2e_units = torch.tensor([float(e_steps * PAIRS_PER_GPU)], dtype=torch.float64, device=device)
             reduce_timing(e2e_ms, e2e_units)
+            h2d_gbs = world * e_steps * h2d / (e2e_ms.item() * 1e-3) / 1e9
             e2e = {"value": float(e2e_units.item()) * FRAME_PIXELS / (e2e_ms.item() * 1e-3) / 1e6, "unit": "Mpixel/s",
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e_steps,
-                   "how": f"vfidkr_b200.PairStream: chunks of {args.e2e_chunk} pair(s), H2D / kernels / D2H on three streams"}
+                   "how": f"vfidkr_b200.PairStream: chunks of {args.e2e_chunk} pair(s), H2D / kernels / D2H on three streams",
+                   # the end-to-end number is the host->device path of the box, not the kernels: say so with numbers
+                   "h2d_achieved_GBps": h2d_gbs, "h2d_ceiling_GBps": ceiling, "frac_of_h2d_ceiling": h2d_gbs / ceiling,
+                   "h2d_ceiling_how": f"{world} rank(s) copying 1 GiB pinned -> device concurrently, summed",
+                   "numa_bound_cpus": len(numa_cpus) if numa_cpus else None}
             del hd, host_out
 
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
@@ -313,27 +441,26 @@ def bench_ours(args):
     value = float(units.item()) * FRAME_PIXELS / (t_ms.item() * 1e-3) / 1e6
 
     peak, peak_src = measured_peak()
-    achieved = FI_BYTES_PER_PIXEL * n_px / (fi_avg_ms * 1e-3) / 1e9
+    alg = FI_BYTES_PER_PIXEL * n_px
+    achieved = alg / (fi_avg_ms * 1e-3) / 1e9
     line = {
-        "metric": "interpolated Mpixel/s (1080p)", "value": value, "unit": "Mpixel/s",
+        "metric": METRIC, "value": value, "unit": "Mpixel/s",
         "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": t_ms.item() / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1080p_pair_inference_b8: 10x correlation fwd (5 PWC levels x 2 dirs) + "
-                               "2x DepthFlowProjection fwd (fillhole) + 2x FilterInterpolation_ori fwd (C=3,F=4)",
-                   "pairs_per_gpu": PAIRS_PER_GPU, "frame": "1920x1080 padded to 1152x1984",
-                   "parallelism": f"pair-sharded x{world}, no data-path collective",
-                   "l2": "inputs_exceed_l2 (one step streams > 4 GB, L2 is 126 MB)",
-                   "flow": "synthetic scene flow: quarter-res smooth field + 6 moving rectangles + 0.25 px jitter, x4 bilinear (bench.py: scene_flow)"},
+        "config": workload_config(world),
         "roofline": {"bound": "hbm", "kernel": "fi_forward_ori_strip_kernel<3>", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak, "traffic": recorded_traffic(),
-                     "peak_source": peak_src, "algorithmic_bytes_per_launch": FI_BYTES_PER_PIXEL * n_px,
-                     "avg_launch_ms": fi_avg_ms},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(nl.item()),
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg, "avg_launch_ms": fi_avg_ms,
+                     # the same kernel on SURVEY.md 8d's stated flow distributions (quarter-resolution N(0,4^2) x4; per-pixel i.i.d.)
+                     "frac_up4_flow": alg / (other_flows["up4"] * 1e-3) / 1e9 / peak if other_flows else None,
+                     "frac_iid_flow": alg / (other_flows["iid"] * 1e-3) / 1e9 / peak if other_flows else None},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(nl.item()), "check": check,
     }
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_arm(steps=5, warmup=1)
+            line["cpu_baseline"]["torch_cpu_fp32"] = torch_cpu_arm()
         emit_result(line)
     if args.table and rank == 0 and world == 1:
         op_table(torch, V, device, args.table)
@@ -341,17 +468,130 @@ def bench_ours(args):
         dist.destroy_process_group()
 
 
-# ----------------------------------------------------------------------------- CPU arm (oracle port)
-def cpu_reference_arm(steps=1, warmup=0):
-    """Times the CPU oracle on a bounded sample of the same workload: ONE frame pair (of the 8 per step),
-    every op of the step, all host threads OpenMP gives it."""
+# ----------------------------------------------------------------------------- BASELINE config 5: a 4K stream, pair-sharded
+def gather_frames(dist, frame, dst_list, rank, world, async_op=False):
+    """One round of the frame gather: every rank contributes the interpolated frame of its pair of this round, rank 0
+    receives them into `dst_list` (one tensor per rank).  NCCL (or gloo in the CPU tests); None when world == 1."""
+    if world == 1:
+        dst_list[0].copy_(frame)
+        return None
+    return dist.gather(frame, gather_list=dst_list if rank == 0 else None, dst=0, async_op=async_op)
+
+
+def bench_4k_stream(args):
+    """P 4K pairs dealt round-robin with shard_pairs; per pair: 10 correlations, 2 DepthFlowProjections (fillhole) and
+    the two adaptive warps blended into ONE interpolated frame (filter_interpolate_blend); the frames are gathered to
+    rank 0 over NCCL inside the timed region.  Strong scaling: the stream is the same for every N."""
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    import vfidkr_b200 as V
+    corr = V.Correlation(4, 1, 4, 1, 1, 1)
+    dproj = V.DepthFlowProjectionModule(False)
+    P, H, W = args.pairs, PAD_H_4K, PAD_W_4K
+    mine = shard_pairs(P, rank, world)
+    rounds = (P + world - 1) // world
+    g = torch.Generator(device=device)
+
+    def pair_inputs(idx):
+        g.manual_seed(5000 + idx)
+        d = {}
+        for k in (0, 1):
+            d[f"frame{k}"] = torch.rand((1, 3, H, W), generator=g, device=device)
+            d[f"flow{k}"] = scene_flow(torch, g, device, 1, H, W)
+            d[f"filter{k}"] = torch.softmax(torch.randn((1, 16, H, W), generator=g, device=device), dim=1)
+            d[f"rawflow{k}"] = scene_flow(torch, g, device, 1, H, W)
+        d["depth"] = torch.rand((1, 1, H, W), generator=g, device=device) * 0.9 + 0.1
+        for lvl, (C, s) in enumerate(PWC_LEVELS):
+            for k in (0, 1):
+                d[f"feat{lvl}_{k}"] = torch.randn((1, C, H // s, W // s), generator=g, device=device)
+        return d
+
+    # distinct inputs per pair while they fit comfortably (1.85 GB each); beyond that the pairs of a rank share 8 sets
+    sets = [pair_inputs(i) for i in mine[:8]]
+    out_rank0 = torch.empty((rounds * world, 3, H, W), device=device) if rank == 0 else None
+    dummy = torch.zeros((1, 3, H, W), device=device)
+
+    def process(j):
+        d = sets[j % len(sets)]
+        for lvl in range(len(PWC_LEVELS)):
+            a, b = d[f"feat{lvl}_0"], d[f"feat{lvl}_1"]
+            corr(a, b)
+            corr(b, a)
+        dproj(d["rawflow0"], d["depth"])
+        dproj(d["rawflow1"], d["depth"])
+        return V.filter_interpolate_blend(d["frame0"], d["frame1"], d["flow0"], d["flow1"], d["filter0"], d["filter1"], 0.5, 0.5)
+
+    def stream_once():
+        works = []
+        for r in range(rounds):
+            frame = process(r) if r < len(mine) else dummy       # ranks without a pair in the last round send a blank
+            dst = [out_rank0[r * world + k].unsqueeze(0) for k in range(world)] if rank == 0 else None
+            w = gather_frames(dist, frame, dst if rank == 0 else [None], rank, world, async_op=True)
+            if w is not None:
+                works.append((w, frame))        # keep the frame alive until the gather has consumed it
+        for w, _ in works:
+            w.wait()
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            stream_once()
+        sync_all()
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        n0 = V.launch_count()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        t0.record()
+        for _ in range(args.steps):
+            stream_once()
+        t1.record()
+        sync_all()
+        clocks = sampler.stop()
+        launches = V.launch_count() - n0
+    t_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+    units = torch.tensor([float(args.steps * len(mine))], dtype=torch.float64, device=device)
+    nl = torch.tensor([float(launches)], dtype=torch.float64, device=device)
+    reduce_timing(t_ms, units)
+    if world > 1:
+        dist.all_reduce(nl, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        frames = float(units.item())
+        emit_result({
+            "metric": "interpolated Mpixel/s (4K)", "value": frames * FRAME_PIXELS_4K / (t_ms.item() * 1e-3) / 1e6, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": t_ms.item() / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"4k_stream: {P} frame pairs 3840x2160 padded to {H}x{W}, one pair per GPU step (10x correlation fwd + "
+                                   "2x DepthFlowProjection fwd (fillhole) + FilterInterpolation_ori both directions blended), dealt round-robin",
+                       "pairs": P, "parallelism": f"pair-sharded x{world}; NCCL gather of the interpolated frames to rank 0 inside the timed region",
+                       "gathered_bytes_per_step": int((P - len(shard_pairs(P, 0, world))) * 3 * H * W * 4),
+                       "l2": "inputs_exceed_l2 (1.85 GB per pair)"},
+            "frames_per_step": P, "ms_per_pair_per_gpu": t_ms.item() / args.steps / max(1, len(mine)),
+            "clocks": clocks, "gpu_launches": int(nl.item()), "e2e": None})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------- CPU arms (oracle port, PyTorch-CPU fp32)
+def _cpu_inputs():
     import numpy as np
-    from oracle import oracle as O
-    O.build()
     r = np.random.default_rng(1004)
     H, W = PAD_H, PAD_W
     frames = [r.random((1, 3, H, W), dtype=np.float32) for _ in (0, 1)]
-    def upflow():   # quarter-resolution N(0,4^2) flow, x4 nearest+box blur stand-in is not needed: the CPU cost is flow-independent
+
+    def upflow():   # quarter-resolution N(0,4^2) flow, x4 (nearest: the CPU cost does not depend on the flow)
         lo = np.clip(r.standard_normal((1, 2, H // 4, W // 4)) * 4, -20, 20).astype(np.float32)
         return np.ascontiguousarray(np.repeat(np.repeat(lo, 4, axis=2), 4, axis=3))
     flows = [upflow() for _ in range(4)]
@@ -360,6 +600,15 @@ def cpu_reference_arm(steps=1, warmup=0):
     filts = [(a / a.sum(1, keepdims=True)).astype(np.float32) for a in filts]
     depth = (0.1 + 0.9 * r.random((1, 1, H, W), dtype=np.float32)).astype(np.float32)
     feats = [[r.standard_normal((1, C, H // s, W // s)).astype(np.float32) for _ in (0, 1)] for C, s in PWC_LEVELS]
+    return frames, flows, filts, depth, feats
+
+
+def cpu_reference_arm(steps=1, warmup=0):
+    """Times the CPU oracle on a bounded sample of the same workload: ONE frame pair (of the 8 per step),
+    every op of the step, all host threads OpenMP gives it."""
+    from oracle import oracle as O
+    O.build()
+    frames, flows, filts, depth, feats = _cpu_inputs()
 
     def step():
         for a, b in feats:
@@ -381,6 +630,37 @@ def cpu_reference_arm(steps=1, warmup=0):
             "seconds": dt, "steps": steps}
 
 
+def torch_cpu_arm(steps=2, warmup=1):
+    """The second CPU baseline of SURVEY.md 8d(ii): the step in vectorised PyTorch-CPU fp32 (oracle/torch_cpu.py:
+    gather / scatter_add_ / shifted products) on the same bounded sample, all host cores."""
+    import torch
+    from oracle import torch_cpu as T
+    torch.set_num_threads(os.cpu_count() or 1)
+    frames, flows, filts, depth, feats = [[torch.from_numpy(a) for a in x] if isinstance(x, list) and not isinstance(x[0], list) else x
+                                          for x in _cpu_inputs()]
+    depth = torch.from_numpy(depth) if not isinstance(depth, torch.Tensor) else depth
+    feats = [[torch.from_numpy(a) for a in pair] for pair in feats]
+
+    def step():
+        for a, b in feats:
+            T.correlation_forward(a, b)
+            T.correlation_forward(b, a)
+        T.flowprojection_forward(flows[2], depth, 1)
+        T.flowprojection_forward(flows[3], depth, 1)
+        for k in (0, 1):
+            T.fi_ori_forward(frames[k], flows[k], filts[k])
+
+    with torch.no_grad():
+        for _ in range(warmup):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        dt = time.perf_counter() - t0
+    return {"value": steps * FRAME_PIXELS / dt / 1e6, "unit": "Mpixel/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": "1 frame pair of the 8 per step, vectorised PyTorch-CPU fp32 (oracle/torch_cpu.py)", "seconds": dt, "steps": steps}
+
+
 def _reference_modules():
     """The reference's own extension modules (oracle/_ref), or None when they / a GPU are not available."""
     try:
@@ -398,47 +678,39 @@ def _reference_modules():
 
 
 def bench_reference_cuda(args, mods):
-    """The same step on the reference's unmodified CUDA kernels, driven the way its Python layers drive them."""
+    """The same step on the reference's unmodified CUDA kernels, driven the way its Python layers drive them.
+    EVERY rank runs its own batch, exactly as in our arm (weak scaling): max time over ranks, units summed."""
     import torch
+    import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
-    corr_m, dproj_m, fi_m = mods["correlation_cuda"], mods["depthflowprojection_cuda"], mods["filterinterpolation_cuda"]
-    B, H, W = PAIRS_PER_GPU, PAD_H, PAD_W
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
 
-    def step(d):
-        for lvl in range(len(PWC_LEVELS)):
-            a, b = d[f"feat{lvl}_0"], d[f"feat{lvl}_1"]
-            for x, y in ((a, b), (b, a)):   # correlation.py:24-31
-                rb1, rb2, o = x.new_empty(0), y.new_empty(0), x.new_empty(0)
-                corr_m.forward(x, y, rb1, rb2, o, 4, 1, 4, 1, 1, 1)
-        for k in (0, 1):                    # DepthFlowProjectionLayer.py:33-35
-            cnt = torch.zeros(B, 1, H, W, device=device)
-            po = torch.zeros(B, 2, H, W, device=device)
-            dproj_m.DepthFlowProjectionLayer_gpu_forward(d[f"rawflow{k}"], d["depth"], cnt, po, 1)
-        warped = []
-        for k in (0, 1):                    # FilterInterpolationLayer.py:34-35
-            out = torch.zeros_like(d[f"frame{k}"])
-            fi_m.FilterInterpolationLayer_gpu_forward_ori(d[f"frame{k}"], d[f"flow{k}"], d[f"filter{k}"], out)
-            warped.append(out)
-        return warped
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
 
     steps, warm = max(1, args.steps), max(args.warmup, 3)
     d = build_inputs(torch, device, seed=1004 + rank)
     with torch.no_grad():
         for _ in range(warm):
-            step(d)
-        torch.cuda.synchronize()
+            reference_step(torch, mods, d)
+        sync_all()
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0.record()
         for _ in range(steps):
-            step(d)
+            reference_step(torch, mods, d)
         t1.record()
-        torch.cuda.synchronize()
-        ms = t0.elapsed_time(t1)
-        value = steps * PAIRS_PER_GPU * FRAME_PIXELS / (ms * 1e-3) / 1e6
+        sync_all()
+        t_ms = torch.tensor([t0.elapsed_time(t1)], dtype=torch.float64, device=device)
+        units = torch.tensor([float(steps * PAIRS_PER_GPU)], dtype=torch.float64, device=device)
+        reduce_timing(t_ms, units)
+        value = float(units.item()) * FRAME_PIXELS / (t_ms.item() * 1e-3) / 1e6
         del d
         torch.cuda.empty_cache()
         # end to end from pinned host buffers, as in our arm
@@ -449,56 +721,58 @@ def bench_reference_cuda(args, mods):
 
         def e2e_step():
             dd = {k: t.to(device, non_blocking=True) for k, t in hd.items()}
-            warped = step(dd)
+            warped = reference_step(torch, mods, dd)[0]
             host_out[0].copy_(warped[0], non_blocking=True)
             host_out[1].copy_(warped[1], non_blocking=True)
         e2e_step()
-        torch.cuda.synchronize()
+        sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(e_steps):
             e2e_step()
         e1.record()
-        torch.cuda.synchronize()
-        e2e_value = e_steps * PAIRS_PER_GPU * FRAME_PIXELS / (e0.elapsed_time(e1) * 1e-3) / 1e6
-    line = {
-        "impl": "reference", "metric": "interpolated Mpixel/s (1080p)", "value": value, "unit": "Mpixel/s",
-        "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": ms / steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1080p_pair_inference_b8: 10x correlation fwd + 2x DepthFlowProjection fwd (fillhole) + "
-                               "2x FilterInterpolation_ori fwd (C=3,F=4)", "pairs_per_gpu": PAIRS_PER_GPU,
-                   "frame": "1920x1080 padded to 1152x1984",
-                   "note": "reference = its own CUDA kernels, unmodified sources compiled for sm_100a (oracle/_ref), on the same "
-                           "GPU; it has no CPU implementation of this path. Rank 0 only."},
-        "reference_kind": "reference CUDA extensions (oracle/_ref)",
-        "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": host_out.numel() * 4, "steps": e_steps},
-        "gpu_launches": 0,
-    }
-    if not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_arm(steps=3, warmup=1)
-    emit_result(line)
+        sync_all()
+        e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+        e_units = torch.tensor([float(e_steps * PAIRS_PER_GPU)], dtype=torch.float64, device=device)
+        reduce_timing(e_ms, e_units)
+        e2e_value = float(e_units.item()) * FRAME_PIXELS / (e_ms.item() * 1e-3) / 1e6
+    if rank == 0:
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": steps, "warmup": warm, "ms_per_step": t_ms.item() / steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(world),
+            "reference_kind": "reference CUDA extensions (oracle/_ref)",
+            "note": "reference = its own CUDA kernels, unmodified sources compiled for sm_100a (oracle/_ref), on the same GPUs -- it "
+                    "has no CPU implementation of this path; every rank runs its own batch, as in our arm",
+            "e2e": {"value": e2e_value, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": host_out.numel() * 4, "steps": e_steps},
+            "gpu_launches": 0,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_reference_arm(steps=3, warmup=1)
+        emit_result(line)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
     mods = None if args.reference_cpu else _reference_modules()
     if mods is not None:
         return bench_reference_cuda(args, mods)
+    if rank != 0:       # the CPU port: rank 0 alone runs and prints it
+        return
     res = cpu_reference_arm(steps=max(1, min(args.steps, 3)), warmup=1 if args.warmup > 0 else 0)
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     line = {
-        "impl": "reference", "metric": "interpolated Mpixel/s (1080p)", "value": res["value"], "unit": "Mpixel/s",
-        "n_gpus": world, "steps": res["steps"], "warmup": 1 if args.warmup > 0 else 0,
+        "impl": "reference", "metric": METRIC, "value": res["value"], "unit": "Mpixel/s",
+        "n_gpus": 1, "steps": res["steps"], "warmup": 1 if args.warmup > 0 else 0,
         "ms_per_step": res["seconds"] / res["steps"] * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "1080p_pair_inference_b8 (bounded sample: 1 pair per step)", "pairs_per_gpu": PAIRS_PER_GPU,
-                   "frame": "1920x1080 padded to 1152x1984",
-                   "note": "the reference has no CPU implementation of this path and its CUDA modules (oracle/_ref) were not "
-                           "available; this arm is the float64 CPU oracle port on the host cores"},
+        "config": workload_config(1),
         "reference_kind": "CPU oracle port",
+        "note": "the reference has no CPU implementation of this path and its CUDA modules (oracle/_ref) were not available; this arm is "
+                "the float64 CPU oracle port on the host cores, rank 0 only, on a bounded sample (1 pair per step)",
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -692,6 +966,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--reference-cpu", action="store_true", help="--impl reference: force the CPU oracle port")
     ap.add_argument("--table", default=None, help="also write the per-operator timing table (JSON lines) here")
+    ap.add_argument("--workload", choices=["1080p_b8", "4k_stream"], default="1080p_b8",
+                    help="1080p_b8: the headline line (BASELINE config 4); 4k_stream: config 5, pair-sharded with an NCCL gather")
+    ap.add_argument("--pairs", type=int, default=16, help="4k_stream: pairs in the stream (same for every N: strong scaling)")
+    ap.add_argument("--no-check", action="store_true", help="skip the pre-timing comparison against the reference's kernels")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON result: everything else a library may print there (NCCL's version banner
     # under NCCL_DEBUG=VERSION, for instance) is sent to stderr, and the result goes to a private copy of the real stdout
@@ -701,6 +979,8 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         bench_reference(args)
+    elif args.workload == "4k_stream":
+        bench_4k_stream(args)
     else:
         bench_ours(args)
 

@@ -46,12 +46,8 @@ def _nearest_valid(valid: torch.Tensor, dim: int, reverse: bool) -> torch.Tensor
     shape[dim] = n
     pos = torch.arange(n).view(shape).expand_as(valid)
     if reverse:
-        v, p = valid.flip(dim), (n - 1 - pos).flip(dim)
-        cand = torch.where(v, n - 1 - p, torch.full_like(p, -1))     # position in flipped coordinates
-        best = torch.cummax(cand, dim).values
-        best = torch.cat([torch.full_like(best.narrow(dim, 0, 1), -1), best.narrow(dim, 0, n - 1)], dim)   # strictly after
-        res = torch.where(best >= 0, n - 1 - best, torch.full_like(best, -1))
-        return res.flip(dim)
+        r = _nearest_valid(valid.flip(dim), dim, False)          # in flipped coordinates
+        return torch.where(r >= 0, n - 1 - r, r).flip(dim)
     cand = torch.where(valid, pos, torch.full_like(pos, -1))
     best = torch.cummax(cand, dim).values
     return torch.cat([torch.full_like(best.narrow(dim, 0, 1), -1), best.narrow(dim, 0, n - 1)], dim)       # strictly before

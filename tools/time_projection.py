@@ -28,10 +28,11 @@ def timeit(fn, iters=10):
     return a.elapsed_time(b) / iters * 1e3
 
 
-print('pipeline grid (CTAs):', V._lib.load().vfidkr_debug_force_projection_path(100))
 with torch.no_grad():
-    for path in ("kernels", "pipeline"):
+    for path, kib in (("kernels", 0), ("chunks_pdl", 0), ("chunks_pdl", 700000), ("chunks_1px", 700000), ("chunks_pdl", 80000)):
         V.debug_force_projection_path(path)
+        V.debug_projection_chunk_kib(kib)
+        path = f"{path}/{kib // 1000}MB"
         for name, f in (("bench flow", fl), ("up4 flow", up4)):
             t_d = timeit(lambda: V.DepthFlowProjectionLayer.apply(f, dep, False))
             t_dn = timeit(lambda: V.DepthFlowProjectionLayer.apply(f, dep, True))
@@ -43,3 +44,4 @@ with torch.no_grad():
             dx = torch.rand(Bx, 1, Hx, Wx, device=dev) * 0.9 + 0.1
             print(f"{path:9s} {Bx}x{Hx}x{Wx}: DepthFlowProjection fill {timeit(lambda: V.DepthFlowProjectionLayer.apply(fx, dx, False)):7.1f} us")
 V.debug_force_projection_path(None)
+V.debug_projection_chunk_kib(0)

@@ -17,6 +17,7 @@
 //     (the reference does eight / sixteen read-modify-writes of its own pixel).
 #include <algorithm>
 #include <atomic>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -131,6 +132,13 @@ projection_splat_kernel(const FlowSource fs, int b0, const float *__restrict__ d
 // Box pass + averaging (:128-135).  One warp owns a 32-column block of a row segment and walks it downwards,
 // carrying the horizontally summed previous row in registers: S is read once (plus one halo row per segment and
 // one halo column per block), count and output are written once, planar.
+// column bitmap: for every column x a row of 64-bit words, word k = rows 64k .. 64k+63 (bit r = row 64k + r); the box
+// pass writes it a byte (8 rows) at a time.  A hole n rows tall costs n / 64 loads per vertical scan.
+__host__ __device__ inline int colwords(int H) { return (H + 63) >> 6; }
+__device__ __forceinline__ unsigned char *colmask_byte(unsigned long long *cm, int x, int seg, int H)
+{
+    return reinterpret_cast<unsigned char *>(cm + (size_t)x * colwords(H) + (seg >> 3)) + (seg & 7);
+}
 constexpr int FIN_ROWS = 8, FIN_WARPS = 4, FIN_UNROLL = 4;   // short segments: one frame per launch must still fill 148 SMs
 
 // raw loads of one row: this lane's cell and (lane 0 only) the cell left of the block
@@ -162,8 +170,11 @@ __device__ __forceinline__ float4 hsum_row(const float4 &cur, const float4 &edge
 
 __global__ void __launch_bounds__(32 * FIN_WARPS)
 projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count, float *__restrict__ out,
-                         unsigned *__restrict__ rowmask, unsigned char *__restrict__ colmask, int H, int W)
+                         unsigned *__restrict__ rowmask, unsigned long long *__restrict__ colmask, unsigned *__restrict__ holemask,
+                         int H, int W)
 {
+    // holemask (with rowmask / colmask): one bit per pixel, set where count <= 0 -- the holes; eight words (one per row)
+    // per 32 x 8 block, contiguous, so that the hole filling finds its work without reading the count plane.
     // rowmask / colmask (inference only, else null): one bit per pixel, set where count != 0 -- the pixels the hole
     // filling may take values from (:175-213) -- packed along rows (32 columns per word) and along columns (the 8 rows
     // of this segment per byte), so that its scans step 32 columns / 8 rows per load instead of one pixel.
@@ -177,7 +188,7 @@ projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count
     float4 c0, e0;
     load_row(Sb + (size_t)max(y0 - 1, 0) * W, x, W, lane, y0 > 0, c0, e0);
     float4 prev = hsum_row(c0, e0, x, W, lane);
-    unsigned colbits = 0;
+    unsigned colbits = 0, holeword = 0;
     for (int yb = y0; yb < y1; yb += FIN_UNROLL) {
         float4 cur[FIN_UNROLL], edge[FIN_UNROLL];
 #pragma unroll
@@ -202,10 +213,14 @@ projection_finish_kernel(const float4 *__restrict__ S, float *__restrict__ count
                 const unsigned m = __ballot_sync(0xffffffffu, src);
                 if (lane == 0 && y < y1) rowmask[((size_t)b * H + y) * ((W + 31) >> 5) + (x >> 5)] = m;
                 colbits |= (src ? 1u : 0u) << (y - y0);
+                const unsigned hm = __ballot_sync(0xffffffffu, live && !(sc > 0.0f));   // count <= 0 (:171)
+                if (lane == (y - y0)) holeword = hm;
             }
         }
     }
-    if (colmask && x < W) colmask[((size_t)b * ((H + 7) >> 3) + blockIdx.y) * W + x] = (unsigned char)colbits;
+    if (colmask && x < W) *colmask_byte(colmask + (size_t)b * W * colwords(H), x, blockIdx.y, H) = (unsigned char)colbits;
+    if (holemask && lane < FIN_ROWS)
+        holemask[(((size_t)b * ((H + 7) >> 3) + blockIdx.y) * ((W + 31) >> 5) + (x >> 5)) * FIN_ROWS + lane] = holeword;
 }
 
 // hole filling (:171-232).  Reads only non-hole pixels (count != 0), which this kernel never writes, so running it in
@@ -238,25 +253,25 @@ __device__ __forceinline__ int scan_right(const unsigned *__restrict__ rm, int x
     }
 }
 template <bool CG = false>
-__device__ __forceinline__ int scan_up(const unsigned char *__restrict__ cm, int y, int W)
+__device__ __forceinline__ int scan_up(const unsigned long long *__restrict__ col, int y)
 {
-    int bi = y >> 3;
-    unsigned m = ldm<CG>(cm + (size_t)bi * W) & ((1u << (y & 7)) - 1u);
+    int wi = y >> 6;
+    unsigned long long m = (CG ? __ldcg(col + wi) : __ldg(col + wi)) & ((1ull << (y & 63)) - 1ull);
     for (;;) {
-        if (m) return y - ((bi << 3) + 31 - __clz(m));
-        if (--bi < 0) return 0;
-        m = ldm<CG>(cm + (size_t)bi * W);
+        if (m) return y - ((wi << 6) + 63 - __clzll((long long)m));
+        if (--wi < 0) return 0;
+        m = CG ? __ldcg(col + wi) : __ldg(col + wi);
     }
 }
 template <bool CG = false>
-__device__ __forceinline__ int scan_down(const unsigned char *__restrict__ cm, int y, int W, int HB)
+__device__ __forceinline__ int scan_down(const unsigned long long *__restrict__ col, int y, int HWd)
 {
-    int bi = y >> 3;
-    unsigned m = ldm<CG>(cm + (size_t)bi * W) & 0xffu & ~((2u << (y & 7)) - 1u);
+    int wi = y >> 6;
+    unsigned long long m = (CG ? __ldcg(col + wi) : __ldg(col + wi)) & ~((2ull << (y & 63)) - 1ull);   // bits above y (none when y & 63 == 63)
     for (;;) {
-        if (m) return (bi << 3) + __ffs(m) - 1 - y;
-        if (++bi >= HB) return 0;
-        m = ldm<CG>(cm + (size_t)bi * W);
+        if (m) return (wi << 6) + __ffsll((long long)m) - 1 - y;
+        if (++wi >= HWd) return 0;
+        m = CG ? __ldcg(col + wi) : __ldg(col + wi);
     }
 }
 
@@ -265,16 +280,16 @@ __device__ __forceinline__ int scan_down(const unsigned char *__restrict__ cm, i
 // ONE frame.  CG: everything was written earlier in the same launch by other SMs -> L2-coherent loads.
 template <bool CG>
 __device__ __forceinline__ void fill_one(const float *__restrict__ cnb, float *__restrict__ ob, const unsigned *__restrict__ rm,
-                                         const unsigned char *__restrict__ cm, int x, int y, int H, int W)
+                                         const unsigned long long *__restrict__ cm, int x, int y, int H, int W)
 {
     auto ld = [](const float *p) { return CG ? __ldcg(p) : __ldg(p); };
     const size_t HW = (size_t)H * W;
-    const int WW = (W + 31) >> 5, HB = (H + 7) >> 3;
+    const int WW = (W + 31) >> 5, HWd = colwords(H);
     const float *cn = cnb + (size_t)y * W + x;
     const int dl = scan_left<CG>(rm + (size_t)y * WW, x);
     const int dr = scan_right<CG>(rm + (size_t)y * WW, x, WW);
-    const int du = scan_up<CG>(cm + x, y, W);
-    const int dd = scan_down<CG>(cm + x, y, W, HB);
+    const int du = scan_up<CG>(cm + (size_t)x * HWd, y);
+    const int dd = scan_down<CG>(cm + (size_t)x * HWd, y, HWd);
     // the counts the reference's loops end on (0 when a scan ran off the plane)
     const float lt = dl ? ld(cn - dl) : 0.0f, rt = dr ? ld(cn + dr) : 0.0f;
     const float ut = du ? ld(cn - (long long)du * W) : 0.0f, dt = dd ? ld(cn + (long long)dd * W) : 0.0f;
@@ -293,151 +308,146 @@ __device__ __forceinline__ void fill_one(const float *__restrict__ cnb, float *_
     }
 }
 
-// Holes are sparse (a few per cent of the pixels) but scattered, so with one thread per pixel most warps would run
-// the scans for one or two live lanes.  The CTA therefore first COMPACTS its holes into a shared list (ballot +
-// one shared atomic per warp) and then fills them with dense warps.
-__global__ void __launch_bounds__(BX *BY)
-projection_fillhole_kernel(const float *__restrict__ count, float *__restrict__ out, const unsigned *__restrict__ rowmask,
-                           const unsigned char *__restrict__ colmask, int H, int W)
+// Hole filling, driven by the hole bitmask the box pass wrote (eight words per 32 x 8 block): warps stride over the
+// blocks of the whole batch, skip blocks and rows without holes after one 32-byte load, and a lane fills the hole in its
+// column.  Neighbouring holes are filled by neighbouring lanes / consecutive rows, so their scans and gathers share
+// sectors.  (Round 1 launched one CTA per 32 x 8 tile that re-read the count plane and compacted its holes: 71 k CTAs
+// at 1080p x 8, 75-180 us of CTA turnover for a few per cent of hole pixels.)
+constexpr int FILL_WARPS = 8;
+__global__ void __launch_bounds__(32 * FILL_WARPS)
+projection_fill_mask_kernel(const float *__restrict__ count, float *__restrict__ out, const unsigned *__restrict__ rowmask,
+                            const unsigned long long *__restrict__ colmask, const unsigned *__restrict__ holemask,
+                            int B, int H, int W, const FastDiv div_items, const FastDiv div_bw)
 {
-    __shared__ int s_n;
-    __shared__ unsigned short s_list[BX * BY];
-    const int tid = threadIdx.y * BX + threadIdx.x, lane = threadIdx.x;
-    const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
-    const int b = blockIdx.z;
+    const int lane = threadIdx.x & 31;
+    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3, nitems = bw * HB;
     const size_t HW = (size_t)H * W;
-    const int WW = (W + 31) >> 5, HB = (H + 7) >> 3;
-    const float *cnb = count + (size_t)b * HW;
-    if (tid == 0) s_n = 0;
-    __syncthreads();
-    const bool hole = w_i < W && h_i < H && !(__ldcs(cnb + (size_t)h_i * W + w_i) > 0.0f);   // count <= 0 (:171)
-    const unsigned m = __ballot_sync(0xffffffffu, hole);
-    if (m) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_n, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (hole) s_list[base + __popc(m & ((1u << lane) - 1u))] = (unsigned short)tid;
-    }
-    __syncthreads();
-    const int n = s_n;
-    for (int q = tid; q < n; q += BX * BY) {
-        const int t = s_list[q];
-        fill_one<false>(cnb, out + (size_t)b * 2 * HW, rowmask + (size_t)b * H * WW, colmask + (size_t)b * HB * W,
-                        blockIdx.x * BX + (t & (BX - 1)), blockIdx.y * BY + t / BX, H, W);
+    const int total = B * nitems;     // < 2^31 (launcher)
+    for (int g = blockIdx.x * FILL_WARPS + (threadIdx.x >> 5); g < total; g += gridDim.x * FILL_WARPS) {
+        const unsigned mine = lane < FIN_ROWS ? __ldg(holemask + (size_t)g * FIN_ROWS + lane) : 0u;
+        if (!__any_sync(0xffffffffu, mine != 0u)) continue;
+        const int f = div_items.quot(g), it = g - f * nitems;
+        const int seg = div_bw.quot(it), x0 = (it - seg * bw) * 32;
+        // the block's holes in raster order, dealt to the lanes densely: hole n is the (n - before[r])-th set bit of row r
+        unsigned w[FIN_ROWS];
+        int upto[FIN_ROWS], n_holes = 0;
+#pragma unroll
+        for (int k = 0; k < FIN_ROWS; ++k) {
+            w[k] = __shfl_sync(0xffffffffu, mine, k);
+            n_holes += __popc(w[k]);
+            upto[k] = n_holes;          // holes in rows 0 .. k
+        }
+        for (int n = lane; n < n_holes; n += 32) {
+            int r = 0, before = 0;
+            unsigned word = w[0];
+#pragma unroll
+            for (int k = 1; k < FIN_ROWS; ++k)
+                if (n >= upto[k - 1]) { r = k; before = upto[k - 1]; word = w[k]; }
+            const int bit = (int)__fns(word, 0, n - before + 1);
+            fill_one<false>(count + (size_t)f * HW, out + (size_t)f * 2 * HW, rowmask + (size_t)f * H * bw,
+                            colmask + (size_t)f * W * colwords(H), x0 + bit, seg * FIN_ROWS + r, H, W);
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Fused forward for batches: ONE persistent, cooperatively launched kernel pipelines the frames of the batch.
+// Forward for batches: L2-resident scratch, persistent kernels, one (splat, box pass) launch pair per chunk of frames.
 //
-// The splat is bound by the rate at which L2 retires vector REDs, the box pass by L2 / DRAM bandwidth: different units,
-// so the two run CONCURRENTLY on different frames.  Half of the CTAs (one per SM) are splat workers, the other half
-// (one more per SM) are finish workers; each role walks the frames in order with a static share of the frame's tiles,
-// and the roles meet only through per-frame counters in global memory:
-//     splat(f)   needs the scratch image f % NB clean      (c_done[f - NB] == workers; the first NB images: see below)
-//     finish(f)  needs every splat worker done with f      (s_done[f] == workers)
-//     clear(f)   needs every finish worker done with f     (f_done[f] == workers) -- it is run one frame LATE, after
-//                finish(f + 1), when that condition has long been true: no worker ever waits at a barrier
-// so the splat workers run up to NB - 1 frames ahead and the RED unit never waits for a box pass.  NB = 3 scratch
-// images of 16 B per pixel rotate; at 1080p they and the streams around them live in the 126 MB L2, so the scratch
-// makes no DRAM round trip (the three-kernel path below moves 2.9x the algorithmic bytes).  Image 0 is cleared on the
-// stream before the launch, images 1 .. NB-1 by the finish workers while the first splat runs.
-// Holes are appended to ONE list for the batch by the box pass (one global atomic per 32 x 4 block that has any); a
-// second, small launch fills exactly those pixels.  (A first version filled the holes of frame f inside the pipeline,
-// behind a barrier of the finish workers: its chain of dependent L2 round trips -- barrier, bitmap scans, value loads --
-// cost 30-90 us PER FRAME with only one frame's holes in flight; measured 736 us against 421 us for three kernels.)
-// All cross-SM traffic inside the launch uses L2-coherent accesses (RED, ld.global.cg / st.global.cg): L1 is not
-// coherent and the images are reused.  The counters need every CTA resident: cudaLaunchCooperativeKernel guarantees it
-// (or fails -> three-kernel path).
+// What bounds the three-kernel path above at 1080p x 8 is DRAM: its scratch image for the whole batch (16 B per pixel,
+// 292 MB) is cleared, read-modify-written by the REDs and read back -- 2.9x the algorithmic bytes.  The vector RED
+// itself is fast when its target lives in L2 (tools/microbench/ffma2.cu: 360 G RED/s into a 36 MB image, 170 G RED/s
+// into a 292 MB one).  So the batch is cut into chunks whose scratch (<= CHUNK_BYTES) stays in the 126 MB L2, two
+// scratch images alternate, and the splat of a chunk clears the image of the next one (cell for cell, in L2).  What
+// made this lose in round 1 -- one launch pair per frame took ~17 us each -- was latency, not bytes: one pixel per
+// thread (a DRAM round trip per wave of CTAs) and 9 k CTAs per launch.  These kernels are persistent (two CTAs of 512
+// threads per SM), a splat thread keeps the loads of four pixels in flight before its first RED, a box-pass warp the
+// loads of four rows, and each launch may start while its predecessor drains (programmatic dependent launch).
+// (Also built and measured, profiles/r02/time_projection_v*.log: ONE cooperative kernel with splat workers and box-pass
+// workers on different frames, meeting through per-frame counters in global memory.  Correct, but every hand-off -- fence,
+// counter, poll -- costs ~2 us and a frame needs six of them in sequence: 12 us per frame of pure latency, 339-363 us
+// for the batch against 313 us for the three kernels.  Removed.)
 // ---------------------------------------------------------------------------------------------------------------
-namespace pipe {
+namespace pf {
 
-constexpr int NT = 512;            // threads per CTA, both roles
-constexpr int NB_MAX = 3;          // scratch images in rotation
-constexpr int SPLAT_UNROLL = 4;    // 32 x 16 pixel sub-tiles whose loads a splat worker keeps in flight
+constexpr int NT = 512;            // threads per CTA
+constexpr int SPLAT_UNROLL = 4;    // 32 x 16 pixel sub-tiles whose loads a thread block keeps in flight
 constexpr int WARPS = NT / 32;
+constexpr size_t CHUNK_BYTES = (size_t)40 << 20;   // scratch of one chunk of frames: two of these + the streams fit in L2
 
-struct FrameCtl { unsigned s_done, f_done, c_done, pad; };        // zeroed on the stream before the launch
-struct Ctl { unsigned pre_done, h_count, pad[2]; };                // images 1 .. NB-1 cleared; holes listed so far
+__device__ __forceinline__ void grid_dependency_wait()      // programmatic dependent launch: the predecessor has completed
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
-__device__ __forceinline__ unsigned ld_acquire(const unsigned *p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-// every thread of the CTA calls these two
-__device__ __forceinline__ void cta_wait(const unsigned *flag, unsigned target)
-{
-    if (threadIdx.x == 0) {
-        unsigned ns = 32;
-        while (ld_acquire(flag) < target) { __nanosleep(ns); if (ns < 512) ns <<= 1; }
-        __threadfence();
-    }
-    __syncthreads();
-}
-__device__ __forceinline__ void cta_signal(unsigned *flag)
-{
-    __syncthreads();   // every thread's REDs / stores are issued ...
-    if (threadIdx.x == 0) { __threadfence(); atomicAdd(flag, 1u); }   // ... and ordered before the count (cumulative fence)
-}
-
+// Splat of a chunk of `nb` frames (the first is frame b0 of the batch) into S, and clear of `clear` (the other scratch
+// image, used by the next chunk; may be null).  Work items: 32 x 16 pixel sub-tiles of all frames of the chunk.
 template <bool DEPTH>
-__device__ __forceinline__ void splat_frame(const FlowSource &fs, const float *__restrict__ depth_f, int frame,
-                                            float4 *__restrict__ S, int H, int W, int worker, int nworkers, const FastDiv div_tx)
+__global__ void __launch_bounds__(NT, 2)
+projection_splat_chunk_kernel(const FlowSource fs, int b0, int nb, const float *__restrict__ depth, float4 *__restrict__ S,
+                              float4 *__restrict__ clear, int H, int W, const FastDiv div_tx, const FastDiv div_tiles)
 {
-    const int tiles_x = (W + 31) >> 5, ntiles = tiles_x * ((H + 15) >> 4);
+    grid_dependency_wait();
+    const size_t HW = (size_t)H * W;
+    const int tiles_x = (W + 31) >> 5, tiles_f = tiles_x * ((H + 15) >> 4), ntiles = tiles_f * nb;
     const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+    const int worker = blockIdx.x, nworkers = gridDim.x;
     for (int t0 = worker; t0 < ntiles; t0 += nworkers * SPLAT_UNROLL) {
         float fx[SPLAT_UNROLL], fy[SPLAT_UNROLL], d[SPLAT_UNROLL];
-        int wi[SPLAT_UNROLL], hi[SPLAT_UNROLL];
+        int wi[SPLAT_UNROLL], hi[SPLAT_UNROLL], fr[SPLAT_UNROLL];
         bool ok[SPLAT_UNROLL];
 #pragma unroll
         for (int k = 0; k < SPLAT_UNROLL; ++k) {   // every load of the group before the first RED
-            const int t = t0 + k * nworkers;
-            const int ty = div_tx.quot(min(t, ntiles - 1)), tx = min(t, ntiles - 1) - ty * tiles_x;
+            const int t = min(t0 + k * nworkers, ntiles - 1);
+            fr[k] = div_tiles.quot(t);
+            const int tt = t - fr[k] * tiles_f, ty = div_tx.quot(tt), tx = tt - ty * tiles_x;
             wi[k] = tx * 32 + lx; hi[k] = ty * 16 + ly;
-            ok[k] = t < ntiles && wi[k] < W && hi[k] < H;
+            ok[k] = t0 + k * nworkers < ntiles && wi[k] < W && hi[k] < H;
             fx[k] = fy[k] = 0.0f; d[k] = 1.0f;
             if (ok[k]) {
-                load_flow(fs, frame, hi[k], wi[k], H, W, fx[k], fy[k]);
-                if (DEPTH) d[k] = ld_stream(depth_f + (size_t)hi[k] * W + wi[k]);
+                load_flow(fs, b0 + fr[k], hi[k], wi[k], H, W, fx[k], fy[k]);
+                if (DEPTH) d[k] = ld_stream(depth + (size_t)(b0 + fr[k]) * HW + (size_t)hi[k] * W + wi[k]);
             }
         }
 #pragma unroll
         for (int k = 0; k < SPLAT_UNROLL; ++k) {
             if (!ok[k]) continue;
+            if (clear) __stcg(clear + (size_t)fr[k] * HW + (size_t)hi[k] * W + wi[k], make_float4(0.f, 0.f, 0.f, 0.f));
             const Corners c = corners(wi[k], hi[k], fx[k], fy[k], W, H);
             if (!c.in_range) continue;
-            const float vx = DEPTH ? -d[k] * fx[k] : -fx[k], vy = DEPTH ? -d[k] * fy[k] : -fy[k];
-            atomicAdd(S + (size_t)c.T * W + c.L, make_float4(vx, vy, d[k], 0.0f));   // REDG.F32x4
+            const float vx = DEPTH ? -d[k] * fx[k] : -fx[k], vy = DEPTH ? -d[k] * fy[k] : -fy[k];   // :75-88 / depth :77-92
+            atomicAdd(S + (size_t)fr[k] * HW + (size_t)c.T * W + c.L, make_float4(vx, vy, d[k], 0.0f));   // REDG.F32x4
         }
     }
+    grid_launch_dependents();
 }
 
-// box pass + averaging of one frame, the finish worker's share: warp items of 32 columns x 8 rows (the arithmetic of
-// projection_finish_kernel, same operation order).  With hole filling: bitmaps and the frame's hole list.
-__device__ __forceinline__ void finish_frame(const float4 *__restrict__ Sf, float *__restrict__ cn, float *__restrict__ ou,
-                                             unsigned *__restrict__ rowmask_f, unsigned char *__restrict__ colmask_f,
-                                             unsigned *__restrict__ hlist, unsigned *__restrict__ h_count, unsigned frame_base,
-                                             int H, int W, int gwarp, int nwarps, const FastDiv div_bw)
+// Box pass + averaging of a chunk (the arithmetic of projection_finish_kernel, same operation order): warp items of
+// 32 columns x 8 rows over all frames of the chunk.  S is read through L2 (ld.global.cg: it was just written there).
+__global__ void __launch_bounds__(NT, 2)
+projection_finish_chunk_kernel(const float4 *__restrict__ S, int nb, float *__restrict__ count, float *__restrict__ out,
+                               unsigned *__restrict__ rowmask, unsigned long long *__restrict__ colmask, unsigned *__restrict__ holemask,
+                               int H, int W, const FastDiv div_bw, const FastDiv div_items)
 {
+    grid_dependency_wait();
     const int lane = threadIdx.x & 31;
-    const int bw = (W + 31) >> 5, nitems = bw * ((H + FIN_ROWS - 1) / FIN_ROWS);
+    const int bw = (W + 31) >> 5, HB = (H + FIN_ROWS - 1) / FIN_ROWS, nitems = bw * HB, total = nitems * nb;
     const size_t HW = (size_t)H * W;
-    float *ov = ou + HW;
-    for (int it = gwarp; it < nitems; it += nwarps) {
+    const int gwarp = blockIdx.x * WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * WARPS;
+    for (int g = gwarp; g < total; g += nwarps) {
+        const int f = div_items.quot(g), it = g - f * nitems;
+        const float4 *Sf = S + (size_t)f * HW;
+        float *cn = count + (size_t)f * HW, *ou = out + (size_t)f * 2 * HW, *ov = ou + HW;
         const int seg = div_bw.quot(it), x = (it - seg * bw) * 32 + lane;
         const int y0 = seg * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
         float4 c0, e0;
         load_row<true>(Sf + (size_t)max(y0 - 1, 0) * W, x, W, lane, y0 > 0, c0, e0);
         float4 prev = hsum_row(c0, e0, x, W, lane);
-        unsigned colbits = 0;
+        unsigned colbits = 0, holeword = 0;
 #pragma unroll
         for (int ybk = 0; ybk < FIN_ROWS; ybk += FIN_UNROLL) {
             const int yb = y0 + ybk;
             float4 cur[FIN_UNROLL], edge[FIN_UNROLL];
-            unsigned holes[FIN_UNROLL];
 #pragma unroll
             for (int k = 0; k < FIN_UNROLL; ++k)
                 load_row<true>(Sf + (size_t)min(yb + k, H - 1) * W, x, W, lane, yb + k < y1, cur[k], edge[k]);
@@ -453,101 +463,193 @@ __device__ __forceinline__ void finish_frame(const float4 *__restrict__ Sf, floa
                 if (live) {
                     if (sc > 0.0f) { su = su / sc; sv = sv / sc; }   // :130-134
                     const size_t a = (size_t)y * W + x;
-                    __stcg(cn + a, sc); __stcg(ou + a, su); __stcg(ov + a, sv);
+                    st_stream(cn + a, sc); st_stream(ou + a, su); st_stream(ov + a, sv);
                 }
-                holes[k] = 0;
-                if (rowmask_f) {   // uniform
+                if (rowmask) {   // uniform
                     const bool src = live && sc != 0.0f;
                     const unsigned m = __ballot_sync(0xffffffffu, src);
-                    if (lane == 0 && y < y1) __stcg(rowmask_f + (size_t)y * bw + (x >> 5), m);
+                    if (lane == 0 && y < y1) rowmask[((size_t)f * H + y) * bw + (x >> 5)] = m;
                     colbits |= (src ? 1u : 0u) << (y - y0);
-                    holes[k] = __ballot_sync(0xffffffffu, live && !(sc > 0.0f));   // count <= 0 (:171)
-                }
-            }
-            if (rowmask_f) {   // the group's holes go to the frame's list: one global atomic per group that has any
-                unsigned total = 0;
-#pragma unroll
-                for (int k = 0; k < FIN_UNROLL; ++k) total += __popc(holes[k]);
-                if (total) {   // uniform
-                    unsigned base = 0;
-                    if (lane == 0) base = atomicAdd(h_count, total);
-                    base = __shfl_sync(0xffffffffu, base, 0);
-#pragma unroll
-                    for (int k = 0; k < FIN_UNROLL; ++k) {
-                        if (holes[k] >> lane & 1u)
-                            __stcg(hlist + base + __popc(holes[k] & ((1u << lane) - 1u)), frame_base + (unsigned)((yb + k) * W + x));
-                        base += __popc(holes[k]);
-                    }
+                    const unsigned hm = __ballot_sync(0xffffffffu, live && !(sc > 0.0f));   // count <= 0 (:171)
+                    if (lane == ybk + k) holeword = hm;
                 }
             }
         }
-        if (rowmask_f && x < W) colmask_f[(size_t)seg * W + x] = (unsigned char)colbits;   // read after the frame's barrier (cg loads)
+        if (rowmask) {
+            if (x < W) *colmask_byte(colmask + (size_t)f * W * colwords(H), x, seg, H) = (unsigned char)colbits;
+            if (lane < FIN_ROWS) holemask[(size_t)g * FIN_ROWS + lane] = holeword;
+        }
     }
+    grid_launch_dependents();
 }
 
+// ---- four pixels per thread (W % 4 == 0, 16-byte aligned tensors, full-resolution flow) -----------------------------
+// ncu on the kernels above (profiles/r02): 103 warp-instructions per pixel in the splat, 192 in the box pass -- the box
+// pass is INSTRUCTION-bound (issue slots 61 % busy at 25 us per 1080p frame), not byte-bound.  Here a thread owns four
+// adjacent pixels: flow / depth / count / output move as 128-bit accesses, the horizontal neighbour comes from the
+// thread's own registers three times out of four, the bitmaps are assembled from 4-bit nibbles with three shuffles.
 template <bool DEPTH>
 __global__ void __launch_bounds__(NT, 2)
-projection_pipeline_kernel(const FlowSource fs, const float *__restrict__ depth, float4 *__restrict__ S, int nbuf,
-                           float *__restrict__ count, float *__restrict__ out, unsigned *__restrict__ rowmask,
-                           unsigned char *__restrict__ colmask, unsigned *__restrict__ hlist, Ctl *__restrict__ ctl,
-                           FrameCtl *__restrict__ fctl, int B, int H, int W, const FastDiv div_tx, const FastDiv div_bw)
+projection_splat4_kernel(const float *__restrict__ flow, int b0, int nb, const float *__restrict__ depth, float4 *__restrict__ S,
+                         float4 *__restrict__ clear, int H, int W, const FastDiv div_w4, const FastDiv div_hw4)
 {
-    const int workers = gridDim.x >> 1;
-    const bool splat_role = (int)blockIdx.x < workers;
-    const int worker = splat_role ? blockIdx.x : blockIdx.x - workers;
+    grid_dependency_wait();
     const size_t HW = (size_t)H * W;
-    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3;
-    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (splat_role) {
-        for (int f = 0; f < B; ++f) {
-            if (f >= nbuf) cta_wait(&fctl[f - nbuf].c_done, workers);
-            else if (f > 0) cta_wait(&ctl->pre_done, workers);
-            splat_frame<DEPTH>(fs, DEPTH ? depth + (size_t)f * HW : nullptr, f, S + (size_t)(f % nbuf) * HW, H, W, worker, workers, div_tx);
-            cta_signal(&fctl[f].s_done);
+    const int W4 = W >> 2, HW4 = H * W4, total = HW4 * nb;     // groups of four pixels (< 2^30: launcher)
+    const int stride = gridDim.x * NT;
+    constexpr int U = 2;
+    for (int g0 = blockIdx.x * NT + threadIdx.x; g0 < total; g0 += stride * U) {
+        float4 fx[U], fy[U], d[U];
+        int fr[U], y[U], x[U];
+        bool ok[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {     // every load of the group before the first store / RED
+            const int g = min(g0 + k * stride, total - 1);
+            ok[k] = g0 + k * stride < total;
+            fr[k] = div_hw4.quot(g);
+            const int r = g - fr[k] * HW4;
+            y[k] = div_w4.quot(r);
+            x[k] = (r - y[k] * W4) << 2;
+            const size_t pix = (size_t)y[k] * W + x[k];
+            const float *fl = flow + (size_t)(b0 + fr[k]) * 2 * HW + pix;
+            fx[k] = ld_stream4(fl);
+            fy[k] = ld_stream4(fl + HW);
+            d[k] = DEPTH ? ld_stream4(depth + (size_t)(b0 + fr[k]) * HW + pix) : make_float4(1.f, 1.f, 1.f, 1.f);
         }
-        return;
-    }
-    // finish worker.  Prologue: scratch images 1 .. nbuf-1 (image 0 was cleared on the stream).
-    for (size_t i = HW + (size_t)worker * NT + threadIdx.x; i < (size_t)nbuf * HW; i += (size_t)workers * NT) __stcg(S + i, zero4);
-    cta_signal(&ctl->pre_done);
-    const int gwarp = worker * WARPS + (threadIdx.x >> 5), nwarps = workers * WARPS;
-    for (int f = 0; f < B; ++f) {
-        cta_wait(&fctl[f].s_done, workers);
-        finish_frame(S + (size_t)(f % nbuf) * HW, count + (size_t)f * HW, out + (size_t)f * 2 * HW,
-                     rowmask ? rowmask + (size_t)f * H * bw : nullptr, colmask ? colmask + (size_t)f * HB * W : nullptr,
-                     hlist, &ctl->h_count, (unsigned)((size_t)f * HW), H, W, gwarp, nwarps, div_bw);
-        cta_signal(&fctl[f].f_done);
-        // the image of the PREVIOUS frame goes back to the splat workers: every finish worker has long left it
-        const int fc = f - 1;
-        if (fc >= 0 && fc + nbuf < B) {
-            cta_wait(&fctl[fc].f_done, workers);
-            float4 *Sc = S + (size_t)(fc % nbuf) * HW;
-            for (size_t i = (size_t)worker * NT + threadIdx.x; i < HW; i += (size_t)workers * NT) __stcg(Sc + i, zero4);
-            cta_signal(&fctl[fc].c_done);
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+            if (!ok[k]) continue;
+            float4 *Sf = S + (size_t)fr[k] * HW;
+            if (clear) {
+                float4 *c = clear + (size_t)fr[k] * HW + (size_t)y[k] * W + x[k];
+                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+                __stcg(c, z); __stcg(c + 1, z); __stcg(c + 2, z); __stcg(c + 3, z);
+            }
+            const float fxs[4] = {fx[k].x, fx[k].y, fx[k].z, fx[k].w}, fys[4] = {fy[k].x, fy[k].y, fy[k].z, fy[k].w};
+            const float ds[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const Corners c = corners(x[k] + j, y[k], fxs[j], fys[j], W, H);
+                if (!c.in_range) continue;
+                const float vx = DEPTH ? -ds[j] * fxs[j] : -fxs[j], vy = DEPTH ? -ds[j] * fys[j] : -fys[j];   // :75-88 / depth :77-92
+                atomicAdd(Sf + (size_t)c.T * W + c.L, make_float4(vx, vy, ds[j], 0.0f));   // REDG.F32x4
+            }
         }
     }
+    grid_launch_dependents();
 }
 
-// Fills the holes the pipeline listed (entries: frame * H * W + pixel).  A separate launch: the bitmaps, counts and
-// outputs are final and the scans may use the read-only path.
-__global__ void __launch_bounds__(256)
-projection_fill_list_kernel(const float *__restrict__ count, float *__restrict__ out, const unsigned *__restrict__ rowmask,
-                            const unsigned char *__restrict__ colmask, const unsigned *__restrict__ hlist,
-                            const Ctl *__restrict__ ctl, int H, int W, const FastDiv div_w)
+// OR of a 4-bit nibble per lane over groups of eight lanes: lane 8b + i contributes bits 4i .. 4i+3 of word b
+__device__ __forceinline__ unsigned gather_nibbles(unsigned nib, int lane)
 {
-    const unsigned n = ctl->h_count;
-    const size_t HW = (size_t)H * W;
-    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3;
-    for (unsigned q = blockIdx.x * blockDim.x + threadIdx.x; q < n; q += gridDim.x * blockDim.x) {
-        const unsigned p = __ldg(hlist + q);
-        const unsigned fr = p / (unsigned)HW, pix = p - fr * (unsigned)HW;     // one 32-bit division per hole
-        const int y = div_w.quot((int)pix), x = (int)pix - y * W;
-        fill_one<false>(count + (size_t)fr * HW, out + (size_t)fr * 2 * HW, rowmask + (size_t)fr * H * bw,
-                        colmask + (size_t)fr * HB * W, x, y, H, W);
-    }
+    unsigned w = nib << ((lane & 7) * 4);
+    w |= __shfl_xor_sync(0xffffffffu, w, 1);
+    w |= __shfl_xor_sync(0xffffffffu, w, 2);
+    w |= __shfl_xor_sync(0xffffffffu, w, 4);
+    return w;
 }
 
-}  // namespace pipe
+constexpr int F4_ROWS = 2;     // rows whose loads a warp keeps in flight
+__global__ void __launch_bounds__(NT, 1)
+projection_finish4_kernel(const float4 *__restrict__ S, int nb, float *__restrict__ count, float *__restrict__ out,
+                          unsigned *__restrict__ rowmask, unsigned long long *__restrict__ colmask, unsigned *__restrict__ holemask,
+                          int H, int W, const FastDiv div_bw4, const FastDiv div_items)
+{
+    grid_dependency_wait();
+    const int lane = threadIdx.x & 31;
+    // warp items: 128 columns x 8 rows
+    const int bw4 = (W + 127) >> 7, bw = (W + 31) >> 5, HB = (H + FIN_ROWS - 1) / FIN_ROWS, nitems = bw4 * HB, total = nitems * nb;
+    const size_t HW = (size_t)H * W;
+    const int gwarp = blockIdx.x * WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * WARPS;
+    for (int g = gwarp; g < total; g += nwarps) {
+        const int f = div_items.quot(g), it = g - f * nitems;
+        const float4 *Sf = S + (size_t)f * HW;
+        float *cn = count + (size_t)f * HW, *ou = out + (size_t)f * 2 * HW, *ov = ou + HW;
+        const int seg = div_bw4.quot(it), x0 = (it - seg * bw4) << 7, x = x0 + 4 * lane;     // this lane: columns x .. x+3
+        const int y0 = seg * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
+        const bool col_ok = x < W;          // W % 4 == 0: all four or none
+        // one row of cells: this lane's four and the cell left of them (lane 0: from memory, else from the lane before)
+        auto load = [&](int y, bool valid, float4 (&c)[4], float4 &edge) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            c[0] = c[1] = c[2] = c[3] = edge = z;
+            if (valid && col_ok) {
+                const float4 *row = Sf + (size_t)y * W + x;
+                c[0] = __ldcg(row); c[1] = __ldcg(row + 1); c[2] = __ldcg(row + 2); c[3] = __ldcg(row + 3);
+                if (lane == 0 && x > 0) edge = __ldcg(row - 1);
+            }
+        };
+        // horizontal half of the box for the four cells: wx(x,0) * S[x] + S[x-1]
+        auto hsum = [&](const float4 (&c)[4], const float4 &edge, float4 (&h)[4]) {
+            float4 left;
+            left.x = __shfl_up_sync(0xffffffffu, c[3].x, 1);
+            left.y = __shfl_up_sync(0xffffffffu, c[3].y, 1);
+            left.z = __shfl_up_sync(0xffffffffu, c[3].z, 1);
+            if (lane == 0) left = edge;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float w0 = (x + j == W - 1) ? 2.0f : 1.0f;
+                const float4 &l = j == 0 ? left : c[j - 1];
+                h[j] = make_float4(w0 * c[j].x + l.x, w0 * c[j].y + l.y, w0 * c[j].z + l.z, 0.f);
+            }
+        };
+        float4 prev[4];
+        {
+            float4 c[4], e;
+            load(max(y0 - 1, 0), y0 > 0, c, e);
+            hsum(c, e, prev);
+        }
+        unsigned colbits[4] = {0u, 0u, 0u, 0u}, myhole = 0;
+#pragma unroll
+        for (int ybk = 0; ybk < FIN_ROWS; ybk += F4_ROWS) {
+            float4 cur[F4_ROWS][4], edge[F4_ROWS];
+#pragma unroll
+            for (int k = 0; k < F4_ROWS; ++k) load(min(y0 + ybk + k, H - 1), y0 + ybk + k < y1, cur[k], edge[k]);
+#pragma unroll
+            for (int k = 0; k < F4_ROWS; ++k) {
+                const int y = y0 + ybk + k;
+                float4 h[4];
+                hsum(cur[k], edge[k], h);
+                const float w0 = (y == H - 1) ? 2.0f : 1.0f;
+                const bool live = y < y1 && col_ok;
+                float su[4], sv[4], sc[4];
+                unsigned src_nib = 0, hole_nib = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    su[j] = w0 * h[j].x + prev[j].x; sv[j] = w0 * h[j].y + prev[j].y; sc[j] = w0 * h[j].z + prev[j].z;
+                    prev[j] = h[j];
+                    if (sc[j] > 0.0f) { su[j] = su[j] / sc[j]; sv[j] = sv[j] / sc[j]; }   // :130-134
+                    if (live && sc[j] != 0.0f) src_nib |= 1u << j;
+                    if (live && !(sc[j] > 0.0f)) hole_nib |= 1u << j;                    // count <= 0 (:171)
+                }
+                if (live) {
+                    const size_t a = (size_t)y * W + x;
+                    st_stream4(cn + a, make_float4(sc[0], sc[1], sc[2], sc[3]));
+                    st_stream4(ou + a, make_float4(su[0], su[1], su[2], su[3]));
+                    st_stream4(ov + a, make_float4(sv[0], sv[1], sv[2], sv[3]));
+                }
+                if (rowmask) {   // uniform
+                    const unsigned srcw = gather_nibbles(src_nib, lane), holew = gather_nibbles(hole_nib, lane);
+                    const int wx = (x0 >> 5) + (lane >> 3);                               // this lane group's 32-column word
+                    if ((lane & 7) == 0 && y < y1 && wx < bw) rowmask[((size_t)f * H + y) * bw + wx] = srcw;
+                    if ((lane & 7) == ybk + k) myhole = holew;                            // lane 8b + r keeps row r of block b
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) colbits[j] |= (src_nib >> j & 1u) << (ybk + k);
+                }
+            }
+        }
+        if (rowmask) {
+            if (col_ok) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) *colmask_byte(colmask + (size_t)f * W * colwords(H), x + j, seg, H) = (unsigned char)colbits[j];
+            }
+            const int wx = (x0 >> 5) + (lane >> 3);
+            if (wx < bw) holemask[(((size_t)f * HB + seg) * bw + wx) * FIN_ROWS + (lane & 7)] = myhole;
+        }
+    }
+    grid_launch_dependents();
+}
+
+}  // namespace pf
 
 // backward gather (:266-297; depth :276-337)
 template <bool DEPTH>
@@ -623,14 +725,15 @@ mindepth_select_kernel(const float *__restrict__ flow, const float *__restrict__
 
 __global__ void __launch_bounds__(32 * FIN_WARPS)
 mindepth_resolve_kernel(const unsigned long long *__restrict__ keys, const float *__restrict__ flow, float *__restrict__ count,
-                        float *__restrict__ out, unsigned *__restrict__ rowmask, unsigned char *__restrict__ colmask, int H, int W)
+                        float *__restrict__ out, unsigned *__restrict__ rowmask, unsigned long long *__restrict__ colmask,
+                        unsigned *__restrict__ holemask, int H, int W)
 {
     const int lane = threadIdx.x, x = (blockIdx.x * FIN_WARPS + threadIdx.y) * 32 + lane;
     if ((blockIdx.x * FIN_WARPS + threadIdx.y) * 32 >= W) return;   // whole warp outside
     const int b = blockIdx.z, y0 = blockIdx.y * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
     const size_t HW = (size_t)H * W;
     const float *fu = flow + (size_t)b * 2 * HW, *fv = fu + HW;
-    unsigned colbits = 0;
+    unsigned colbits = 0, holeword = 0;
     for (int y = y0; y < y0 + FIN_ROWS; ++y) {
         const bool live = y < y1 && x < W;
         float cnt = 0.0f, u = 0.0f, v = 0.0f;
@@ -652,9 +755,13 @@ mindepth_resolve_kernel(const unsigned long long *__restrict__ keys, const float
             const unsigned m = __ballot_sync(0xffffffffu, src_ok);
             if (lane == 0 && y < y1) rowmask[((size_t)b * H + y) * ((W + 31) >> 5) + (x >> 5)] = m;
             colbits |= (src_ok ? 1u : 0u) << (y - y0);
+            const unsigned hm = __ballot_sync(0xffffffffu, live && !(cnt > 0.0f));
+            if (lane == y - y0) holeword = hm;
         }
     }
-    if (colmask && x < W) colmask[((size_t)b * ((H + 7) >> 3) + blockIdx.y) * W + x] = (unsigned char)colbits;
+    if (colmask && x < W) *colmask_byte(colmask + (size_t)b * W * colwords(H), x, blockIdx.y, H) = (unsigned char)colbits;
+    if (holemask && lane < FIN_ROWS)
+        holemask[(((size_t)b * ((H + 7) >> 3) + blockIdx.y) * ((W + 31) >> 5) + (x >> 5)) * FIN_ROWS + lane] = holeword;
 }
 
 // backward (:216-312): a source pixel receives -gradoutput of each of its four corners whose count equals its input2
@@ -689,74 +796,115 @@ mindepth_backward_kernel(const float *__restrict__ flow, const float *__restrict
 namespace {
 
 // ---- host side of the fused pipeline ------------------------------------------------------------------------
-std::atomic<int> g_projection_path{0};     // test hook: 0 = automatic, 1 = three-kernel path, 2 = fused pipeline
+// test hook: 0 = automatic (= 3), 1 = whole-batch kernels, 2 = L2-resident chunks with persistent kernels, 3 = the same with programmatic
+// dependent launch, 4 = as 3 but never the four-pixels-per-thread kernels
+std::atomic<int> g_projection_path{0};
 inline int forced_projection_path() { return g_projection_path.load(std::memory_order_relaxed); }
+std::atomic<long long> g_chunk_bytes{0};    // test hook: scratch budget of a chunk (0 = pf::CHUNK_BYTES)
 
-static int pipeline_grid(const void *kernel)
+// the hole-filling bitmaps of a batch inside one scratch block: [column bitmap (64-bit words) | row bitmap | hole bitmask]
+struct FillMaps {
+    unsigned long long *colmask; unsigned *rowmask, *holemask;
+    size_t colmask_bytes, bytes;
+};
+static FillMaps fill_maps(char *base, int B, int H, int W, bool enabled)
 {
-    int dev = 0, coop = 0, per_sm = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop ||
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, pipe::NT, 0) != cudaSuccess || per_sm < 1) {
-        (void)cudaGetLastError();
-        return 0;
+    FillMaps m{nullptr, nullptr, nullptr, 0, 0};
+    if (!enabled) return m;
+    const size_t bw = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
+    m.colmask_bytes = sizeof(unsigned long long) * B * W * colwords(H);
+    const size_t rowmask_bytes = sizeof(unsigned) * B * H * bw, holemask_bytes = sizeof(unsigned) * B * HB * bw * FIN_ROWS;
+    m.bytes = m.colmask_bytes + rowmask_bytes + holemask_bytes;
+    if (base) {
+        m.colmask = reinterpret_cast<unsigned long long *>(base);
+        m.rowmask = reinterpret_cast<unsigned *>(base + m.colmask_bytes);
+        m.holemask = reinterpret_cast<unsigned *>(base + m.colmask_bytes + rowmask_bytes);
     }
-    const int sms = sm_count();
-    return (per_sm >= 2 ? 2 * sms : sms) & ~1;      // one splat and one finish worker per SM when both fit
+    return m;
 }
 
-template <bool DEPTH>
-int projection_forward_pipelined(const FlowSource fs, const float *depth, float *count, float *out,
-                                 int B, int H, int W, int fillhole, cudaStream_t s)
+// launch of the mask-walking hole filling for a whole batch (shared by every forward path)
+static int launch_fill(const float *count, float *out, const FillMaps &m, int B, int H, int W, cudaStream_t s)
 {
-    using namespace pipe;
-    auto kernel = projection_pipeline_kernel<DEPTH>;
-    const int grid = pipeline_grid((const void *)kernel);
+    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3;
+    const long long total = (long long)B * bw * HB;
+    if (total >= (1ll << 31)) return VFIDKR_ERR_ARG;
+    const unsigned nb = (unsigned)std::min<long long>((total + FILL_WARPS - 1) / FILL_WARPS, (long long)sm_count() * 8);
+    projection_fill_mask_kernel<<<nb, 32 * FILL_WARPS, 0, s>>>(count, out, m.rowmask, m.colmask, m.holemask, B, H, W,
+                                                              FastDiv((unsigned)(bw * HB)), FastDiv((unsigned)bw));
+    note_launch();
+    return check_launch("flow projection hole filling");
+}
+
+template <typename... Params, typename... Args>
+static cudaError_t launch_persistent(void (*kernel)(Params...), unsigned grid, bool pdl, cudaStream_t s, Args... args)
+{
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(pf::NT);
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
+}
+
+// chunks of frames whose scratch stays in L2, persistent kernels (see namespace pf)
+template <bool DEPTH>
+int projection_forward_chunked(const FlowSource fs, const float *depth, float *count, float *out,
+                               int B, int H, int W, int fillhole, bool pdl, cudaStream_t s)
+{
+    using namespace pf;
     const size_t HW = (size_t)H * W;
-    if (grid < 2 || (fillhole && (unsigned long long)B * HW >= (1ull << 32))) return -1;   // hole-list entries are 32-bit
-    const int nbuf = std::min(B, NB_MAX);
-    const size_t WW = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
-    // one stream-ordered block: [scratch images | row bitmaps | column bitmaps | hole list | counters]
-    const size_t s_bytes = sizeof(float4) * HW * nbuf;
-    const size_t rowmask_bytes = fillhole ? sizeof(unsigned) * B * H * WW : 0;
-    const size_t colmask_bytes = fillhole ? (((size_t)B * HB * W + 15) & ~(size_t)15) : 0;
-    const size_t hlist_bytes = fillhole ? sizeof(unsigned) * B * HW : 0;     // worst case: every pixel a hole
-    const size_t ctl_bytes = sizeof(Ctl) + sizeof(FrameCtl) * B;
-    void *mem = nullptr;
-    int e = stream_scratch_alloc(&mem, s_bytes + rowmask_bytes + colmask_bytes + hlist_bytes + ctl_bytes, s);
+    const long long forced_budget = g_chunk_bytes.load(std::memory_order_relaxed);
+    const size_t budget = forced_budget > 0 ? (size_t)forced_budget : CHUNK_BYTES;
+    const int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, budget / (sizeof(float4) * HW)));
+    const int nchunks = (B + per_chunk - 1) / per_chunk;
+    const size_t chunk_cells = (size_t)per_chunk * HW;
+    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3;
+    if ((long long)per_chunk * bw * HB >= (1ll << 31) || (long long)per_chunk * bw * ((H + 15) >> 4) >= (1ll << 30)) return -1;
+    // one stream-ordered block: [scratch image(s) | bitmaps for the hole filling]
+    const size_t scratch_bytes = sizeof(float4) * chunk_cells * (nchunks > 1 ? 2 : 1);
+    void *scratch = nullptr;
+    int e = stream_scratch_alloc(&scratch, scratch_bytes + fill_maps(nullptr, B, H, W, fillhole).bytes, s);
     if (e) return e;
-    char *base = static_cast<char *>(mem);
-    float4 *S = reinterpret_cast<float4 *>(base);
-    unsigned *rowmask = fillhole ? reinterpret_cast<unsigned *>(base + s_bytes) : nullptr;
-    unsigned char *colmask = fillhole ? reinterpret_cast<unsigned char *>(base + s_bytes + rowmask_bytes) : nullptr;
-    unsigned *hlist = fillhole ? reinterpret_cast<unsigned *>(base + s_bytes + rowmask_bytes + colmask_bytes) : nullptr;
-    Ctl *ctl = reinterpret_cast<Ctl *>(base + s_bytes + rowmask_bytes + colmask_bytes + hlist_bytes);
-    FrameCtl *fctl = reinterpret_cast<FrameCtl *>(ctl + 1);
-    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * HW, s), "clear projection scratch image 0");
-    if (!e) e = set_error(cudaMemsetAsync(ctl, 0, ctl_bytes, s), "clear projection pipeline counters");
-    if (!e) {
-        FlowSource fsv = fs;
-        const float *depth_v = depth;
-        int nbuf_v = nbuf, Bv = B, Hv = H, Wv = W;
-        FastDiv div_tx((unsigned)((W + 31) >> 5)), div_bw((unsigned)((W + 31) >> 5));
-        void *args[] = {&fsv, &depth_v, &S, &nbuf_v, &count, &out, &rowmask, &colmask, &hlist, &ctl, &fctl, &Bv, &Hv, &Wv,
-                        &div_tx, &div_bw};
-        const cudaError_t le = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(NT), args, 0, s);
-        if (le == cudaErrorCooperativeLaunchTooLarge || le == cudaErrorNotSupported) {
-            (void)cudaGetLastError();
-            cudaFreeAsync(mem, s);
-            return -1;
+    float4 *S = static_cast<float4 *>(scratch);
+    const FillMaps fm = fill_maps(static_cast<char *>(scratch) + scratch_bytes, B, H, W, fillhole);
+    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * chunk_cells, s), "clear projection scratch");
+    if (!e && fillhole) e = set_error(cudaMemsetAsync(fm.colmask, 0, fm.colmask_bytes, s), "clear column bitmap");   // rows past H stay 0
+    const unsigned grid = 2u * (unsigned)sm_count();
+    // four pixels per thread when rows are whole float4s and everything is 16-byte aligned (not for the low-resolution flow source)
+    const bool four = !fs.lowres && W % 4 == 0 && aligned16(fs.flow) && aligned16(count) && aligned16(out) && (!DEPTH || aligned16(depth)) &&
+                      (long long)per_chunk * H * (W >> 2) < (1ll << 30) && forced_projection_path() != 4;
+    const FastDiv div_tx((unsigned)bw), div_tiles((unsigned)(bw * ((H + 15) >> 4))), div_bw((unsigned)bw), div_items((unsigned)(bw * HB));
+    for (int c = 0; c < nchunks && !e; ++c) {
+        const int b0 = c * per_chunk, nb = std::min(per_chunk, B - b0);
+        float4 *cur = S + (size_t)(c & 1) * chunk_cells;
+        float4 *nxt = (c + 1 < nchunks) ? S + (size_t)((c + 1) & 1) * chunk_cells : nullptr;
+        // (the next chunk may be shorter than this one; clearing nb frames of it is always enough or more)
+        unsigned *rm = fillhole ? fm.rowmask + (size_t)b0 * H * bw : nullptr, *hm = fillhole ? fm.holemask + (size_t)b0 * HB * bw * FIN_ROWS : nullptr;
+        unsigned long long *cm = fillhole ? fm.colmask + (size_t)b0 * W * colwords(H) : nullptr;
+        if (four) {
+            e = set_error(launch_persistent(projection_splat4_kernel<DEPTH>, grid, pdl && c > 0, s, fs.flow, b0, nb, depth, cur, nxt, H, W,
+                                            FastDiv((unsigned)(W >> 2)), FastDiv((unsigned)(H * (W >> 2)))), "flow projection splat");
+            if (!e) e = set_error(launch_persistent(projection_finish4_kernel, (unsigned)sm_count(), pdl, s, (const float4 *)cur, nb,
+                                                    count + (size_t)b0 * HW, out + (size_t)b0 * 2 * HW, rm, cm, hm, H, W,
+                                                    FastDiv((unsigned)((W + 127) >> 7)), FastDiv((unsigned)(((W + 127) >> 7) * HB))),
+                                  "flow projection box pass");
+        } else {
+            e = set_error(launch_persistent(projection_splat_chunk_kernel<DEPTH>, grid, pdl && c > 0, s, fs, b0, nb, depth, cur, nxt, H, W,
+                                            div_tx, div_tiles), "flow projection splat");
+            if (!e) e = set_error(launch_persistent(projection_finish_chunk_kernel, grid, pdl, s, (const float4 *)cur, nb, count + (size_t)b0 * HW,
+                                                    out + (size_t)b0 * 2 * HW, rm, cm, hm, H, W, div_bw, div_items), "flow projection box pass");
         }
-        e = set_error(le, "flow projection forward (pipelined)");
-        if (!e) { note_launch(); e = check_launch("flow projection forward (pipelined)"); }
-        if (!e && fillhole) {
-            // the list length lives on the device: a fixed grid strides over it
-            const unsigned nb = (unsigned)std::min<size_t>(((size_t)B * HW + 255) / 256, (size_t)sm_count() * 8);
-            projection_fill_list_kernel<<<nb, 256, 0, s>>>(count, out, rowmask, colmask, hlist, ctl, H, W, FastDiv((unsigned)W));
-            note_launch();
-            e = check_launch("flow projection hole filling (list)");
-        }
+        note_launch(2);
     }
-    const int e2 = set_error(cudaFreeAsync(mem, s), "projection scratch (cudaFreeAsync)");
+    if (!e) e = check_launch("flow projection forward");
+    if (!e && fillhole) e = launch_fill(count, out, fm, B, H, W, s);
+    const int e2 = set_error(cudaFreeAsync(scratch, s), "projection scratch (cudaFreeAsync)");
     return e ? e : e2;
 }
 
@@ -768,51 +916,31 @@ int projection_forward(const FlowSource fs, const float *depth, float *count, fl
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !flow || !count || !out || (DEPTH && !depth)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
-    if (B >= 2 && forced_projection_path() != 1) {
-        const int e = projection_forward_pipelined<DEPTH>(fs, depth, count, out, B, H, W, fillhole, s);
-        if (e >= 0) return e;     // -1: cooperative launch not possible here -> the three-kernel path below
+    if (forced_projection_path() != 1) {
+        const int e = projection_forward_chunked<DEPTH>(fs, depth, count, out, B, H, W, fillhole, forced_projection_path() != 2, s);
+        if (e >= 0) return e;     // -1: index ranges of the persistent kernels exceeded -> the three-kernel path below
     }
-    // Frames are processed in chunks whose scratch image (16 B per pixel) is at most SCRATCH_BYTES; two such buffers
-    // alternate and the splat of one chunk clears the buffer of the next.  Keeping the scratch L2-RESIDENT (one 1080p
-    // frame, 36 MB, per chunk) was measured: the splat's DRAM traffic fell from 731 MB to its 219 MB of input, its time
-    // did not move (the L2 atomic unit bounds it either way) and sixteen small launches cost 5 % more than two large
-    // ones -- so the budget is generous and only very large batches are chunked.
-    constexpr size_t SCRATCH_BYTES = (size_t)512 << 20;
-    const int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, SCRATCH_BYTES / (sizeof(float4) * HW)));
-    const int nchunks = (B + per_chunk - 1) / per_chunk;
-    const size_t chunk_cells = (size_t)per_chunk * HW;
-    // one stream-ordered block: [scratch image(s) | row bitmap | column bitmap] (bitmaps only for hole filling)
-    const size_t scratch_bytes = sizeof(float4) * chunk_cells * (nchunks > 1 ? 2 : 1);
+    // Round-1 path, kept as the fallback and as a reference implementation for the tests: ONE splat and ONE box pass
+    // over the whole batch, one pixel / one 32 x 8 block per thread / warp, scratch image of the batch in DRAM.
     const size_t WW = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
-    const size_t rowmask_bytes = fillhole ? sizeof(unsigned) * B * H * WW : 0, colmask_bytes = fillhole ? (size_t)B * HB * W : 0;
+    const size_t scratch_bytes = sizeof(float4) * B * HW;
     void *scratch = nullptr;
-    int e = stream_scratch_alloc(&scratch, scratch_bytes + rowmask_bytes + colmask_bytes, s);
+    int e = stream_scratch_alloc(&scratch, scratch_bytes + fill_maps(nullptr, B, H, W, fillhole).bytes, s);
     if (e) return e;
     float4 *S = static_cast<float4 *>(scratch);
-    unsigned *rowmask = fillhole ? reinterpret_cast<unsigned *>(static_cast<char *>(scratch) + scratch_bytes) : nullptr;
-    unsigned char *colmask = fillhole ? reinterpret_cast<unsigned char *>(rowmask) + rowmask_bytes : nullptr;
-    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * chunk_cells, s), "clear projection scratch");
+    const FillMaps fm = fill_maps(static_cast<char *>(scratch) + scratch_bytes, B, H, W, fillhole);
+    e = set_error(cudaMemsetAsync(S, 0, scratch_bytes, s), "clear projection scratch");
+    if (!e && fillhole) e = set_error(cudaMemsetAsync(fm.colmask, 0, fm.colmask_bytes, s), "clear column bitmap");
     if (!e) {
-        for (int c = 0; c < nchunks; ++c) {
-            const int b0 = c * per_chunk, nb = std::min(per_chunk, B - b0);
-            float4 *cur = S + (size_t)(c & 1) * chunk_cells;
-            float4 *nxt = (c + 1 < nchunks) ? S + (size_t)((c + 1) & 1) * chunk_cells : nullptr;
-            dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), nb);
-            // the next chunk may be shorter than this one; clearing nb frames of it is always enough or more
-            projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(fs, b0, DEPTH ? depth + (size_t)b0 * HW : nullptr, cur, nxt, H, W);
-            dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), nb);
-            projection_finish_kernel<<<fgrid, fblock, 0, s>>>(cur, count + (size_t)b0 * HW, out + (size_t)b0 * 2 * HW,
-                                                              fillhole ? rowmask + (size_t)b0 * H * WW : nullptr,
-                                                              fillhole ? colmask + (size_t)b0 * HB * W : nullptr, H, W);
-            note_launch(2);
-        }
-        if (fillhole) {
-            dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
-            projection_fillhole_kernel<<<grid, block, 0, s>>>(count, out, rowmask, colmask, H, W);
-            note_launch();
-        }
+        dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
+        projection_splat_kernel<DEPTH><<<grid, block, 0, s>>>(fs, 0, depth, S, nullptr, H, W);
+        dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), B);
+        projection_finish_kernel<<<fgrid, fblock, 0, s>>>(S, count, out, fm.rowmask, fm.colmask, fm.holemask, H, W);
+        note_launch(2);
         e = check_launch("flow projection forward");
+        if (!e && fillhole) e = launch_fill(count, out, fm, B, H, W, s);
     }
+    (void)WW; (void)HB;
     const int e2 = set_error(cudaFreeAsync(scratch, s), "projection scratch (cudaFreeAsync)");
     return e ? e : e2;
 }
@@ -837,8 +965,8 @@ using namespace vfidkr;
 
 VFIDKR_API int vfidkr_debug_force_projection_path(int path)
 {
-    if (path == 100) return pipeline_grid((const void *)pipe::projection_pipeline_kernel<true>);   // query: CTAs of the pipeline grid
-    if (path < 0 || path > 2) return -1;
+    if (path >= 1000) { g_chunk_bytes.store((long long)(path - 1000) << 10, std::memory_order_relaxed); return 0; }   // chunk budget in KiB (1000 = default)
+    if (path < 0 || path > 4) return -1;
     return g_projection_path.exchange(path, std::memory_order_relaxed);
 }
 
@@ -867,27 +995,24 @@ VFIDKR_API int vfidkr_mindepthflowprojection_forward(const float *input1, const 
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !input1 || !input2 || !count || !output) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    const size_t HW = (size_t)H * W, WW = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
+    const size_t HW = (size_t)H * W;
     const size_t key_bytes = sizeof(unsigned long long) * B * HW;
-    const size_t rowmask_bytes = fillhole ? sizeof(unsigned) * B * H * WW : 0, colmask_bytes = fillhole ? (size_t)B * HB * W : 0;
     void *mem = nullptr;
-    int e = stream_scratch_alloc(&mem, key_bytes + rowmask_bytes + colmask_bytes, s);
+    int e = stream_scratch_alloc(&mem, key_bytes + fill_maps(nullptr, B, H, W, fillhole).bytes, s);
     if (e) return e;
     unsigned long long *keys = static_cast<unsigned long long *>(mem);
-    unsigned *rowmask = fillhole ? reinterpret_cast<unsigned *>(static_cast<char *>(mem) + key_bytes) : nullptr;
-    unsigned char *colmask = fillhole ? reinterpret_cast<unsigned char *>(rowmask) + rowmask_bytes : nullptr;
+    const FillMaps fm = fill_maps(static_cast<char *>(mem) + key_bytes, B, H, W, fillhole);
+    if (fillhole) e = set_error(cudaMemsetAsync(fm.colmask, 0, fm.colmask_bytes, s), "clear column bitmap");
+    if (e) { cudaFreeAsync(mem, s); return e; }
     e = set_error(cudaMemsetAsync(keys, 0, key_bytes, s), "clear min-depth keys");
     if (!e) {
         dim3 block(BX, BY), grid(ceil_div(W, BX), ceil_div(H, BY), B);
         mindepth_select_kernel<<<grid, block, 0, s>>>(input1, input2, keys, H, W);
         dim3 fblock(32, FIN_WARPS), fgrid(ceil_div(W, 32 * FIN_WARPS), ceil_div(H, FIN_ROWS), B);
-        mindepth_resolve_kernel<<<fgrid, fblock, 0, s>>>(keys, input1, count, output, rowmask, colmask, H, W);
+        mindepth_resolve_kernel<<<fgrid, fblock, 0, s>>>(keys, input1, count, output, fm.rowmask, fm.colmask, fm.holemask, H, W);
         note_launch(2);
-        if (fillhole) {
-            projection_fillhole_kernel<<<grid, block, 0, s>>>(count, output, rowmask, colmask, H, W);
-            note_launch();
-        }
         e = check_launch("min-depth flow projection forward");
+        if (!e && fillhole) e = launch_fill(count, output, fm, B, H, W, s);
     }
     const int e2 = set_error(cudaFreeAsync(mem, s), "min-depth scratch (cudaFreeAsync)");
     return e ? e : e2;
