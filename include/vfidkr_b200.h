@@ -63,12 +63,6 @@ const char *vfidkr_last_error(void);
  * 0 = automatic (production), 1 = strip kernels, 2 = tile kernel, 3 = direct kernels -- so that the parity tests
  * can hold every implementation to the oracle.  Process-wide; returns the previous setting, -1 on a bad value. */
 int vfidkr_debug_force_forward_path(int path);
-/* TEST HOOK: implementation of the Flow / DepthFlow projection forwards -- 0 = automatic, 1 = one splat and one box
- * pass over the whole batch (scratch image of the batch in DRAM), 2 = chunks of frames whose scratch stays in L2, persistent
- * kernels, 3 = the same with programmatic dependent launch (what automatic selects).  1000 + k: scratch budget of a chunk
- * = k KiB (1000: the default, 40 MiB), so that small test shapes run through many chunks.  Process-wide; returns the
- * previous setting (0 for the budget call), -1 on a bad value. */
-int vfidkr_debug_force_projection_path(int path);
 /* Return the scratch memory the library's private pool has cached on the current device to the device
  * (see "Common contract"; blocks still in use by enqueued work are not affected).  No reference counterpart. */
 int vfidkr_trim_scratch(void);

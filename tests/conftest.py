@@ -51,8 +51,6 @@ def _forward_path_is_automatic_again():
     mod = sys.modules.get("vfidkr_b200")
     if mod is not None and getattr(mod._lib, "_lib", None) is not None:
         mod.debug_force_forward_path(None)
-        mod.debug_force_projection_path(None)
-        mod.debug_projection_chunk_kib(0)
 
 
 def pytest_terminal_summary(terminalreporter):

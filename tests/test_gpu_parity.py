@@ -228,17 +228,15 @@ def test_flowprojection_count_is_bit_exact(lib, oracle):
     assert np.array_equal(host(count).astype(np.float64), cnt)
 
 
-PATHS = ("kernels", "chunks", "chunks_pdl", "chunks_1px")
-PIPE_SHAPES = [(2, 37, 29, "stress"), (3, 97, 131, "stress"), (8, 256, 448, "gauss"), (5, 64, 200, "smooth"),
+PROJ_SHAPES = [(2, 37, 29, "stress"), (3, 97, 131, "stress"), (8, 256, 448, "gauss"), (5, 64, 200, "smooth"),
                (2, 1, 1, "unit"), (4, 9, 33, "unit"), (7, 40, 96, "gauss"), (3, 67, 132, "stress"), (2, 130, 260, "stress"), (1, 23, 4, "unit")]
 
 
-@pytest.mark.parametrize("B,H,W,fk", PIPE_SHAPES)
+@pytest.mark.parametrize("B,H,W,fk", PROJ_SHAPES)
 @pytest.mark.parametrize("with_depth", [False, True])
-def test_projection_pipeline_and_three_kernel_paths(lib, oracle, B, H, W, fk, with_depth):
-    """The chunked forward (L2-resident scratch images alternating between chunks of frames, persistent splat / box-pass
-    kernels, with and without programmatic dependent launch) against the oracle and against the whole-batch kernels, with
-    and without hole filling: ragged shapes, one-pixel frames, holes, batches of one and of many chunks."""
+def test_projection_forward_through_the_c_abi(lib, oracle, B, H, W, fk, with_depth):
+    """Splat + box pass + bitmask-driven hole filling (64-row column words, dense lanes) through the C ABI, with and
+    without hole filling: ragged shapes, one-pixel frames, heights that are not a multiple of 8 / 64, wide holes."""
     from vfidkr_b200 import _lib
     from vfidkr_b200._common import ptr, stream_ptr
     r = U.rng(1350 + B + H)
@@ -246,45 +244,40 @@ def test_projection_pipeline_and_three_kernel_paths(lib, oracle, B, H, W, fk, wi
     d = U.depth_inv(r, B, H, W) if with_depth else None
     tf, td = cu(fl), (cu(d) if with_depth else None)
     sp = stream_ptr(tf.device)
-    res = {}
-    # a budget of ~1.5 frames: one frame per chunk, B chunks, the two scratch images alternate
-    lib.debug_projection_chunk_kib(max(1, 24 * H * W // 1024))
-    for path in PATHS:
-        lib.debug_force_projection_path(path)
-        for fill in (0, 1):
-            cnt, out = torch.full((B, 1, H, W), -7.0, device="cuda"), torch.full((B, 2, H, W), -7.0, device="cuda")
-            before = lib.launch_count()
-            if with_depth:
-                _lib.call("vfidkr_depthflowprojection_forward", ptr(tf), ptr(td), ptr(cnt), ptr(out), B, H, W, fill, sp)
-            else:
-                _lib.call("vfidkr_flowprojection_forward", ptr(tf), ptr(cnt), ptr(out), B, H, W, fill, sp)
-            torch.cuda.synchronize()
-            launches = lib.launch_count() - before
-            assert launches >= 2 + fill, (path, launches)
-            res[path, fill] = (host(out), host(cnt))
-    lib.debug_force_projection_path(None)
     for fill in (0, 1):
+        cnt, out = torch.full((B, 1, H, W), -7.0, device="cuda"), torch.full((B, 2, H, W), -7.0, device="cuda")
+        if with_depth:
+            _lib.call("vfidkr_depthflowprojection_forward", ptr(tf), ptr(td), ptr(cnt), ptr(out), B, H, W, fill, sp)
+        else:
+            _lib.call("vfidkr_flowprojection_forward", ptr(tf), ptr(cnt), ptr(out), B, H, W, fill, sp)
         ref, rc = oracle.flowprojection_forward(fl, d, fill)
-        for path in PATHS:
-            out, cnt = res[path, fill]
-            U.assert_close(out, ref, U.RTOL_ATOMIC, f"projection {path} fillhole={fill}")
-            if with_depth:
-                U.assert_close(cnt, rc, U.RTOL_ATOMIC, f"projection {path} count fillhole={fill}")
-            else:
-                assert np.array_equal(cnt.astype(np.float64), rc), f"{path}: FlowProjection counts are exact integers"
-        # the two implementations add the same fp32 terms per cell, in hardware order: equal to rounding
-        for path in PATHS[1:]:
-            assert U.max_err(res[path, fill][0], res["kernels", fill][0].astype(np.float64)) <= 2e-6
+        U.assert_close(host(out), ref, U.RTOL_ATOMIC, f"projection fillhole={fill}")
+        if with_depth:
+            U.assert_close(host(cnt), rc, U.RTOL_ATOMIC, f"projection count fillhole={fill}")
+        else:
+            assert np.array_equal(host(cnt).astype(np.float64), rc), "FlowProjection counts are exact integers"
 
 
-def test_projection_pipeline_is_repeatable_back_to_back(lib):
-    """Back-to-back launches on one stream reuse the cached scratch block (dirty images, stale counters): every launch
-    must clear what it needs itself."""
+def test_projection_hole_filling_across_tall_and_wide_holes(lib, oracle):
+    """Holes taller than one 64-row column word and wider than one 32-column row word, holes reaching the borders, and
+    a frame that is one hole (nothing to fill from)."""
+    B, H, W = 3, 200, 150
+    fl = np.zeros((B, 2, H, W), np.float32)
+    fl[0, 0, :, 40:] = 70.0                 # columns 40..109 empty over the full height
+    fl[1, 1, 30:, :] = 140.0                # rows 30..169 empty over the full width
+    fl[2, 0] = 3.0 * W                      # everything out of range
+    out = lib.FlowProjectionModule(False)(cu(fl))
+    ref, _ = oracle.flowprojection_forward(fl, None, 1)
+    U.assert_close(host(out), ref, U.RTOL_ATOMIC, "hole filling, large holes")
+    assert not host(out)[2].any()
+
+
+def test_projection_is_repeatable_back_to_back(lib):
+    """Back-to-back launches on one stream reuse the cached scratch block (dirty scratch image, stale bitmaps): every
+    launch must clear what it needs itself."""
     r = U.rng(1399)
     B, H, W = 6, 120, 168
     fl, d = cu(U.flow(r, B, H, W, "stress")), cu(U.depth_inv(r, B, H, W))
-    lib.debug_force_projection_path("chunks_pdl")
-    lib.debug_projection_chunk_kib(2 * 16 * H * W // 1024 + 1)       # two frames per chunk: three chunks
     mod = lib.DepthFlowProjectionModule(False)
     first = mod(fl, d).clone()
     for _ in range(5):
@@ -292,7 +285,6 @@ def test_projection_pipeline_is_repeatable_back_to_back(lib):
         again = mod(fl, d)
         assert torch.isfinite(other).all()
         assert (again - first).abs().max().item() <= 2e-5 * first.abs().max().item()
-    lib.debug_force_projection_path(None)
 
 
 def test_projection_known_answers_on_gpu(lib):

@@ -59,7 +59,6 @@ _SIGNATURES = {
     "vfidkr_abi_version": [],
     "vfidkr_trim_scratch": [],
     "vfidkr_debug_force_forward_path": [_I],
-    "vfidkr_debug_force_projection_path": [_I],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vfidkr_launch_count", "vfidkr_last_error"])
 
@@ -106,20 +105,6 @@ def debug_force_forward_path(path) -> int:
     prev = load().vfidkr_debug_force_forward_path(_PATHS[path])
     if prev < 0:
         raise VfidkrError("vfidkr_debug_force_forward_path rejected the value")
-    return prev
-
-
-def debug_projection_chunk_kib(kib: int = 0) -> None:
-    """TEST HOOK: scratch budget of one chunk of frames of the projection forward, in KiB (0 = default, 40 MiB)."""
-    load().vfidkr_debug_force_projection_path(1000 + int(kib))
-
-
-def debug_force_projection_path(path) -> int:
-    """TEST HOOK: None/"auto", "kernels" (round 1: one splat, one box pass over the whole batch), "chunks" (L2-resident
-    chunks, persistent kernels) or "chunks_pdl" (the same with programmatic dependent launch = automatic)."""
-    prev = load().vfidkr_debug_force_projection_path({None: 0, "auto": 0, "kernels": 1, "chunks": 2, "chunks_pdl": 3, "chunks_1px": 4}[path])
-    if prev < 0:
-        raise VfidkrError("vfidkr_debug_force_projection_path rejected the value")
     return prev
 
 

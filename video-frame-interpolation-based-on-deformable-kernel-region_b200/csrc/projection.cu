@@ -351,305 +351,20 @@ projection_fill_mask_kernel(const float *__restrict__ count, float *__restrict__
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Forward for batches: L2-resident scratch, persistent kernels, one (splat, box pass) launch pair per chunk of frames.
-//
-// What bounds the three-kernel path above at 1080p x 8 is DRAM: its scratch image for the whole batch (16 B per pixel,
-// 292 MB) is cleared, read-modify-written by the REDs and read back -- 2.9x the algorithmic bytes.  The vector RED
-// itself is fast when its target lives in L2 (tools/microbench/ffma2.cu: 360 G RED/s into a 36 MB image, 170 G RED/s
-// into a 292 MB one).  So the batch is cut into chunks whose scratch (<= CHUNK_BYTES) stays in the 126 MB L2, two
-// scratch images alternate, and the splat of a chunk clears the image of the next one (cell for cell, in L2).  What
-// made this lose in round 1 -- one launch pair per frame took ~17 us each -- was latency, not bytes: one pixel per
-// thread (a DRAM round trip per wave of CTAs) and 9 k CTAs per launch.  These kernels are persistent (two CTAs of 512
-// threads per SM), a splat thread keeps the loads of four pixels in flight before its first RED, a box-pass warp the
-// loads of four rows, and each launch may start while its predecessor drains (programmatic dependent launch).
-// (Also built and measured, profiles/r02/time_projection_v*.log: ONE cooperative kernel with splat workers and box-pass
-// workers on different frames, meeting through per-frame counters in global memory.  Correct, but every hand-off -- fence,
-// counter, poll -- costs ~2 us and a frame needs six of them in sequence: 12 us per frame of pure latency, 339-363 us
-// for the batch against 313 us for the three kernels.  Removed.)
+// What else was built for the forward in round 2, verified against the oracle, measured and REMOVED (git history;
+// profiles/r02/time_projection_v*.log, ncu_dproj_chunks_v1.txt, launches_dproj_chunks_warm_v1.csv) -- the whole-batch
+// splat + box pass above stayed the fastest at 1080p x 8 (313 us without hole filling):
+//   * one cooperative kernel, splat workers and box-pass workers on different frames, per-frame counters in global
+//     memory: every hand-off (fence, counter, poll) costs ~2 us and a frame needs six in sequence -- 339-736 us;
+//   * chunks of one frame with two alternating scratch images meant to stay in L2, persistent kernels (one and four
+//     pixels per thread), programmatic dependent launch: 316-350 us.  The premise failed: with a 36.5 MB image being
+//     RED into, a second one being cleared and 54 MB of streams per frame, L2 does NOT keep the image (ncu, warm caches:
+//     the box pass reads its 36.6 MB from DRAM again, L2 hit rate 47-50 %), and a one-frame launch takes 19-28 us however
+//     few instructions it issues (3.3 M vs 7.4 M warp-instructions per frame made no difference): latency-bound at
+//     32 warps per SM.  The microbenchmark's 360 G vector REDs/s into a resident 36 MB image (tools/microbench/ffma2.cu)
+//     needs the image to be the ONLY thing in flight.
+// What did pay: the hole filling below (bitmask-driven, dense lanes, 64-row column words).
 // ---------------------------------------------------------------------------------------------------------------
-namespace pf {
-
-constexpr int NT = 512;            // threads per CTA
-constexpr int SPLAT_UNROLL = 4;    // 32 x 16 pixel sub-tiles whose loads a thread block keeps in flight
-constexpr int WARPS = NT / 32;
-constexpr size_t CHUNK_BYTES = (size_t)40 << 20;   // scratch of one chunk of frames: two of these + the streams fit in L2
-
-__device__ __forceinline__ void grid_dependency_wait()      // programmatic dependent launch: the predecessor has completed
-{
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
-
-// Splat of a chunk of `nb` frames (the first is frame b0 of the batch) into S, and clear of `clear` (the other scratch
-// image, used by the next chunk; may be null).  Work items: 32 x 16 pixel sub-tiles of all frames of the chunk.
-template <bool DEPTH>
-__global__ void __launch_bounds__(NT, 2)
-projection_splat_chunk_kernel(const FlowSource fs, int b0, int nb, const float *__restrict__ depth, float4 *__restrict__ S,
-                              float4 *__restrict__ clear, int H, int W, const FastDiv div_tx, const FastDiv div_tiles)
-{
-    grid_dependency_wait();
-    const size_t HW = (size_t)H * W;
-    const int tiles_x = (W + 31) >> 5, tiles_f = tiles_x * ((H + 15) >> 4), ntiles = tiles_f * nb;
-    const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
-    const int worker = blockIdx.x, nworkers = gridDim.x;
-    for (int t0 = worker; t0 < ntiles; t0 += nworkers * SPLAT_UNROLL) {
-        float fx[SPLAT_UNROLL], fy[SPLAT_UNROLL], d[SPLAT_UNROLL];
-        int wi[SPLAT_UNROLL], hi[SPLAT_UNROLL], fr[SPLAT_UNROLL];
-        bool ok[SPLAT_UNROLL];
-#pragma unroll
-        for (int k = 0; k < SPLAT_UNROLL; ++k) {   // every load of the group before the first RED
-            const int t = min(t0 + k * nworkers, ntiles - 1);
-            fr[k] = div_tiles.quot(t);
-            const int tt = t - fr[k] * tiles_f, ty = div_tx.quot(tt), tx = tt - ty * tiles_x;
-            wi[k] = tx * 32 + lx; hi[k] = ty * 16 + ly;
-            ok[k] = t0 + k * nworkers < ntiles && wi[k] < W && hi[k] < H;
-            fx[k] = fy[k] = 0.0f; d[k] = 1.0f;
-            if (ok[k]) {
-                load_flow(fs, b0 + fr[k], hi[k], wi[k], H, W, fx[k], fy[k]);
-                if (DEPTH) d[k] = ld_stream(depth + (size_t)(b0 + fr[k]) * HW + (size_t)hi[k] * W + wi[k]);
-            }
-        }
-#pragma unroll
-        for (int k = 0; k < SPLAT_UNROLL; ++k) {
-            if (!ok[k]) continue;
-            if (clear) __stcg(clear + (size_t)fr[k] * HW + (size_t)hi[k] * W + wi[k], make_float4(0.f, 0.f, 0.f, 0.f));
-            const Corners c = corners(wi[k], hi[k], fx[k], fy[k], W, H);
-            if (!c.in_range) continue;
-            const float vx = DEPTH ? -d[k] * fx[k] : -fx[k], vy = DEPTH ? -d[k] * fy[k] : -fy[k];   // :75-88 / depth :77-92
-            atomicAdd(S + (size_t)fr[k] * HW + (size_t)c.T * W + c.L, make_float4(vx, vy, d[k], 0.0f));   // REDG.F32x4
-        }
-    }
-    grid_launch_dependents();
-}
-
-// Box pass + averaging of a chunk (the arithmetic of projection_finish_kernel, same operation order): warp items of
-// 32 columns x 8 rows over all frames of the chunk.  S is read through L2 (ld.global.cg: it was just written there).
-__global__ void __launch_bounds__(NT, 2)
-projection_finish_chunk_kernel(const float4 *__restrict__ S, int nb, float *__restrict__ count, float *__restrict__ out,
-                               unsigned *__restrict__ rowmask, unsigned long long *__restrict__ colmask, unsigned *__restrict__ holemask,
-                               int H, int W, const FastDiv div_bw, const FastDiv div_items)
-{
-    grid_dependency_wait();
-    const int lane = threadIdx.x & 31;
-    const int bw = (W + 31) >> 5, HB = (H + FIN_ROWS - 1) / FIN_ROWS, nitems = bw * HB, total = nitems * nb;
-    const size_t HW = (size_t)H * W;
-    const int gwarp = blockIdx.x * WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * WARPS;
-    for (int g = gwarp; g < total; g += nwarps) {
-        const int f = div_items.quot(g), it = g - f * nitems;
-        const float4 *Sf = S + (size_t)f * HW;
-        float *cn = count + (size_t)f * HW, *ou = out + (size_t)f * 2 * HW, *ov = ou + HW;
-        const int seg = div_bw.quot(it), x = (it - seg * bw) * 32 + lane;
-        const int y0 = seg * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
-        float4 c0, e0;
-        load_row<true>(Sf + (size_t)max(y0 - 1, 0) * W, x, W, lane, y0 > 0, c0, e0);
-        float4 prev = hsum_row(c0, e0, x, W, lane);
-        unsigned colbits = 0, holeword = 0;
-#pragma unroll
-        for (int ybk = 0; ybk < FIN_ROWS; ybk += FIN_UNROLL) {
-            const int yb = y0 + ybk;
-            float4 cur[FIN_UNROLL], edge[FIN_UNROLL];
-#pragma unroll
-            for (int k = 0; k < FIN_UNROLL; ++k)
-                load_row<true>(Sf + (size_t)min(yb + k, H - 1) * W, x, W, lane, yb + k < y1, cur[k], edge[k]);
-#pragma unroll
-            for (int k = 0; k < FIN_UNROLL; ++k) {
-                const int y = yb + k;
-                const float4 h = hsum_row(cur[k], edge[k], x, W, lane);
-                const float w0 = (y == H - 1) ? 2.0f : 1.0f;
-                float su = w0 * h.x + prev.x, sv = w0 * h.y + prev.y;
-                const float sc = w0 * h.z + prev.z;
-                prev = h;
-                const bool live = y < y1 && x < W;
-                if (live) {
-                    if (sc > 0.0f) { su = su / sc; sv = sv / sc; }   // :130-134
-                    const size_t a = (size_t)y * W + x;
-                    st_stream(cn + a, sc); st_stream(ou + a, su); st_stream(ov + a, sv);
-                }
-                if (rowmask) {   // uniform
-                    const bool src = live && sc != 0.0f;
-                    const unsigned m = __ballot_sync(0xffffffffu, src);
-                    if (lane == 0 && y < y1) rowmask[((size_t)f * H + y) * bw + (x >> 5)] = m;
-                    colbits |= (src ? 1u : 0u) << (y - y0);
-                    const unsigned hm = __ballot_sync(0xffffffffu, live && !(sc > 0.0f));   // count <= 0 (:171)
-                    if (lane == ybk + k) holeword = hm;
-                }
-            }
-        }
-        if (rowmask) {
-            if (x < W) *colmask_byte(colmask + (size_t)f * W * colwords(H), x, seg, H) = (unsigned char)colbits;
-            if (lane < FIN_ROWS) holemask[(size_t)g * FIN_ROWS + lane] = holeword;
-        }
-    }
-    grid_launch_dependents();
-}
-
-// ---- four pixels per thread (W % 4 == 0, 16-byte aligned tensors, full-resolution flow) -----------------------------
-// ncu on the kernels above (profiles/r02): 103 warp-instructions per pixel in the splat, 192 in the box pass -- the box
-// pass is INSTRUCTION-bound (issue slots 61 % busy at 25 us per 1080p frame), not byte-bound.  Here a thread owns four
-// adjacent pixels: flow / depth / count / output move as 128-bit accesses, the horizontal neighbour comes from the
-// thread's own registers three times out of four, the bitmaps are assembled from 4-bit nibbles with three shuffles.
-template <bool DEPTH>
-__global__ void __launch_bounds__(NT, 2)
-projection_splat4_kernel(const float *__restrict__ flow, int b0, int nb, const float *__restrict__ depth, float4 *__restrict__ S,
-                         float4 *__restrict__ clear, int H, int W, const FastDiv div_w4, const FastDiv div_hw4)
-{
-    grid_dependency_wait();
-    const size_t HW = (size_t)H * W;
-    const int W4 = W >> 2, HW4 = H * W4, total = HW4 * nb;     // groups of four pixels (< 2^30: launcher)
-    const int stride = gridDim.x * NT;
-    constexpr int U = 2;
-    for (int g0 = blockIdx.x * NT + threadIdx.x; g0 < total; g0 += stride * U) {
-        float4 fx[U], fy[U], d[U];
-        int fr[U], y[U], x[U];
-        bool ok[U];
-#pragma unroll
-        for (int k = 0; k < U; ++k) {     // every load of the group before the first store / RED
-            const int g = min(g0 + k * stride, total - 1);
-            ok[k] = g0 + k * stride < total;
-            fr[k] = div_hw4.quot(g);
-            const int r = g - fr[k] * HW4;
-            y[k] = div_w4.quot(r);
-            x[k] = (r - y[k] * W4) << 2;
-            const size_t pix = (size_t)y[k] * W + x[k];
-            const float *fl = flow + (size_t)(b0 + fr[k]) * 2 * HW + pix;
-            fx[k] = ld_stream4(fl);
-            fy[k] = ld_stream4(fl + HW);
-            d[k] = DEPTH ? ld_stream4(depth + (size_t)(b0 + fr[k]) * HW + pix) : make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-#pragma unroll
-        for (int k = 0; k < U; ++k) {
-            if (!ok[k]) continue;
-            float4 *Sf = S + (size_t)fr[k] * HW;
-            if (clear) {
-                float4 *c = clear + (size_t)fr[k] * HW + (size_t)y[k] * W + x[k];
-                const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-                __stcg(c, z); __stcg(c + 1, z); __stcg(c + 2, z); __stcg(c + 3, z);
-            }
-            const float fxs[4] = {fx[k].x, fx[k].y, fx[k].z, fx[k].w}, fys[4] = {fy[k].x, fy[k].y, fy[k].z, fy[k].w};
-            const float ds[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const Corners c = corners(x[k] + j, y[k], fxs[j], fys[j], W, H);
-                if (!c.in_range) continue;
-                const float vx = DEPTH ? -ds[j] * fxs[j] : -fxs[j], vy = DEPTH ? -ds[j] * fys[j] : -fys[j];   // :75-88 / depth :77-92
-                atomicAdd(Sf + (size_t)c.T * W + c.L, make_float4(vx, vy, ds[j], 0.0f));   // REDG.F32x4
-            }
-        }
-    }
-    grid_launch_dependents();
-}
-
-// OR of a 4-bit nibble per lane over groups of eight lanes: lane 8b + i contributes bits 4i .. 4i+3 of word b
-__device__ __forceinline__ unsigned gather_nibbles(unsigned nib, int lane)
-{
-    unsigned w = nib << ((lane & 7) * 4);
-    w |= __shfl_xor_sync(0xffffffffu, w, 1);
-    w |= __shfl_xor_sync(0xffffffffu, w, 2);
-    w |= __shfl_xor_sync(0xffffffffu, w, 4);
-    return w;
-}
-
-constexpr int F4_ROWS = 2;     // rows whose loads a warp keeps in flight
-__global__ void __launch_bounds__(NT, 1)
-projection_finish4_kernel(const float4 *__restrict__ S, int nb, float *__restrict__ count, float *__restrict__ out,
-                          unsigned *__restrict__ rowmask, unsigned long long *__restrict__ colmask, unsigned *__restrict__ holemask,
-                          int H, int W, const FastDiv div_bw4, const FastDiv div_items)
-{
-    grid_dependency_wait();
-    const int lane = threadIdx.x & 31;
-    // warp items: 128 columns x 8 rows
-    const int bw4 = (W + 127) >> 7, bw = (W + 31) >> 5, HB = (H + FIN_ROWS - 1) / FIN_ROWS, nitems = bw4 * HB, total = nitems * nb;
-    const size_t HW = (size_t)H * W;
-    const int gwarp = blockIdx.x * WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * WARPS;
-    for (int g = gwarp; g < total; g += nwarps) {
-        const int f = div_items.quot(g), it = g - f * nitems;
-        const float4 *Sf = S + (size_t)f * HW;
-        float *cn = count + (size_t)f * HW, *ou = out + (size_t)f * 2 * HW, *ov = ou + HW;
-        const int seg = div_bw4.quot(it), x0 = (it - seg * bw4) << 7, x = x0 + 4 * lane;     // this lane: columns x .. x+3
-        const int y0 = seg * FIN_ROWS, y1 = min(y0 + FIN_ROWS, H);
-        const bool col_ok = x < W;          // W % 4 == 0: all four or none
-        // one row of cells: this lane's four and the cell left of them (lane 0: from memory, else from the lane before)
-        auto load = [&](int y, bool valid, float4 (&c)[4], float4 &edge) {
-            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            c[0] = c[1] = c[2] = c[3] = edge = z;
-            if (valid && col_ok) {
-                const float4 *row = Sf + (size_t)y * W + x;
-                c[0] = __ldcg(row); c[1] = __ldcg(row + 1); c[2] = __ldcg(row + 2); c[3] = __ldcg(row + 3);
-                if (lane == 0 && x > 0) edge = __ldcg(row - 1);
-            }
-        };
-        // horizontal half of the box for the four cells: wx(x,0) * S[x] + S[x-1]
-        auto hsum = [&](const float4 (&c)[4], const float4 &edge, float4 (&h)[4]) {
-            float4 left;
-            left.x = __shfl_up_sync(0xffffffffu, c[3].x, 1);
-            left.y = __shfl_up_sync(0xffffffffu, c[3].y, 1);
-            left.z = __shfl_up_sync(0xffffffffu, c[3].z, 1);
-            if (lane == 0) left = edge;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const float w0 = (x + j == W - 1) ? 2.0f : 1.0f;
-                const float4 &l = j == 0 ? left : c[j - 1];
-                h[j] = make_float4(w0 * c[j].x + l.x, w0 * c[j].y + l.y, w0 * c[j].z + l.z, 0.f);
-            }
-        };
-        float4 prev[4];
-        {
-            float4 c[4], e;
-            load(max(y0 - 1, 0), y0 > 0, c, e);
-            hsum(c, e, prev);
-        }
-        unsigned colbits[4] = {0u, 0u, 0u, 0u}, myhole = 0;
-#pragma unroll
-        for (int ybk = 0; ybk < FIN_ROWS; ybk += F4_ROWS) {
-            float4 cur[F4_ROWS][4], edge[F4_ROWS];
-#pragma unroll
-            for (int k = 0; k < F4_ROWS; ++k) load(min(y0 + ybk + k, H - 1), y0 + ybk + k < y1, cur[k], edge[k]);
-#pragma unroll
-            for (int k = 0; k < F4_ROWS; ++k) {
-                const int y = y0 + ybk + k;
-                float4 h[4];
-                hsum(cur[k], edge[k], h);
-                const float w0 = (y == H - 1) ? 2.0f : 1.0f;
-                const bool live = y < y1 && col_ok;
-                float su[4], sv[4], sc[4];
-                unsigned src_nib = 0, hole_nib = 0;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    su[j] = w0 * h[j].x + prev[j].x; sv[j] = w0 * h[j].y + prev[j].y; sc[j] = w0 * h[j].z + prev[j].z;
-                    prev[j] = h[j];
-                    if (sc[j] > 0.0f) { su[j] = su[j] / sc[j]; sv[j] = sv[j] / sc[j]; }   // :130-134
-                    if (live && sc[j] != 0.0f) src_nib |= 1u << j;
-                    if (live && !(sc[j] > 0.0f)) hole_nib |= 1u << j;                    // count <= 0 (:171)
-                }
-                if (live) {
-                    const size_t a = (size_t)y * W + x;
-                    st_stream4(cn + a, make_float4(sc[0], sc[1], sc[2], sc[3]));
-                    st_stream4(ou + a, make_float4(su[0], su[1], su[2], su[3]));
-                    st_stream4(ov + a, make_float4(sv[0], sv[1], sv[2], sv[3]));
-                }
-                if (rowmask) {   // uniform
-                    const unsigned srcw = gather_nibbles(src_nib, lane), holew = gather_nibbles(hole_nib, lane);
-                    const int wx = (x0 >> 5) + (lane >> 3);                               // this lane group's 32-column word
-                    if ((lane & 7) == 0 && y < y1 && wx < bw) rowmask[((size_t)f * H + y) * bw + wx] = srcw;
-                    if ((lane & 7) == ybk + k) myhole = holew;                            // lane 8b + r keeps row r of block b
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) colbits[j] |= (src_nib >> j & 1u) << (ybk + k);
-                }
-            }
-        }
-        if (rowmask) {
-            if (col_ok) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) *colmask_byte(colmask + (size_t)f * W * colwords(H), x + j, seg, H) = (unsigned char)colbits[j];
-            }
-            const int wx = (x0 >> 5) + (lane >> 3);
-            if (wx < bw) holemask[(((size_t)f * HB + seg) * bw + wx) * FIN_ROWS + (lane & 7)] = myhole;
-        }
-    }
-    grid_launch_dependents();
-}
-
-}  // namespace pf
 
 // backward gather (:266-297; depth :276-337)
 template <bool DEPTH>
@@ -795,13 +510,6 @@ mindepth_backward_kernel(const float *__restrict__ flow, const float *__restrict
 
 namespace {
 
-// ---- host side of the fused pipeline ------------------------------------------------------------------------
-// test hook: 0 = automatic (= 3), 1 = whole-batch kernels, 2 = L2-resident chunks with persistent kernels, 3 = the same with programmatic
-// dependent launch, 4 = as 3 but never the four-pixels-per-thread kernels
-std::atomic<int> g_projection_path{0};
-inline int forced_projection_path() { return g_projection_path.load(std::memory_order_relaxed); }
-std::atomic<long long> g_chunk_bytes{0};    // test hook: scratch budget of a chunk (0 = pf::CHUNK_BYTES)
-
 // the hole-filling bitmaps of a batch inside one scratch block: [column bitmap (64-bit words) | row bitmap | hole bitmask]
 struct FillMaps {
     unsigned long long *colmask; unsigned *rowmask, *holemask;
@@ -836,78 +544,6 @@ static int launch_fill(const float *count, float *out, const FillMaps &m, int B,
     return check_launch("flow projection hole filling");
 }
 
-template <typename... Params, typename... Args>
-static cudaError_t launch_persistent(void (*kernel)(Params...), unsigned grid, bool pdl, cudaStream_t s, Args... args)
-{
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(pf::NT);
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kernel, static_cast<Params>(args)...);
-}
-
-// chunks of frames whose scratch stays in L2, persistent kernels (see namespace pf)
-template <bool DEPTH>
-int projection_forward_chunked(const FlowSource fs, const float *depth, float *count, float *out,
-                               int B, int H, int W, int fillhole, bool pdl, cudaStream_t s)
-{
-    using namespace pf;
-    const size_t HW = (size_t)H * W;
-    const long long forced_budget = g_chunk_bytes.load(std::memory_order_relaxed);
-    const size_t budget = forced_budget > 0 ? (size_t)forced_budget : CHUNK_BYTES;
-    const int per_chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)B, budget / (sizeof(float4) * HW)));
-    const int nchunks = (B + per_chunk - 1) / per_chunk;
-    const size_t chunk_cells = (size_t)per_chunk * HW;
-    const int bw = (W + 31) >> 5, HB = (H + 7) >> 3;
-    if ((long long)per_chunk * bw * HB >= (1ll << 31) || (long long)per_chunk * bw * ((H + 15) >> 4) >= (1ll << 30)) return -1;
-    // one stream-ordered block: [scratch image(s) | bitmaps for the hole filling]
-    const size_t scratch_bytes = sizeof(float4) * chunk_cells * (nchunks > 1 ? 2 : 1);
-    void *scratch = nullptr;
-    int e = stream_scratch_alloc(&scratch, scratch_bytes + fill_maps(nullptr, B, H, W, fillhole).bytes, s);
-    if (e) return e;
-    float4 *S = static_cast<float4 *>(scratch);
-    const FillMaps fm = fill_maps(static_cast<char *>(scratch) + scratch_bytes, B, H, W, fillhole);
-    e = set_error(cudaMemsetAsync(S, 0, sizeof(float4) * chunk_cells, s), "clear projection scratch");
-    if (!e && fillhole) e = set_error(cudaMemsetAsync(fm.colmask, 0, fm.colmask_bytes, s), "clear column bitmap");   // rows past H stay 0
-    const unsigned grid = 2u * (unsigned)sm_count();
-    // four pixels per thread when rows are whole float4s and everything is 16-byte aligned (not for the low-resolution flow source)
-    const bool four = !fs.lowres && W % 4 == 0 && aligned16(fs.flow) && aligned16(count) && aligned16(out) && (!DEPTH || aligned16(depth)) &&
-                      (long long)per_chunk * H * (W >> 2) < (1ll << 30) && forced_projection_path() != 4;
-    const FastDiv div_tx((unsigned)bw), div_tiles((unsigned)(bw * ((H + 15) >> 4))), div_bw((unsigned)bw), div_items((unsigned)(bw * HB));
-    for (int c = 0; c < nchunks && !e; ++c) {
-        const int b0 = c * per_chunk, nb = std::min(per_chunk, B - b0);
-        float4 *cur = S + (size_t)(c & 1) * chunk_cells;
-        float4 *nxt = (c + 1 < nchunks) ? S + (size_t)((c + 1) & 1) * chunk_cells : nullptr;
-        // (the next chunk may be shorter than this one; clearing nb frames of it is always enough or more)
-        unsigned *rm = fillhole ? fm.rowmask + (size_t)b0 * H * bw : nullptr, *hm = fillhole ? fm.holemask + (size_t)b0 * HB * bw * FIN_ROWS : nullptr;
-        unsigned long long *cm = fillhole ? fm.colmask + (size_t)b0 * W * colwords(H) : nullptr;
-        if (four) {
-            e = set_error(launch_persistent(projection_splat4_kernel<DEPTH>, grid, pdl && c > 0, s, fs.flow, b0, nb, depth, cur, nxt, H, W,
-                                            FastDiv((unsigned)(W >> 2)), FastDiv((unsigned)(H * (W >> 2)))), "flow projection splat");
-            if (!e) e = set_error(launch_persistent(projection_finish4_kernel, (unsigned)sm_count(), pdl, s, (const float4 *)cur, nb,
-                                                    count + (size_t)b0 * HW, out + (size_t)b0 * 2 * HW, rm, cm, hm, H, W,
-                                                    FastDiv((unsigned)((W + 127) >> 7)), FastDiv((unsigned)(((W + 127) >> 7) * HB))),
-                                  "flow projection box pass");
-        } else {
-            e = set_error(launch_persistent(projection_splat_chunk_kernel<DEPTH>, grid, pdl && c > 0, s, fs, b0, nb, depth, cur, nxt, H, W,
-                                            div_tx, div_tiles), "flow projection splat");
-            if (!e) e = set_error(launch_persistent(projection_finish_chunk_kernel, grid, pdl, s, (const float4 *)cur, nb, count + (size_t)b0 * HW,
-                                                    out + (size_t)b0 * 2 * HW, rm, cm, hm, H, W, div_bw, div_items), "flow projection box pass");
-        }
-        note_launch(2);
-    }
-    if (!e) e = check_launch("flow projection forward");
-    if (!e && fillhole) e = launch_fill(count, out, fm, B, H, W, s);
-    const int e2 = set_error(cudaFreeAsync(scratch, s), "projection scratch (cudaFreeAsync)");
-    return e ? e : e2;
-}
-
 template <bool DEPTH>
 int projection_forward(const FlowSource fs, const float *depth, float *count, float *out,
                        int B, int H, int W, int fillhole, cudaStream_t s)
@@ -916,13 +552,7 @@ int projection_forward(const FlowSource fs, const float *depth, float *count, fl
     if (B <= 0 || H <= 0 || W <= 0 || B > 65535 || !flow || !count || !out || (DEPTH && !depth)) return VFIDKR_ERR_ARG;
     if ((long long)H * W >= (1ll << 31) || ceil_div(H, FIN_ROWS) > 65535u) return VFIDKR_ERR_ARG;
     const size_t HW = (size_t)H * W;
-    if (forced_projection_path() != 1) {
-        const int e = projection_forward_chunked<DEPTH>(fs, depth, count, out, B, H, W, fillhole, forced_projection_path() != 2, s);
-        if (e >= 0) return e;     // -1: index ranges of the persistent kernels exceeded -> the three-kernel path below
-    }
-    // Round-1 path, kept as the fallback and as a reference implementation for the tests: ONE splat and ONE box pass
-    // over the whole batch, one pixel / one 32 x 8 block per thread / warp, scratch image of the batch in DRAM.
-    const size_t WW = ((size_t)W + 31) >> 5, HB = ((size_t)H + 7) >> 3;
+    // ONE splat and ONE box pass over the whole batch (one pixel / one 32 x 8 block per thread / warp), then the hole filling
     const size_t scratch_bytes = sizeof(float4) * B * HW;
     void *scratch = nullptr;
     int e = stream_scratch_alloc(&scratch, scratch_bytes + fill_maps(nullptr, B, H, W, fillhole).bytes, s);
@@ -940,7 +570,6 @@ int projection_forward(const FlowSource fs, const float *depth, float *count, fl
         e = check_launch("flow projection forward");
         if (!e && fillhole) e = launch_fill(count, out, fm, B, H, W, s);
     }
-    (void)WW; (void)HB;
     const int e2 = set_error(cudaFreeAsync(scratch, s), "projection scratch (cudaFreeAsync)");
     return e ? e : e2;
 }
@@ -962,13 +591,6 @@ int projection_backward(const float *flow, const float *depth, const float *coun
 }  // namespace vfidkr
 
 using namespace vfidkr;
-
-VFIDKR_API int vfidkr_debug_force_projection_path(int path)
-{
-    if (path >= 1000) { g_chunk_bytes.store((long long)(path - 1000) << 10, std::memory_order_relaxed); return 0; }   // chunk budget in KiB (1000 = default)
-    if (path < 0 || path > 4) return -1;
-    return g_projection_path.exchange(path, std::memory_order_relaxed);
-}
 
 VFIDKR_API int vfidkr_flowprojection_forward(const float *input1, float *count, float *output,
                                              int B, int H, int W, int fillhole, vfidkr_stream_t s)
