@@ -226,8 +226,9 @@ def run_step(V, mods, d, fi_events=None):
     outs = []
     for lvl in range(len(PWC_LEVELS)):
         a, b = d[f"feat{lvl}_0"], d[f"feat{lvl}_1"]
-        outs.append(corr(a, b))     # direction 0 -> 1
-        outs.append(corr(b, a))     # direction 1 -> 0
+        o01, o10 = corr.both_directions(a, b)     # direction 0 -> 1 and 1 -> 0 of this pyramid level: one launch
+        outs.append(o01)
+        outs.append(o10)
     p0 = dproj(d["rawflow0"], d["depth"])
     p1 = dproj(d["rawflow1"], d["depth"])
     warped = []
@@ -522,9 +523,7 @@ def bench_4k_stream(args):
     def process(j):
         d = sets[j % len(sets)]
         for lvl in range(len(PWC_LEVELS)):
-            a, b = d[f"feat{lvl}_0"], d[f"feat{lvl}_1"]
-            corr(a, b)
-            corr(b, a)
+            corr.both_directions(d[f"feat{lvl}_0"], d[f"feat{lvl}_1"])
         dproj(d["rawflow0"], d["depth"])
         dproj(d["rawflow1"], d["depth"])
         return V.filter_interpolate_blend(d["frame0"], d["frame1"], d["flow0"], d["flow1"], d["filter0"], d["filter1"], 0.5, 0.5)

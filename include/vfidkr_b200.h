@@ -200,6 +200,13 @@ int vfidkr_correlation_forward(const float *input1, const float *input2, float *
                                int B, int C, int H, int W, int pad_size, int kernel_size,
                                int max_displacement, int stride1, int stride2, int corr_type_multiply,
                                vfidkr_stream_t stream);
+/* No reference counterpart (it calls the correlation once per direction): both temporal directions of one pyramid
+ * level in ONE launch -- output12 = correlation(input1, input2), output21 = correlation(input2, input1): the results of
+ * two vfidkr_correlation_forward calls (bit-identical, except that maps small enough for the channel split may be split
+ * differently, i.e. summed in another order).  Twice the tiles per launch: the coarse pyramid levels fill the machine. */
+int vfidkr_correlation_forward_pair(const float *input1, const float *input2, float *output12, float *output21,
+                                    int B, int C, int H, int W, int pad_size, int kernel_size, int max_displacement,
+                                    int stride1, int stride2, int corr_type_multiply, vfidkr_stream_t stream);
 int vfidkr_correlation_backward(const float *input1, const float *input2, const float *gradoutput,
                                 float *gradinput1, float *gradinput2,
                                 int B, int C, int H, int W, int pad_size, int kernel_size,

@@ -401,6 +401,46 @@ def test_correlation_generic_configurations(lib, oracle, pad, k, md, s1, s2):
         U.assert_close(host(t2.grad), gi2, U.RTOL_FWD, "gradinput2")
 
 
+@pytest.mark.parametrize("B,C,H,W,pad,k,md,s1,s2", [
+    (2, 32, 40, 64, 4, 1, 4, 1, 1),      # TMA path
+    (8, 196, 18, 31, 4, 1, 4, 1, 1),     # PWC level 6 at 1080p: split-K, odd width (cp.async staging)
+    (8, 128, 36, 62, 4, 1, 4, 1, 1),     # PWC level 5: row-padded TMA path
+    (1, 5, 9, 13, 4, 1, 4, 1, 1),
+    (3, 16, 72, 124, 4, 1, 4, 1, 1),
+    (1, 4, 14, 18, 7, 3, 6, 1, 2),       # generic configuration: two launches inside
+])
+def test_correlation_both_directions_in_one_launch(lib, oracle, B, C, H, W, pad, k, md, s1, s2):
+    """vfidkr_correlation_forward_pair: equal to two single calls (bit-identical unless the channel split differs), equal to
+    the oracle, differentiable."""
+    r = U.rng(1750 + C + W)
+    f1, f2 = U.image(r, B, C, H, W, "normal"), U.image(r, B, C, H, W, "normal")
+    t1, t2 = cu(f1).requires_grad_(), cu(f2).requires_grad_()
+    mod = lib.Correlation(pad, k, md, s1, s2, 1)
+    before = lib.launch_count()
+    o12, o21 = mod.both_directions(t1, t2)
+    torch.cuda.synchronize()
+    pair_launches = lib.launch_count() - before
+    a, b = mod(t1.detach(), t2.detach()), mod(t2.detach(), t1.detach())
+    # same arithmetic per output; where the channels are split over work items (coarse levels) the pair launch may
+    # choose another slice count than the single one, i.e. another summation order: equal to rounding, else bit-identical
+    split = B * ((H + 7) // 8) * ((W + 31) // 32) <= 148
+    if split:
+        assert U.max_err(host(o12), host(a).astype(np.float64)) <= 2e-6 and U.max_err(host(o21), host(b).astype(np.float64)) <= 2e-6
+    else:
+        assert torch.equal(o12, a) and torch.equal(o21, b)
+    if k == 1:
+        assert pair_launches <= 3      # (row padding) + kernel + (split-K reduce): never two of each
+    U.assert_close(host(o12), oracle.correlation_forward(f1, f2, pad, k, md, s1, s2), U.RTOL_FWD, "pair: corr(f1, f2)")
+    U.assert_close(host(o21), oracle.correlation_forward(f2, f1, pad, k, md, s1, s2), U.RTOL_FWD, "pair: corr(f2, f1)")
+    g12, g21 = r.standard_normal(tuple(o12.shape)).astype(np.float32), r.standard_normal(tuple(o12.shape)).astype(np.float32)
+    (o12 * cu(g12)).sum().backward(retain_graph=True)
+    (o21 * cu(g21)).sum().backward()
+    a1, a2 = oracle.correlation_backward(f1, f2, g12, pad, k, md, s1, s2)
+    b2, b1 = oracle.correlation_backward(f2, f1, g21, pad, k, md, s1, s2)
+    U.assert_close(host(t1.grad), a1 + b1, U.RTOL_FWD, "pair: gradinput1")
+    U.assert_close(host(t2.grad), a2 + b2, U.RTOL_FWD, "pair: gradinput2")
+
+
 def test_correlation_of_ones_on_gpu(lib):
     f = torch.ones(1, 8, 10, 12, device="cuda")
     out = lib.Correlation(4, 1, 4, 1, 1, 1)(f, f)

@@ -6,7 +6,7 @@ C ABI of libvfidkr_b200.so (include/vfidkr_b200.h); there is no CPU or framework
 """
 from . import _lib
 from ._lib import VfidkrError, abi_version, debug_force_forward_path, launch_count, trim_scratch
-from .correlation import Correlation, CorrelationFunction, correlation_output_shape
+from .correlation import Correlation, CorrelationFunction, correlation_output_shape, correlation_pair
 from .filter_interpolation import (FilterInterpolationBlendLayer, filter_interpolate_blend,
                                    FilterInterpolationLayer, FilterInterpolationLayerDeforConv,
                                    FilterInterpolationLayerDKR, FilterInterpolationLayerNoFilterWithDeforConv,
@@ -18,7 +18,7 @@ from .interpolation import InterpolationChLayer, InterpolationChModule, Interpol
 from .separable_conv import (SeparableConvFlowLayer, SeparableConvFlowModule, SeparableConvLayer,
                              SeparableConvModule)
 from .compat import install_reference_aliases
-from .host_stream import PairStream
+from .host_stream import PairStream, bind_to_gpu_numa_node
 from .pwc_warp import PWCWarpLayer, pwc_warp
 from .frame_io import frame_padding, frames_to_padded, padded_to_frames
 

@@ -55,6 +55,7 @@ _SIGNATURES = {
     "vfidkr_separableconvflow_backward": [_P] * 5 + [_I] * 4 + [_P],
     "vfidkr_correlation_outshape": [_I] * 7 + [ctypes.POINTER(_I)] * 3,
     "vfidkr_correlation_forward": [_P] * 3 + [_I] * 10 + [_P],
+    "vfidkr_correlation_forward_pair": [_P] * 4 + [_I] * 10 + [_P],
     "vfidkr_correlation_backward": [_P] * 5 + [_I] * 10 + [_P],
     "vfidkr_abi_version": [],
     "vfidkr_trim_scratch": [],

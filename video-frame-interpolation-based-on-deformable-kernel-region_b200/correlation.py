@@ -18,7 +18,7 @@ from torch.nn import Module
 from . import _lib
 from ._common import check_input, ptr, stream_ptr
 
-__all__ = ["Correlation", "CorrelationFunction", "correlation_output_shape"]
+__all__ = ["Correlation", "CorrelationFunction", "correlation_output_shape", "correlation_pair"]
 
 
 def correlation_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2):
@@ -61,6 +61,47 @@ class _CorrelationOp(Function):
         return g1, g2, None, None, None, None, None, None
 
 
+class _CorrelationPairOp(Function):
+    """Both temporal directions of one pyramid level in ONE launch: (corr(input1, input2), corr(input2, input1)), the
+    results of two calls of the single op (vfidkr_correlation_forward_pair; no reference counterpart)."""
+
+    @staticmethod
+    def forward(ctx, input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply):
+        check_input(input1, "input1")
+        check_input(input2, "input2")
+        if input1.shape != input2.shape or input1.dim() != 4:
+            raise _lib.VfidkrError("input1 and input2 must be [B,C,H,W] tensors of the same shape")
+        B, C, H, W = input1.shape
+        oc, oh, ow = correlation_output_shape(H, W, pad_size, kernel_size, max_displacement, stride1, stride2)
+        if oh <= 0 or ow <= 0:
+            raise _lib.VfidkrError("correlation output would be empty")
+        out12 = torch.empty((B, oc, oh, ow), dtype=input1.dtype, device=input1.device)
+        out21 = torch.empty_like(out12)
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_correlation_forward_pair", ptr(input1), ptr(input2), ptr(out12), ptr(out21), B, C, H, W,
+                      pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply, stream_ptr(input1.device))
+        ctx.save_for_backward(input1, input2)
+        ctx.params = (pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)
+        return out12, out21
+
+    @staticmethod
+    def backward(ctx, g12, g21):
+        input1, input2 = ctx.saved_tensors
+        B, C, H, W = input1.shape
+        a1, a2, b2, b1 = (torch.empty_like(input1) for _ in range(4))
+        with torch.cuda.device(input1.device):
+            _lib.call("vfidkr_correlation_backward", ptr(input1), ptr(input2), ptr(g12.contiguous()), ptr(a1), ptr(a2),
+                      B, C, H, W, *ctx.params, stream_ptr(input1.device))
+            _lib.call("vfidkr_correlation_backward", ptr(input2), ptr(input1), ptr(g21.contiguous()), ptr(b2), ptr(b1),
+                      B, C, H, W, *ctx.params, stream_ptr(input1.device))
+        return a1 + b1, a2 + b2, None, None, None, None, None, None
+
+
+def correlation_pair(input1, input2, pad_size=4, kernel_size=1, max_displacement=4, stride1=1, stride2=1, corr_multiply=1):
+    """(Correlation(...)(input1, input2), Correlation(...)(input2, input1)) from one launch."""
+    return _CorrelationPairOp.apply(input1, input2, pad_size, kernel_size, max_displacement, stride1, stride2, corr_multiply)
+
+
 class CorrelationFunction:
     """Callable with the reference's constructor defaults (correlation.py:8)."""
 
@@ -82,3 +123,8 @@ class Correlation(Module):
     def forward(self, input1, input2):
         return CorrelationFunction(self.pad_size, self.kernel_size, self.max_displacement, self.stride1,
                                    self.stride2, self.corr_multiply)(input1, input2)
+
+    def both_directions(self, input1, input2):
+        """(self(input1, input2), self(input2, input1)) from ONE launch (not in the reference's Module)."""
+        return correlation_pair(input1, input2, self.pad_size, self.kernel_size, self.max_displacement, self.stride1,
+                                self.stride2, self.corr_multiply)

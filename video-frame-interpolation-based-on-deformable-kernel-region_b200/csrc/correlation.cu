@@ -124,11 +124,15 @@ static_assert(D % TJ == 0 && TX % PX == 0, "tile shape");
 template <bool TMA, int STAGES>
 __global__ void __launch_bounds__(cfast::NTHREADS, STAGES <= 3 ? 2 : 1)
 corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid_constant__ CUtensorMap map2,
+                          const __grid_constant__ CUtensorMap map1b, const __grid_constant__ CUtensorMap map2b,
                           const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
+                          const float *__restrict__ in1b, const float *__restrict__ in2b, float *__restrict__ outb, int bsplit,
                           int C, int H, int W, int shift, int oh, int ow, int tiles_x, int tiles_y, int num_tiles,
                           const FastDiv div_tiles_x, const FastDiv div_tiles_image,
                           int ksplit, int cps, const FastDiv div_ksplit, float *__restrict__ partial, size_t part_stride)
 {
+    // Two problems of the same shape in one launch (both temporal directions of a PWC level, vfidkr_correlation_forward_pair):
+    // "batch" items n >= bsplit belong to the second problem (map1b / map2b / in1b / in2b -> outb, item n - bsplit).
     // Split-K for maps with too few tiles to fill the machine: a work item is (tile, channel slice); every slice
     // walks `cps` chunks of CK channels (chunks past C are zero-filled by the loader) and, when ksplit > 1, writes
     // its UNSCALED partial sums to `partial`[slice]; corr_reduce_kernel adds the slices.  num_tiles counts
@@ -150,6 +154,8 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
     if (TMA && tid == 0) {
         prefetch_tensormap(&map1);
         prefetch_tensormap(&map2);
+        prefetch_tensormap(&map1b);
+        prefetch_tensormap(&map2b);
         for (int s = 0; s < STAGES; ++s) mbar_init(&s_full[s], 1);
         fence_mbar_init();
     }
@@ -168,8 +174,9 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
         chunk += (tile - div_ksplit.quot(tile) * ksplit) * cps;   // first chunk of this item's channel slice
         const int ix0 = bx * TX + shift, iy0 = by * TY + shift;
         mbar_arrive_expect_tx(&s_full[stage], STAGE_BYTES);
-        tma_load_4d(s1 + stage * F1_FLOATS, &map1, &s_full[stage], ix0, iy0, chunk * CK, n);
-        tma_load_4d(s2 + stage * F2_FLOATS, &map2, &s_full[stage], ix0 - DR, iy0 - DR, chunk * CK, n);
+        const bool second = n >= bsplit;
+        tma_load_4d(s1 + stage * F1_FLOATS, second ? &map1b : &map1, &s_full[stage], ix0, iy0, chunk * CK, second ? n - bsplit : n);
+        tma_load_4d(s2 + stage * F2_FLOATS, second ? &map2b : &map2, &s_full[stage], ix0 - DR, iy0 - DR, chunk * CK, second ? n - bsplit : n);
     };
 
     // cp.async staging of one (tile, chunk) item by all threads: one warp per tile row, lanes along x;
@@ -180,7 +187,9 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
         chunk += (tile - div_ksplit.quot(tile) * ksplit) * cps;   // first chunk of this item's channel slice
         const int ix0 = bx * TX + shift, iy0 = by * TY + shift;
         const int warp = tid >> 5, lane = tid & 31, nwarps = NTHREADS / 32;
-        const float *f1 = in1 + (size_t)n * C * HW, *f2 = in2 + (size_t)n * C * HW;
+        const bool second = n >= bsplit;
+        const float *f1 = (second ? in1b : in1) + (size_t)(second ? n - bsplit : n) * C * HW;
+        const float *f2 = (second ? in2b : in2) + (size_t)(second ? n - bsplit : n) * C * HW;
         float *d1 = s1 + stage * F1_FLOATS, *d2 = s2 + stage * F2_FLOATS;
         for (int row = warp; row < CK * TY; row += nwarps) {
             const int c = row / TY, y = row % TY, gy = iy0 + y, cc = chunk * CK + c, gx = ix0 + lane;
@@ -222,6 +231,9 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
         decode(tile, n, by, bx);
         const int ox0 = bx * TX, oy0 = by * TY;
 
+        // (Packed FFMA2 -- fma.rn.f32x2, 114 instead of 85.6 FMA/clk/SM in tools/microbench/ffma2.cu -- was tried here with
+        // the accumulators as pairs of adjacent pixels: the b-operand pairs (columns j, j + 1) are register-aligned only for
+        // even j, the odd ones cost two moves each, and the kernel ran 43 % SLOWER (PWC level 2: 278 vs 194 us).  Removed.)
         float acc[TJ][PX][D];
 #pragma unroll
         for (int t = 0; t < TJ; ++t)
@@ -271,21 +283,25 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
             // instructions x 108 outputs per thread)
             const float inv = ksplit > 1 ? 1.0f : 1.0f / (float)C;
             const size_t plane = (size_t)oh * ow;
-            float *dst = out;
-            if (ksplit > 1) dst = partial + (size_t)(tile - div_ksplit.quot(tile) * ksplit) * part_stride;
-            float *o = dst + ((size_t)n * D * D + (size_t)(TJ * tjg) * D) * plane + (size_t)oy * ow + ox;
+            // direct: the problem's own output, item within the problem; split-K: the slice's partial volume, which holds
+            // both problems back to back (item n)
+            float *dst = n >= bsplit ? outb : out;
+            int nn = n >= bsplit ? n - bsplit : n;
+            if (ksplit > 1) { dst = partial + (size_t)(tile - div_ksplit.quot(tile) * ksplit) * part_stride; nn = n; }
+            float *o = dst + ((size_t)nn * D * D + (size_t)(TJ * tjg) * D) * plane + (size_t)oy * ow + ox;
             const bool vec = (ow % 4 == 0) && (ox + 3 < ow) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
 #pragma unroll
             for (int t = 0; t < TJ; ++t)
 #pragma unroll
                 for (int d = 0; d < D; ++d) {
                     float *ot = o + (size_t)(t * D + d) * plane;
+                    const float r[4] = {acc[t][0][d] * inv, acc[t][1][d] * inv, acc[t][2][d] * inv, acc[t][3][d] * inv};
                     if (vec) {
-                        st_stream4(ot, make_float4(acc[t][0][d] * inv, acc[t][1][d] * inv, acc[t][2][d] * inv, acc[t][3][d] * inv));
+                        st_stream4(ot, make_float4(r[0], r[1], r[2], r[3]));
                     } else {
 #pragma unroll
                         for (int p = 0; p < PX; ++p)
-                            if (ox + p < ow) ot[p] = acc[t][p][d] * inv;
+                            if (ox + p < ow) ot[p] = r[p];
                     }
                 }
         }
@@ -294,12 +310,15 @@ corr_forward_tiled_kernel(const __grid_constant__ CUtensorMap map1, const __grid
 
 // adds the ksplit partial cost volumes and applies the 1 / (kernel_size^2 * C) scaling (:104, :143)
 __global__ void __launch_bounds__(256)
-corr_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, size_t n, int ksplit, float inv)
+corr_reduce_kernel(const float *__restrict__ partial, float *__restrict__ out, float *__restrict__ outb, size_t n_first,
+                   size_t n, int ksplit, float inv)
 {
+    // n elements per slice: the first n_first belong to `out`, the rest (second problem of a pair launch) to `outb`
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float acc = 0.0f;
         for (int s = 0; s < ksplit; ++s) acc += __ldcs(partial + (size_t)s * n + i);
-        out[i] = acc * inv;
+        if (i < n_first) out[i] = acc * inv;
+        else outb[i - n_first] = acc * inv;
     }
 }
 
@@ -629,6 +648,111 @@ VFIDKR_API int vfidkr_correlation_outshape(int H, int W, int pad, int k, int md,
     return VFIDKR_OK;
 }
 
+// fast path (kernel_size 1, strides 1, max_displacement 4): output = corr(input1, input2) and, when output_b is given,
+// output_b = corr(input2, input1) in the SAME launch (twice the tiles: the coarse PWC levels fill the machine, no
+// second launch / second split-K reduce)
+static int corr_forward_fast(const float *input1, const float *input2, float *output, float *output_b,
+                             int B, int C, int H, int W, int pad, int md, const CorrShape &cs, cudaStream_t s)
+{
+    using namespace cfast;
+    const int nprob = output_b ? 2 : 1;
+    const int tiles_x = ceil_div(cs.ow, TX), tiles_y = ceil_div(cs.oh, TY);
+    const long long num_tiles = (long long)tiles_x * tiles_y * B * nprob;
+    if (num_tiles >= (1ll << 31)) return VFIDKR_ERR_ARG;
+    const FastDiv dx((unsigned)tiles_x), di((unsigned)(tiles_x * tiles_y));
+    CUtensorMap m1, m2, m1b, m2b;
+    // (TMA box origins are kept at multiples of 4 elements: pad != max_displacement shifts them by md - pad, and an
+    // origin of -2 was observed to fault -- such configurations, which VFIDKR never uses, take the cp.async path)
+    const bool tma_ok = (md - pad) % 4 == 0;
+    bool tma = tma_ok && (W % 4 == 0) && aligned16(input1) && aligned16(input2) &&
+               encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
+               encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK) &&
+               (!output_b || (encode_tensor_map_4d(&m1b, input2, W, H, C, B, TX, TY, CK) &&
+                              encode_tensor_map_4d(&m2b, input1, W, H, C, B, F2W, F2H, CK)));
+    // Rows that are not a multiple of 16 bytes (the two coarsest PWC levels at 1080p are 62 and 31 wide) cannot be
+    // described to TMA.  Both feature maps are then copied once into a row-padded scratch (one small kernel, a few
+    // MB) and the tensor maps keep the true width as extent -- reads past it are zero-filled, which is the op's own
+    // padding -- so these levels run the TMA kernel too instead of the 4-byte cp.async staging path.
+    void *pitched = nullptr;
+    // (worth it between ~1.5 M and 64 M elements per map: below, the extra launch costs more than the staging path
+    // loses -- measured 44 -> 50 us at 18 x 31 x 196 x 8, 66 -> 51 us at 36 x 62 x 128 x 8 -- above, the copy is real
+    // traffic; a pair launch reads each padded map twice, so it pays from half that size)
+    const size_t map_elems = (size_t)B * C * H * W;
+    if (!tma && tma_ok && map_elems * nprob >= ((size_t)3 << 19) && map_elems <= ((size_t)64 << 20)) {
+        const size_t pitch = ((size_t)W + 3) & ~(size_t)3, rows = (size_t)B * C * H;
+        if (stream_scratch_alloc(&pitched, 2 * rows * pitch * sizeof(float), s) == VFIDKR_OK) {
+            float *p1 = static_cast<float *>(pitched), *p2 = p1 + rows * pitch;
+            const unsigned nb = (unsigned)std::min<size_t>((rows * pitch + 255) / 256, (size_t)sm_count() * 16);
+            corr_pad_rows_kernel<<<nb, 256, 0, s>>>(input1, input2, p1, p2, rows, W, (int)pitch);
+            note_launch();
+            tma = cudaGetLastError() == cudaSuccess &&
+                  encode_tensor_map_4d_pitched(&m1, p1, W, H, C, B, pitch, TX, TY, CK) &&
+                  encode_tensor_map_4d_pitched(&m2, p2, W, H, C, B, pitch, F2W, F2H, CK) &&
+                  (!output_b || (encode_tensor_map_4d_pitched(&m1b, p2, W, H, C, B, pitch, TX, TY, CK) &&
+                                 encode_tensor_map_4d_pitched(&m2b, p1, W, H, C, B, pitch, F2W, F2H, CK)));
+        }
+        (void)cudaGetLastError();
+    }
+    struct PitchedGuard {   // the scratch is released on the stream, after the kernel that reads it
+        void *p; cudaStream_t s;
+        ~PitchedGuard() { if (p) cudaFreeAsync(p, s); }
+    } pitched_guard{pitched, s};
+    if (!tma) { memset(&m1, 0, sizeof m1); memset(&m2, 0, sizeof m2); }
+    if (!tma || !output_b) { m1b = m1; m2b = m2; }
+    // Too few tiles to fill the machine (the two coarsest PWC levels at 1080p): split the channels over
+    // ksplit work items per tile and add the partial volumes in a second, tiny kernel.
+    const int nchunks = (C + CK - 1) / CK;
+    // The slice count is chosen by cost, not by "as many items as CTA slots": an item costs its chunks plus ~2
+    // chunk-times of pipeline fill / partial write, and items are dealt in rounds of (2 x SMs).  (80 tiles x 16
+    // chunks at PWC level 5: 4 slices made 320 items = 2 rounds of 4 chunks; 3 slices make 240 items = 1 round of 6.)
+    int ksplit = 1;
+    if (num_tiles <= (long long)sm_count()) {
+        const long long slots = 2ll * sm_count();
+        long long best = -1;
+        for (int ks = 1; ks <= nchunks; ++ks) {
+            const int cp = (nchunks + ks - 1) / ks, eff = (nchunks + cp - 1) / cp;
+            const long long rounds = (num_tiles * eff + slots - 1) / slots;
+            const long long cost = rounds * (cp + 2) + (eff > 1 ? 1 : 0);   // + the reduce kernel
+            if (best < 0 || cost < best) { best = cost; ksplit = eff; }
+        }
+    }
+    const int cps = (nchunks + ksplit - 1) / ksplit;
+    ksplit = (nchunks + cps - 1) / cps;   // drop slices that would be empty
+    const long long num_items = num_tiles * ksplit;
+    const size_t out_elems = (size_t)B * D * D * cs.oh * cs.ow;     // one problem
+    void *partial = nullptr;
+    if (ksplit > 1) {
+        const int e = stream_scratch_alloc(&partial, sizeof(float) * out_elems * nprob * ksplit, s);
+        if (e) return e;
+    }
+    auto launch = [&](auto kernel, int stages, int ctas_per_sm) {
+        // raising the dynamic shared memory limit is idempotent and cheap; do it on every launch so the
+        // attribute is set on whichever device is current
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(stages));
+        const int nblk = (int)std::min<long long>(num_items, (long long)sm_count() * ctas_per_sm);
+        kernel<<<nblk, NTHREADS, smem_bytes(stages), s>>>(m1, m2, m1b, m2b, input1, input2, output, input2, input1, output_b, B,
+                                                          C, H, W, md - pad, cs.oh, cs.ow,
+                                                          tiles_x, tiles_y, (int)num_items, dx, di, ksplit, cps,
+                                                          FastDiv((unsigned)ksplit), static_cast<float *>(partial), out_elems * nprob);
+    };
+    if (tma) launch(corr_forward_tiled_kernel<true, STAGES_LARGE>, STAGES_LARGE, 2);
+    else     launch(corr_forward_tiled_kernel<false, STAGES_LARGE>, STAGES_LARGE, 2);
+    note_launch();
+    if (ksplit > 1) {
+        int e = check_launch("correlation forward (split-K)");
+        if (!e) {
+            const size_t n_all = out_elems * nprob;
+            const unsigned nb = (unsigned)std::min<size_t>((n_all + 255) / 256, (size_t)sm_count() * 8);
+            corr_reduce_kernel<<<nb, 256, 0, s>>>(static_cast<const float *>(partial), output, output_b, out_elems, n_all, ksplit, 1.0f / (float)C);
+            note_launch();
+            e = check_launch("correlation forward (reduce)");
+        }
+        const int e2 = set_error(cudaFreeAsync(partial, s), "free correlation scratch");
+        return e ? e : e2;
+    }
+    return check_launch("correlation forward");
+}
+
 VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *input2, float *output,
                                           int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
                                           int corr_type_multiply, vfidkr_stream_t stream)
@@ -639,100 +763,33 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
     const CorrShape cs = corr_shape(H, W, pad, k, md, s1, s2);
     if (cs.oh <= 0 || cs.ow <= 0) return VFIDKR_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    if (k == 1 && s1 == 1 && s2 == 1 && md == 4) {
-        using namespace cfast;
-        const int tiles_x = ceil_div(cs.ow, TX), tiles_y = ceil_div(cs.oh, TY);
-        const long long num_tiles = (long long)tiles_x * tiles_y * B;
-        if (num_tiles >= (1ll << 31)) return VFIDKR_ERR_ARG;
-        const FastDiv dx((unsigned)tiles_x), di((unsigned)(tiles_x * tiles_y));
-        CUtensorMap m1, m2;
-        // (TMA box origins are kept at multiples of 4 elements: pad != max_displacement shifts them by md - pad, and an
-        // origin of -2 was observed to fault -- such configurations, which VFIDKR never uses, take the cp.async path)
-        const bool tma_ok = (md - pad) % 4 == 0;
-        bool tma = tma_ok && (W % 4 == 0) && aligned16(input1) && aligned16(input2) &&
-                   encode_tensor_map_4d(&m1, input1, W, H, C, B, TX, TY, CK) &&
-                   encode_tensor_map_4d(&m2, input2, W, H, C, B, F2W, F2H, CK);
-        // Rows that are not a multiple of 16 bytes (the two coarsest PWC levels at 1080p are 62 and 31 wide) cannot be
-        // described to TMA.  Both feature maps are then copied once into a row-padded scratch (one small kernel, a few
-        // MB) and the tensor maps keep the true width as extent -- reads past it are zero-filled, which is the op's own
-        // padding -- so these levels run the TMA kernel too instead of the 4-byte cp.async staging path.
-        void *pitched = nullptr;
-        // (worth it between ~1.5 M and 64 M elements per map: below, the extra launch costs more than the staging path
-        // loses -- measured 44 -> 50 us at 18 x 31 x 196 x 8, 66 -> 51 us at 36 x 62 x 128 x 8 -- above, the copy is real traffic)
-        const size_t map_elems = (size_t)B * C * H * W;
-        if (!tma && tma_ok && map_elems >= ((size_t)3 << 19) && map_elems <= ((size_t)64 << 20)) {
-            const size_t pitch = ((size_t)W + 3) & ~(size_t)3, rows = (size_t)B * C * H;
-            if (stream_scratch_alloc(&pitched, 2 * rows * pitch * sizeof(float), s) == VFIDKR_OK) {
-                float *p1 = static_cast<float *>(pitched), *p2 = p1 + rows * pitch;
-                const unsigned nb = (unsigned)std::min<size_t>((rows * pitch + 255) / 256, (size_t)sm_count() * 16);
-                corr_pad_rows_kernel<<<nb, 256, 0, s>>>(input1, input2, p1, p2, rows, W, (int)pitch);
-                note_launch();
-                tma = cudaGetLastError() == cudaSuccess &&
-                      encode_tensor_map_4d_pitched(&m1, p1, W, H, C, B, pitch, TX, TY, CK) &&
-                      encode_tensor_map_4d_pitched(&m2, p2, W, H, C, B, pitch, F2W, F2H, CK);
-            }
-            (void)cudaGetLastError();
-        }
-        struct PitchedGuard {   // the scratch is released on the stream, after the kernel that reads it
-            void *p; cudaStream_t s;
-            ~PitchedGuard() { if (p) cudaFreeAsync(p, s); }
-        } pitched_guard{pitched, s};
-        if (!tma) { memset(&m1, 0, sizeof m1); memset(&m2, 0, sizeof m2); }
-        // Too few tiles to fill the machine (the two coarsest PWC levels at 1080p): split the channels over
-        // ksplit work items per tile and add the partial volumes in a second, tiny kernel.
-        const int nchunks = (C + CK - 1) / CK;
-        // The slice count is chosen by cost, not by "as many items as CTA slots": an item costs its chunks plus ~2
-        // chunk-times of pipeline fill / partial write, and items are dealt in rounds of (2 x SMs).  (80 tiles x 16
-        // chunks at PWC level 5: 4 slices made 320 items = 2 rounds of 4 chunks; 3 slices make 240 items = 1 round of 6.)
-        int ksplit = 1;
-        if (num_tiles <= (long long)sm_count()) {
-            const long long slots = 2ll * sm_count();
-            long long best = -1;
-            for (int ks = 1; ks <= nchunks; ++ks) {
-                const int cp = (nchunks + ks - 1) / ks, eff = (nchunks + cp - 1) / cp;
-                const long long rounds = (num_tiles * eff + slots - 1) / slots;
-                const long long cost = rounds * (cp + 2) + (eff > 1 ? 1 : 0);   // + the reduce kernel
-                if (best < 0 || cost < best) { best = cost; ksplit = eff; }
-            }
-        }
-        const int cps = (nchunks + ksplit - 1) / ksplit;
-        ksplit = (nchunks + cps - 1) / cps;   // drop slices that would be empty
-        const long long num_items = num_tiles * ksplit;
-        const size_t out_elems = (size_t)B * D * D * cs.oh * cs.ow;
-        void *partial = nullptr;
-        if (ksplit > 1) {
-            const int e = stream_scratch_alloc(&partial, sizeof(float) * out_elems * ksplit, s);
-            if (e) return e;
-        }
-        auto launch = [&](auto kernel, int stages, int ctas_per_sm) {
-            // raising the dynamic shared memory limit is idempotent and cheap; do it on every launch so the
-            // attribute is set on whichever device is current
-            cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(stages));
-            const int nblk = (int)std::min<long long>(num_items, (long long)sm_count() * ctas_per_sm);
-            kernel<<<nblk, NTHREADS, smem_bytes(stages), s>>>(m1, m2, input1, input2, output, C, H, W, md - pad, cs.oh, cs.ow,
-                                                              tiles_x, tiles_y, (int)num_items, dx, di, ksplit, cps,
-                                                              FastDiv((unsigned)ksplit), static_cast<float *>(partial), out_elems);
-        };
-        if (tma) launch(corr_forward_tiled_kernel<true, STAGES_LARGE>, STAGES_LARGE, 2);
-        else     launch(corr_forward_tiled_kernel<false, STAGES_LARGE>, STAGES_LARGE, 2);
-        if (ksplit > 1) {
-            note_launch();
-            int e = check_launch("correlation forward (split-K)");
-            if (!e) {
-                const unsigned nb = (unsigned)std::min<size_t>((out_elems + 255) / 256, (size_t)sm_count() * 8);
-                corr_reduce_kernel<<<nb, 256, 0, s>>>(static_cast<const float *>(partial), output, out_elems, ksplit, 1.0f / (float)C);
-                note_launch();
-                e = check_launch("correlation forward (reduce)");
-            }
-            const int e2 = set_error(cudaFreeAsync(partial, s), "free correlation scratch");
-            return e ? e : e2;
-        }
-    } else {
-        dim3 block(32, 8), grid(ceil_div(cs.ow, 32), ceil_div(cs.oh, 8), B);
-        corr_forward_generic_kernel<<<grid, block, 0, s>>>(input1, input2, output, C, H, W, pad, k, md, s1, s2, cs);
-    }
+    if (k == 1 && s1 == 1 && s2 == 1 && md == 4) return corr_forward_fast(input1, input2, output, nullptr, B, C, H, W, pad, md, cs, s);
+    dim3 block(32, 8), grid(ceil_div(cs.ow, 32), ceil_div(cs.oh, 8), B);
+    corr_forward_generic_kernel<<<grid, block, 0, s>>>(input1, input2, output, C, H, W, pad, k, md, s1, s2, cs);
     note_launch();
     return check_launch("correlation forward");
+}
+
+// Both temporal directions of a pyramid level at once: output12 = correlation(input1, input2), output21 =
+// correlation(input2, input1) (PWC-Net is run once per direction, networks/DAIN.py:196-202, and calls the correlation
+// with the roles of the two feature maps exchanged; when the second map is not warped -- pyramid level 6,
+// PWCNet/PWCNet.py:230 -- or a caller evaluates both directions level by level, the two calls share their inputs).
+VFIDKR_API int vfidkr_correlation_forward_pair(const float *input1, const float *input2, float *output12, float *output21,
+                                               int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
+                                               int corr_type_multiply, vfidkr_stream_t stream)
+{
+    (void)corr_type_multiply;
+    if (B <= 0 || C <= 0 || H <= 0 || W <= 0 || pad < 0 || k <= 0 || md < 0 || s1 <= 0 || s2 <= 0 || 2 * B > 65535) return VFIDKR_ERR_ARG;
+    if (!input1 || !input2 || !output12 || !output21) return VFIDKR_ERR_ARG;
+    const CorrShape cs = corr_shape(H, W, pad, k, md, s1, s2);
+    if (cs.oh <= 0 || cs.ow <= 0) return VFIDKR_ERR_ARG;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (k == 1 && s1 == 1 && s2 == 1 && md == 4) return corr_forward_fast(input1, input2, output12, output21, B, C, H, W, pad, md, cs, s);
+    dim3 block(32, 8), grid(ceil_div(cs.ow, 32), ceil_div(cs.oh, 8), B);
+    corr_forward_generic_kernel<<<grid, block, 0, s>>>(input1, input2, output12, C, H, W, pad, k, md, s1, s2, cs);
+    corr_forward_generic_kernel<<<grid, block, 0, s>>>(input2, input1, output21, C, H, W, pad, k, md, s1, s2, cs);
+    note_launch(2);
+    return check_launch("correlation forward (pair)");
 }
 
 VFIDKR_API int vfidkr_correlation_backward(const float *input1, const float *input2, const float *gradoutput,

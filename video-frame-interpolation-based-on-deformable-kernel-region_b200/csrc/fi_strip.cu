@@ -382,16 +382,22 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 for (int c = 0; c < CG; ++c) prev[c] = __ldcs(op + (size_t)c * HW);
             }
 
-            STAT_TIME(0, mbar_wait_backoff_a(a_img_full + sb * 8, (uint32_t)((j / NB) & 1)));
-            STAT_INC(2);
-            const int mode = s_meta[sb].mode, xorg = s_meta[sb].xorg, soff = s_meta[sb].soff;
-            STAT_TIME(1, mbar_wait_backoff_a(a_filt_full + sf * 8, (uint32_t)((j / SF) & 1)));
+            // Both barriers are probed back to back (a try_wait answers after ~90 cycles even when the phase is long
+            // complete: probing them one after the other put two such latencies on every tile of every warp), the taps are
+            // requested as soon as the filter stage is there, and only then does the warp wait for its image rows.
+            const uint32_t par_i = (uint32_t)((j / NB) & 1), par_f = (uint32_t)((j / SF) & 1);
+            const bool ok_f = mbar_try_wait_a(a_filt_full + sf * 8, par_f);
+            const bool ok_i = mbar_try_wait_a(a_img_full + sb * 8, par_i);
+            if (!ok_f) STAT_TIME(1, mbar_wait_backoff_a(a_filt_full + sf * 8, par_f));
             // The 16 taps go to registers at once and the stage is handed back BEFORE the window arithmetic: the kernel
             // is bound by the bytes it keeps in flight (4 stages x 32 KB per SM; a stage that waits for the slowest
             // warp to finish the whole tile spends a third of its life neither in flight nor in use).
             float w[16];
 #pragma unroll
             for (int k = 0; k < 16; ++k) w[k] = ft[k * NPIX];
+            if (!ok_i) STAT_TIME(0, mbar_wait_backoff_a(a_img_full + sb * 8, par_i));
+            STAT_INC(2);
+            const int mode = s_meta[sb].mode, xorg = s_meta[sb].xorg, soff = s_meta[sb].soff;
             __syncwarp();
             if (lane == 0) mbar_arrive_a(a_filt_free + sf * 8);   // release: this warp's reads of stage sf are complete
 

@@ -16,6 +16,30 @@ from typing import Callable, Mapping, Sequence
 import torch
 
 
+def bind_to_gpu_numa_node(device) -> list[int] | None:
+    """Pin the calling process to the CPUs NVML reports as local to `device` (its NUMA node), so that pinned host buffers
+    allocated AFTERWARDS are first-touched there and host -> device copies do not cross the socket interconnect.
+    Returns the CPU list, or None when NVML / the affinity call is unavailable (nothing is changed then).  Host-side
+    plumbing for the end-to-end path of several ranks on one box; no reference counterpart."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        props = torch.cuda.get_device_properties(device)
+        bus = f"{props.pci_domain_id:08X}:{props.pci_bus_id:02X}:{props.pci_device_id:02X}.0"
+        handle = pynvml.nvmlDeviceGetHandleByPciBusId(bus.encode())
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, (ncpu + 63) // 64)
+        cpus = [i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
 class PairStream:
     """step_fn(chunk_inputs: dict[str, Tensor on device]) -> sequence of device tensors with the pair dimension first.
 
