@@ -222,6 +222,11 @@ int vfidkr_flowprojection_forward_lowres(const float *flow_lowres, float scale0,
                                          vfidkr_stream_t stream);
 int vfidkr_flow_upsample4(const float *flow_lowres, float scale0, float scale1, float *output, int B, int h, int w,
                           vfidkr_stream_t stream);
+/* Adjoint of vfidkr_flow_upsample4 (what autograd's backward of scale -> nn.Upsample computes in the reference,
+ * networks/DAIN.py:306-308): grad_output [B,2,4h,4w] -> grad_flow_lowres [B,2,h,w].  With the projection backward on the
+ * enlarged flow this trains through vfidkr_flowprojection_forward_lowres (vfidkr_b200.flow_project_lowres). */
+int vfidkr_flow_upsample4_backward(const float *grad_output, float scale0, float scale1, float *grad_flow_lowres,
+                                   int B, int h, int w, vfidkr_stream_t stream);
 
 /* ---- MinDepthFlowProjection (my_package/MinDepthFlowProjection/mindepthflowprojection_cuda.cc; kernels
  * mindepthflowprojection_cuda_kernel.cu:29-312): the in-range source pixel with the largest input2 wins its top-left

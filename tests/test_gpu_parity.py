@@ -878,6 +878,33 @@ def test_fi_blend_writes_into_a_channel_slice(lib):
         lib.filter_interpolate_blend(I0.requires_grad_(), I2, f0, f2, k0, k2, out=cat[:, 4:7])
 
 
+@pytest.mark.parametrize("B,C,H,W", [(1, 196, 40, 96), (2, 12, 64, 192), (1, 7, 33, 70)])
+def test_fi_many_channels_into_a_channel_slice(lib, oracle, B, C, H, W):
+    """VERDICT r1 (missing 7): the many-channel kernel carries the scale / accumulate / batch-stride epilogue, so the warped
+    context features (C = 196) go straight into their slices of the rectify-input concat (DAIN_slowmotion.py:167-181)."""
+    r = U.rng(2950 + C)
+    ctx0, ctx2 = U.image(r, B, C, H, W, "normal"), U.image(r, B, C, H, W, "normal")
+    f0, f2 = U.flow(r, B, H, W, "gauss"), U.flow(r, B, H, W, "stress")
+    k0, k2 = U.filt(r, B, 4, H, W), U.filt(r, B, 4, H, W, "uniform")
+    cat = torch.full((B, 3 + 2 * C + 5, H, W), -5.0, device="cuda")
+    n0 = lib.launch_count()
+    with torch.no_grad():
+        lib.filter_interpolate_into(cu(ctx0), cu(f0), cu(k0), cat[:, 3:3 + C])
+        lib.filter_interpolate_into(cu(ctx2), cu(f2), cu(k2), cat[:, 3 + C:3 + 2 * C])
+        # blend epilogue on the many-channel path: 0.25 * warp0 + 0.75 * warp2 accumulated in place
+        acc = torch.empty((B, C, H, W), device="cuda")
+        lib.filter_interpolate_into(cu(ctx0), cu(f0), cu(k0), acc, scale=0.25)
+        lib.filter_interpolate_into(cu(ctx2), cu(f2), cu(k2), acc, scale=0.75, accumulate=True)
+    assert lib.launch_count() - n0 == 4
+    r0, r2 = oracle.fi_forward("ori", ctx0, f0, k0), oracle.fi_forward("ori", ctx2, f2, k2)
+    U.assert_close(host(cat[:, 3:3 + C]), r0, U.RTOL_FWD, "ctx0 into its slice")
+    U.assert_close(host(cat[:, 3 + C:3 + 2 * C]), r2, U.RTOL_FWD, "ctx2 into its slice")
+    assert (cat[:, :3] == -5).all() and (cat[:, 3 + 2 * C:] == -5).all()
+    U.assert_close(host(acc), 0.25 * r0 + 0.75 * r2, U.RTOL_FWD, "blend on the many-channel path")
+    with pytest.raises(lib.VfidkrError):
+        lib.filter_interpolate_into(cu(ctx0).requires_grad_(), cu(f0), cu(k0), cat[:, 3:3 + C])
+
+
 # ------------------------------------------------------------------------------ SURVEY 8f rank 2: PWCDCNet.warp
 @pytest.mark.parametrize("ac", [True, False])
 @pytest.mark.parametrize("B,C,H,W", [(2, 32, 64, 112), (1, 128, 18, 31), (3, 5, 17, 23), (1, 2, 1, 9), (1, 196, 8, 14)])
@@ -911,6 +938,31 @@ def test_pwc_warp(lib, oracle, B, C, H, W, ac):
         # 0.9999 mask / the floor differ by a little more than the forward tolerance (seen: 1.02e-5); the oracle
         # comparison above is the parity criterion, this one only guards against a different FORMULA
         assert (out.detach() - o * m).abs().max().item() <= 5e-5 * max(1.0, float(np.abs(x).max()))
+
+
+@pytest.mark.parametrize("B,h,w", [(2, 16, 28), (1, 9, 13), (1, 1, 1), (2, 64, 112)])
+@pytest.mark.parametrize("with_depth", [False, True])
+def test_flow_projection_from_lowres_flow_is_differentiable(lib, B, h, w, with_depth):
+    """Gradients through flow_project_lowres (missing 7) equal those of the unfused chain
+    scale -> nn.Upsample(x4, bilinear) -> (Depth)FlowProjection that networks/DAIN.py:306-308 + FlowProject build --
+    PyTorch's own autograd through its own Upsample around this package's projection layer."""
+    r = U.rng(3600 + h + w)
+    lo = (r.standard_normal((B, 2, h, w)) * 0.4).astype(np.float32)
+    d = U.depth_inv(r, B, 4 * h, 4 * w)
+    g = r.standard_normal((B, 2, 4 * h, 4 * w)).astype(np.float32)
+    t_lo, t_d = cu(lo).requires_grad_(), cu(d).requires_grad_()
+    fused = lib.flow_project_lowres(t_lo, 20.0, 0.5, depth=t_d if with_depth else None, fillhole=False)
+    fused.backward(cu(g))
+    r_lo, r_d = cu(lo).requires_grad_(), cu(d).requires_grad_()
+    up = torch.nn.Upsample(scale_factor=4, mode="bilinear", align_corners=False)(20.0 * r_lo * 0.5)
+    ref = lib.DepthFlowProjectionModule(True)(up, r_d) if with_depth else lib.FlowProjectionModule(True)(up)
+    ref.backward(cu(g))
+    assert (fused - ref).abs().max().item() <= 1e-4 * max(1.0, ref.abs().max().item())
+    U.assert_close(host(t_lo.grad), host(r_lo.grad).astype(np.float64), U.RTOL_ATOMIC, "grad wrt the low-resolution flow")
+    if with_depth:
+        U.assert_close(host(t_d.grad), host(r_d.grad).astype(np.float64), U.RTOL_ATOMIC, "grad wrt the depth")
+    with pytest.raises(lib.VfidkrError):     # hole filling is inference-only, as in the reference
+        lib.flow_project_lowres(t_lo, 20.0, 0.5, fillhole=True)
 
 
 # ------------------------------------------------------------------------------ SURVEY 8f rank 4: MinDepthFlowProjection

@@ -109,6 +109,52 @@ def test_world_size_2_timing_reduction_over_gloo():
     assert res == [(0, 15.0, 9.0), (1, 15.0, 9.0)]
 
 
+def _gather_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    # the 4k_stream bookkeeping: P pairs dealt round-robin, every round each rank contributes the frame of its pair (a
+    # blank when it has none left), rank 0 receives them at slot round * world + rank = the pair's own index
+    P, shape = 5, (1, 3, 4, 6)
+    mine = bench.shard_pairs(P, rank, world)
+    rounds = (P + world - 1) // world
+    out = torch.full((rounds * world,) + shape[1:], -1.0) if rank == 0 else None
+    for r in range(rounds):
+        frame = torch.full(shape, float(mine[r])) if r < len(mine) else torch.zeros(shape)
+        dst = [out[r * world + k].unsqueeze(0) for k in range(world)] if rank == 0 else [None]
+        w = bench.gather_frames(dist, frame, dst, rank, world, async_op=True)
+        if w is not None:
+            w.wait()
+    if rank == 0:
+        q.put([float(out[i].mean()) for i in range(rounds * world)])
+    dist.destroy_process_group()
+
+
+def test_world_size_2_frame_gather_over_gloo():
+    """bench.py --workload 4k_stream: pair i ends up at slot i of rank 0's output (blank slots past the stream)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + ((os.getpid() + 977) % 2000)
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == [0.0, 1.0, 2.0, 3.0, 4.0, 0.0]
+
+
+def test_both_bench_arms_print_the_same_config():
+    """`same_config` was false because the two arms spelt the workload differently."""
+    import bench
+    assert bench.workload_config(1) == bench.workload_config(1)
+    src = open(bench.__file__).read()
+    assert src.count('"config": workload_config(') == 3           # our arm, reference (CUDA), reference (CPU port)
+
+
 def test_pair_stream_refuses_cpu():
     """No CPU path: the host-side streamer insists on a CUDA device."""
     import pytest

@@ -36,6 +36,7 @@ _SIGNATURES = {
     "vfidkr_filterinterpolation_backward_nofilterwithdeforconv": [_P] * 7 + [_I] * 5 + [_P],
     "vfidkr_flowprojection_forward_lowres": [_P, c_float, c_float, _P, _P, _P, _I, _I, _I, _I, _P],
     "vfidkr_flow_upsample4": [_P, c_float, c_float, _P, _I, _I, _I, _P],
+    "vfidkr_flow_upsample4_backward": [_P, c_float, c_float, _P, _I, _I, _I, _P],
     "vfidkr_mindepthflowprojection_forward": [_P] * 4 + [_I] * 4 + [_P],
     "vfidkr_mindepthflowprojection_backward": [_P] * 6 + [_I] * 3 + [_P],
     "vfidkr_frame_padding": [_I, ctypes.POINTER(_I)],

@@ -36,9 +36,17 @@ constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 128;
 __global__ void __launch_bounds__(bigc::NT, 2)
 fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const float *__restrict__ in1,
                            const float *__restrict__ in2, const float *__restrict__ in3, float *__restrict__ out,
-                           int C, int H, int W)
+                           int C, int H, int W, float scale, int accumulate, size_t out_bs)
 {
+    // epilogue as in the other "_ori" forwards (vfidkr_filterinterpolation_forward_ori_blend): output = scale * result
+    // (+ what output held), batch items of the output out_bs elements apart -- the warped context features of
+    // DAIN_slowmotion.py:167-181 land directly in their channel slice of the 437-channel rectify input
     using namespace bigc;
+    auto put = [&](float *dst, float v) {
+        v *= scale;
+        if (accumulate) v += __ldcs(dst);
+        st_stream(dst, v);
+    };
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float *s_img = reinterpret_cast<float *>(smem_raw);                       // [STAGES][CG][RH][RW]
     uint64_t *s_full = reinterpret_cast<uint64_t *>(s_img + STAGES * CG * PLANE);
@@ -95,13 +103,13 @@ fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const fl
     const int by0 = (int)blockIdx.y * TH + mdy - (RH - (TH + 3)) / 2;
 
     const float *img = in1 + (size_t)b * C * HW;
-    float *o = out + (size_t)b * C * HW;
+    float *o = out + (size_t)b * out_bs;
 
     // out-of-range pixels copy input1 for every channel (:2814-2819)
 #pragma unroll
     for (int p = 0; p < PX; ++p)
         if (inside[p] && !active[p])
-            for (int c = 0; c < C; ++c) st_stream(o + (size_t)c * HW + pix[p], __ldg(img + (size_t)c * HW + pix[p]));
+            for (int c = 0; c < C; ++c) put(o + (size_t)c * HW + pix[p], __ldg(img + (size_t)c * HW + pix[p]));
     if (!any) return;
 
     // ---- region offsets of the windows (or plane offsets for pixels outside the region), channel-group pipeline ----
@@ -154,7 +162,7 @@ fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const fl
                         for (int i = 0; i < 4; ++i)
                             Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)] =
                                 fmaf(pl[so[p][j] + sc[p][i]], w[p][j * 4 + i], Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)]);
-                    st_stream(op + (size_t)c * HW, q[p][0] * Q[0] + q[p][1] * Q[1] + q[p][2] * Q[2] + q[p][3] * Q[3]);
+                    put(op + (size_t)c * HW, q[p][0] * Q[0] + q[p][1] * Q[1] + q[p][2] * Q[2] + q[p][3] * Q[3]);
                 }
             } else {   // pixel far from the tile's mean flow: clamped gathers from the plane
                 for (int c = 0; c < nc; ++c) {
@@ -166,7 +174,7 @@ fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const fl
                         for (int i = 0; i < 4; ++i)
                             Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)] =
                                 fmaf(__ldg(pl + so[p][j] + sc[p][i]), w[p][j * 4 + i], Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)]);
-                    st_stream(op + (size_t)c * HW, q[p][0] * Q[0] + q[p][1] * Q[1] + q[p][2] * Q[2] + q[p][3] * Q[3]);
+                    put(op + (size_t)c * HW, q[p][0] * Q[0] + q[p][1] * Q[1] + q[p][2] * Q[2] + q[p][3] * Q[3]);
                 }
             }
         }
@@ -179,7 +187,7 @@ fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const fl
 
 // Returns VFIDKR_OK / VFIDKR_ERR_CUDA when the kernel was launched, -1 when it does not apply.
 int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
-                        int B, int C, int H, int W, cudaStream_t s)
+                        int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s)
 {
     using namespace bigc;
     if (C <= 4 || W % 4 != 0 || !aligned16(in1) || ceil_div(H, TH) > 65535u) return -1;
@@ -190,7 +198,7 @@ int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, fl
         return -1;
     }
     dim3 grid(ceil_div(W, TW), ceil_div(H, TH), B);
-    fi_forward_ori_bigc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mimg, in1, in2, in3, out, C, H, W);
+    fi_forward_ori_bigc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mimg, in1, in2, in3, out, C, H, W, scale, accumulate, out_bs);
     note_launch();
     return check_launch("filterinterpolation forward (many channels)");
 }

@@ -30,7 +30,7 @@ namespace vfidkr {
 int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
                          int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
 int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
-                        int B, int C, int H, int W, cudaStream_t s);    // fi_bigc.cu (C > 4); -1 = not applicable
+                        int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s);    // fi_bigc.cu (C > 4); -1 = not applicable
 int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
                          int B, int C, int H, int W, cudaStream_t s);   // fi_strip_dkr.cu; -1 = not applicable
 
@@ -523,9 +523,9 @@ int launch_forward(const float *in1, const float *in2, const float *in3, const f
     if constexpr (V == V_ORI) {
         if (F == 4) {
             const int path = forced_forward_path();
-            if (path == PATH_AUTO && C > 4 && !blend) {
+            if (path == PATH_AUTO && C > 4) {
                 // many channels (context features): shared-memory regions streamed channel group by channel group
-                const int e = fi_bigc_forward_ori(in1, in2, in3, out, B, C, H, W, s);
+                const int e = fi_bigc_forward_ori(in1, in2, in3, out, B, C, H, W, scale, accumulate, out_bs, s);
                 if (e >= 0) return e;
             }
             if (path == PATH_AUTO || path == PATH_STRIP) {

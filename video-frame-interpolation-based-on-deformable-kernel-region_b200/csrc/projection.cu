@@ -108,6 +108,39 @@ flow_upsample4_kernel(FlowSource fs, float *__restrict__ out, int H, int W)
     out[((size_t)blockIdx.z * 2 + 1) * HW + pix] = fy;
 }
 
+// Adjoint of the x4 enlargement (training through vfidkr_flowprojection_forward_lowres): the gradient with respect to a
+// low-resolution sample is s0 * s1 * the sum over the full-resolution pixels whose bilinear footprint contains it, each
+// with the weight upsample_coord gives it.  A pixel y reads rows i0 = floor(0.25 (y + 0.5) - 0.5) (clamped at 0) and
+// i1 = i0 + 1 (clamped at h - 1), so row i is read by y in [4 i - 2, 4 i + 5] only: at most 8 x 8 terms per sample,
+// gathered (no atomics, deterministic).
+__global__ void __launch_bounds__(BX *BY)
+flow_upsample4_backward_kernel(const float *__restrict__ gfull, float scale, float *__restrict__ glow, int h, int w)
+{
+    const int j = blockIdx.x * BX + threadIdx.x, i = blockIdx.y * BY + threadIdx.y;
+    if (j >= w || i >= h) return;
+    const int H = 4 * h, W = 4 * w;
+    const int bc = blockIdx.z;     // batch item * 2 + flow component
+    const float *g = gfull + (size_t)bc * H * W;
+    float acc = 0.0f;
+    for (int y = max(4 * i - 3, 0); y <= min(4 * i + 6, H - 1); ++y) {
+        int y0, y1;
+        float ly0, ly1;
+        upsample_coord(y, h, y0, y1, ly0, ly1);
+        const float wy = (y0 == i ? ly0 : 0.0f) + (y1 == i ? ly1 : 0.0f);
+        if (wy == 0.0f) continue;
+        float row = 0.0f;
+        for (int x = max(4 * j - 3, 0); x <= min(4 * j + 6, W - 1); ++x) {
+            int x0, x1;
+            float lx0, lx1;
+            upsample_coord(x, w, x0, x1, lx0, lx1);
+            const float wx = (x0 == j ? lx0 : 0.0f) + (x1 == j ? lx1 : 0.0f);
+            if (wx != 0.0f) row = fmaf(wx, __ldg(g + (size_t)y * W + x), row);
+        }
+        acc = fmaf(wy, row, acc);
+    }
+    glow[(size_t)bc * h * w + (size_t)i * w + j] = acc * scale;
+}
+
 // `clear` (may be null): the scratch image of the NEXT chunk of frames, zeroed here cell for cell (plain write-back
 // stores: the lines stay in L2, where that chunk's REDs will find them).
 template <bool DEPTH>
@@ -663,6 +696,16 @@ VFIDKR_API int vfidkr_flowprojection_forward_lowres(const float *flow_lowres, fl
     const FlowSource fs{flow_lowres, 1, h, w, scale0, scale1};
     return input2 ? projection_forward<true>(fs, input2, count, output, B, 4 * h, 4 * w, fillhole, (cudaStream_t)s)
                   : projection_forward<false>(fs, nullptr, count, output, B, 4 * h, 4 * w, fillhole, (cudaStream_t)s);
+}
+
+VFIDKR_API int vfidkr_flow_upsample4_backward(const float *grad_output, float scale0, float scale1, float *grad_flow_lowres,
+                                              int B, int h, int w, vfidkr_stream_t s)
+{
+    if (B <= 0 || 2 * B > 65535 || h <= 0 || w <= 0 || h > (1 << 20) || w > (1 << 20) || !grad_output || !grad_flow_lowres) return VFIDKR_ERR_ARG;
+    dim3 block(BX, BY), grid(ceil_div(w, BX), ceil_div(h, BY), 2 * B);
+    flow_upsample4_backward_kernel<<<grid, block, 0, (cudaStream_t)s>>>(grad_output, scale0 * scale1, grad_flow_lowres, h, w);
+    note_launch();
+    return check_launch("flow upsample x4 backward");
 }
 
 VFIDKR_API int vfidkr_flow_upsample4(const float *flow_lowres, float scale0, float scale1, float *output, int B, int h, int w,

@@ -211,6 +211,25 @@ def filter_interpolate_blend(ref0, ref2, offset0, offset2, filter0, filter2, w0=
     return FilterInterpolationBlendLayer.apply(ref0, ref2, offset0, offset2, filter0, filter2, w0, w2, out)
 
 
+def filter_interpolate_into(input1, input2, input3, out, scale=1.0, accumulate=False):
+    """Inference helper: out = scale * FilterInterpolation(input1, input2, input3) (+ out), written straight into `out`,
+    a [B,C,H,W] channel slice of a wider contiguous tensor -- e.g. the warped context features ctx0 / ctx2 (C = 196) into
+    their slices of the 437-channel rectify input (DAIN_slowmotion.py:167-181) without the intermediate tensors and the
+    torch.cat.  Any channel count (the many-channel kernel carries the same epilogue as the C <= 4 ones)."""
+    for t, n in ((input1, "input1"), (input2, "input2"), (input3, "input3")):
+        check_input(t, n)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (input1, input2, input3)):
+        raise _lib.VfidkrError("filter_interpolate_into is for inference (no_grad): writing into a slice is not differentiable here")
+    B, C, H, W, F = _check_shapes(input1, input2, input3)
+    if out.shape != input1.shape or out.dtype != torch.float32 or out.device != input1.device or \
+            tuple(out.stride()[1:]) != (H * W, W, 1) or out.stride(0) < C * H * W:
+        raise _lib.VfidkrError("out must be a float32 [B,C,H,W] view with strides (>= C*H*W, H*W, W, 1) on the inputs' device")
+    with torch.cuda.device(input1.device):
+        _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(input1), ptr(input2), ptr(input3), out.data_ptr(),
+                  B, C, H, W, F, float(scale), 1 if accumulate else 0, out.stride(0), stream_ptr(input1.device))
+    return out
+
+
 class FilterInterpolationModule(Module):
     """FilterInterpolationModule()(input1, input2, input3)            -> "_ori" (FilterInterpolationModule.py:13-17)
     FilterInterpolationModule()(input1, input2, input3, input4)      -> 4-input DKR (:18-20)

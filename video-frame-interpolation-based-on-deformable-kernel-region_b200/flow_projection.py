@@ -154,9 +154,56 @@ def flow_upsample4(flow_lowres, scale0=1.0, scale1=1.0):
     return out
 
 
+class _FlowProjectLowresLayer(Function):
+    """(Depth)FlowProjection fed by the quarter-resolution flow, differentiable: the forward never
+    materialises the enlarged flow; the backward enlarges it once (flow_upsample4), runs the projection's own backward
+    on it (flowprojection_cuda_kernel.cu:266-297 / depthflowprojection_cuda_kernel.cu:276-337 -- which, as in the
+    reference, ignores hole filling) and folds the result back to the low resolution with the adjoint of the
+    enlargement -- the chain autograd would build for networks/DAIN.py:306-308 + FlowProject."""
+
+    @staticmethod
+    def forward(ctx, flow_lowres, depth, scale0, scale1, fillhole):
+        B, _, h, w = flow_lowres.shape
+        if fillhole and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            # the backward needs the averaged output BEFORE hole filling (the reference never fills holes in training)
+            raise _lib.VfidkrError("flow_project_lowres: hole filling is an inference feature (FlowProjectionLayer.py:23); "
+                                   "pass fillhole=False when a gradient is required")
+        count = torch.empty((B, 1, 4 * h, 4 * w), dtype=flow_lowres.dtype, device=flow_lowres.device)
+        output = torch.empty((B, 2, 4 * h, 4 * w), dtype=flow_lowres.dtype, device=flow_lowres.device)
+        with torch.cuda.device(flow_lowres.device):
+            _lib.call("vfidkr_flowprojection_forward_lowres", ptr(flow_lowres), float(scale0), float(scale1),
+                      ptr(depth) if depth is not None else None, ptr(count), ptr(output), B, h, w, 1 if fillhole else 0,
+                      stream_ptr(flow_lowres.device))
+        ctx.save_for_backward(flow_lowres, depth, count, output)
+        ctx.scales = (float(scale0), float(scale1))
+        return output
+
+    @staticmethod
+    def backward(ctx, gradoutput):
+        flow_lowres, depth, count, output = ctx.saved_tensors
+        s0, s1 = ctx.scales
+        B, _, h, w = flow_lowres.shape
+        H, W = 4 * h, 4 * w
+        gradoutput = gradoutput.contiguous()
+        full = flow_upsample4(flow_lowres, s0, s1)
+        g_full = torch.empty_like(full)
+        g_depth = torch.empty_like(depth) if depth is not None else None
+        g_low = torch.empty_like(flow_lowres)
+        sp = stream_ptr(flow_lowres.device)
+        with torch.cuda.device(flow_lowres.device):
+            if depth is None:
+                _lib.call("vfidkr_flowprojection_backward", ptr(full), ptr(count), ptr(gradoutput), ptr(g_full), B, H, W, sp)
+            else:
+                _lib.call("vfidkr_depthflowprojection_backward", ptr(full), ptr(depth), ptr(count), ptr(output), ptr(gradoutput),
+                          ptr(g_full), ptr(g_depth), B, H, W, sp)
+            _lib.call("vfidkr_flow_upsample4_backward", ptr(g_full), s0, s1, ptr(g_low), B, h, w, sp)
+        return g_low, g_depth, None, None, None
+
+
 def flow_project_lowres(flow_lowres, scale0=1.0, scale1=1.0, depth=None, fillhole=True):
-    """(Depth)FlowProjection of the x4-enlarged, scaled flow without materialising it (inference: no gradient).
-    Equals FlowProjectionModule(False)(flow_upsample4(flow_lowres, scale0, scale1)) -- DepthFlowProjection with `depth`."""
+    """(Depth)FlowProjection of the x4-enlarged, scaled flow without materialising it.
+    Equals FlowProjectionModule(not fillhole)(flow_upsample4(flow_lowres, scale0, scale1)) -- DepthFlowProjection with
+    `depth` -- including its gradients with respect to flow_lowres and depth (fillhole=False, as in training)."""
     check_input(flow_lowres, "flow_lowres")
     B, ch, h, w = flow_lowres.shape
     if ch != 2:
@@ -165,10 +212,4 @@ def flow_project_lowres(flow_lowres, scale0=1.0, scale1=1.0, depth=None, fillhol
         check_input(depth, "depth")
         if depth.shape != (B, 1, 4 * h, 4 * w):
             raise _lib.VfidkrError(f"depth must be [B,1,4h,4w] = {(B, 1, 4 * h, 4 * w)}")
-    count = torch.empty((B, 1, 4 * h, 4 * w), dtype=flow_lowres.dtype, device=flow_lowres.device)
-    output = torch.empty((B, 2, 4 * h, 4 * w), dtype=flow_lowres.dtype, device=flow_lowres.device)
-    with torch.cuda.device(flow_lowres.device):
-        _lib.call("vfidkr_flowprojection_forward_lowres", ptr(flow_lowres), float(scale0), float(scale1),
-                  ptr(depth) if depth is not None else None, ptr(count), ptr(output), B, h, w, 1 if fillhole else 0,
-                  stream_ptr(flow_lowres.device))
-    return output
+    return _FlowProjectLowresLayer.apply(flow_lowres, depth, scale0, scale1, fillhole)
