@@ -1,0 +1,130 @@
+// umma_tf32.cu -- bring-up test of the tcgen05 path used by the tensor-core correlation prototype: one CTA computes
+// D[128 x N] = A[128 x K] * B[N x K]^T with tcgen05.mma kind::tf32 (accumulator in TMEM), operands written to shared memory
+// by the threads in the canonical K-major no-swizzle core-matrix layout, result read back with tcgen05.ld and compared
+// with a CPU product.  Also times a loop of MMAs (tensor rate at M = 128).  Inputs are exactly representable in tf32.
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o _build/umma_tf32 umma_tf32.cu && timeout 60 ./_build/umma_tf32
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+#include <cuda_runtime.h>
+
+constexpr int M = 128, N = 192, K = 32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// K-major, no swizzle: element (row, k) of an R-row operand lives at [(k / 4)][row][k % 4] (floats):
+// core matrix = 8 rows x 16 bytes, 8-row groups 128 B apart (SBO), K groups R * 16 B apart (LBO)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes)
+{
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n)
+{
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);   // f32 accum, tf32 x tf32, K-major both
+}
+
+__global__ void __launch_bounds__(128) umma_kernel(const float *A, const float *B, float *D, int reps, unsigned long long *cycles)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *sA = reinterpret_cast<float *>(smem);            // [K/4][M][4]
+    float *sB = sA + M * K;                                  // [K/4][N][4]
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < M * K; i += 128) { const int m = i / K, k = i % K; sA[((k >> 2) * M + m) * 4 + (k & 3)] = A[m * K + k]; }
+    for (int i = tid; i < N * K; i += 128) { const int n = i / K, k = i % K; sB[((k >> 2) * N + n) * 4 + (k & 3)] = B[n * K + k]; }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // the threads' operand stores -> visible to the tensor core (async proxy)
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base;
+    const uint32_t idesc = make_idesc(M, N);
+    long long t0 = clock64();
+    if (tid == 0) {
+        for (int r = 0; r < reps; ++r)
+            for (int ks = 0; ks < K / 8; ++ks) {
+                const uint64_t da = make_desc(smem_u32(sA) + ks * 2 * (M * 16), M * 16, 128);
+                const uint64_t db = make_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+                const uint32_t acc = (r > 0 || ks > 0) ? 1u : 0u;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+            }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    // everybody waits for the MMAs
+    {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    }
+    long long t1 = clock64();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    // warp w reads TMEM lanes 32 w .. 32 w + 31 (its own quarter), 32 columns at a time
+    for (int c0 = 0; c0 < N; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                     "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                       "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                       "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 32; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+    if (tid == 0 && cycles) *cycles = (unsigned long long)(t1 - t0);
+}
+
+int main()
+{
+    std::vector<float> hA(M * K), hB(N * K), hD(M * N), ref(M * N);
+    srand(1);
+    for (auto &v : hA) v = (float)(rand() % 17 - 8) / 8.0f;
+    for (auto &v : hB) v = (float)(rand() % 17 - 8) / 8.0f;
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            double s = 0;
+            for (int k = 0; k < K; ++k) s += (double)hA[m * K + k] * hB[n * K + k];
+            ref[m * N + n] = (float)s;
+        }
+    float *dA, *dB, *dD;
+    unsigned long long *dc, hc = 0;
+    cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dB, hB.size() * 4); cudaMalloc(&dD, hD.size() * 4); cudaMalloc(&dc, 8);
+    cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice);
+    const size_t smem = (size_t)(M + N) * K * 4 + 128;
+    cudaFuncSetAttribute(umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma_kernel<<<1, 128, smem>>>(dA, dB, dD, 1, dc);
+    cudaError_t e = cudaDeviceSynchronize();
+    printf("launch: %s\n", cudaGetErrorString(e));
+    if (e != cudaSuccess) return 1;
+    cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0;
+    int bad = 0;
+    for (int i = 0; i < M * N; ++i) { const double d = fabs((double)hD[i] - ref[i]); if (d > maxerr) maxerr = d; if (d > 1e-4) ++bad; }
+    printf("D = A * B^T (tf32, M=%d N=%d K=%d): max |err| = %.3g, %d of %d entries off; D[0][0..3] = %g %g %g %g (ref %g %g %g %g)\n", M, N, K,
+           maxerr, bad, M * N, hD[0], hD[1], hD[2], hD[3], ref[0], ref[1], ref[2], ref[3]);
+    // rate: many MMAs back to back on one SM
+    const int reps = 2000;
+    umma_kernel<<<1, 128, smem>>>(dA, dB, dD, reps, dc);
+    e = cudaDeviceSynchronize();
+    cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+    printf("rate: %s, %d x %d MMAs of %dx%dx8 in %llu cycles = %.1f MAC/clk/SM (tf32, cta_group::1)\n", cudaGetErrorString(e), reps, K / 8, M, N, hc,
+           (double)reps * (K / 8) * M * N * 8 / (double)hc);
+    return bad ? 2 : 0;
+}
