@@ -63,6 +63,10 @@ const char *vfidkr_last_error(void);
  * 0 = automatic (production), 1 = strip kernels, 2 = tile kernel, 3 = direct kernels -- so that the parity tests
  * can hold every implementation to the oracle.  Process-wide; returns the previous setting, -1 on a bad value. */
 int vfidkr_debug_force_forward_path(int path);
+/* TEST / MEASUREMENT HOOK: implementation of the correlation forward (kernel_size 1, strides 1, max_displacement 4, pad 4) --
+ * 0 = automatic, 1 = the SIMT register-tile kernels, 2 = the tensor-core kernel (tcgen05.mma kind::tf32, 3 x TF32 split,
+ * accumulator in tensor memory; correlation_tc.cu).  Process-wide; returns the previous setting, -1 on a bad value. */
+int vfidkr_debug_force_correlation_path(int path);
 /* Return the scratch memory the library's private pool has cached on the current device to the device
  * (see "Common contract"; blocks still in use by enqueued work are not affected).  No reference counterpart. */
 int vfidkr_trim_scratch(void);

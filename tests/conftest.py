@@ -51,6 +51,7 @@ def _forward_path_is_automatic_again():
     mod = sys.modules.get("vfidkr_b200")
     if mod is not None and getattr(mod._lib, "_lib", None) is not None:
         mod.debug_force_forward_path(None)
+        mod.debug_force_correlation_path(None)
 
 
 def pytest_terminal_summary(terminalreporter):

@@ -441,6 +441,39 @@ def test_correlation_both_directions_in_one_launch(lib, oracle, B, C, H, W, pad,
     U.assert_close(host(t2.grad), a2 + b2, U.RTOL_FWD, "pair: gradinput2")
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 40, 64), (1, 8, 12, 20), (8, 196, 18, 31), (8, 128, 36, 62), (3, 16, 72, 124),
+                                     (1, 5, 9, 13), (2, 64, 33, 50), (1, 32, 96, 256)])
+def test_correlation_tensor_core_path(lib, oracle, B, C, H, W):
+    """correlation_tc.cu (tcgen05.mma kind::tf32, 3 x TF32 split, accumulator in tensor memory) against the oracle at the
+    forward tolerance and against the SIMT kernel: ragged patches, odd widths, channel counts that are not a multiple of
+    the 32-channel stage (zero-filled), the PWC level shapes."""
+    r = U.rng(1790 + C + W)
+    f1, f2 = U.image(r, B, C, H, W, "normal"), U.image(r, B, C, H, W, "normal")
+    mod = lib.Correlation(4, 1, 4, 1, 1, 1)
+    lib.debug_force_correlation_path("tensor")
+    tc = mod(cu(f1), cu(f2))
+    lib.debug_force_correlation_path("simt")
+    simt = mod(cu(f1), cu(f2))
+    lib.debug_force_correlation_path(None)
+    ref = oracle.correlation_forward(f1, f2, 4, 1, 4, 1, 1)
+    U.assert_close(host(tc), ref, U.RTOL_FWD, "tensor-core correlation vs oracle")
+    U.assert_close(host(simt), ref, U.RTOL_FWD, "SIMT correlation vs oracle")
+    print(f"tensor vs SIMT: {U.max_err(host(tc), host(simt).astype(np.float64)):.2e}; tensor vs oracle: {U.max_err(host(tc), ref):.2e}; "
+          f"SIMT vs oracle: {U.max_err(host(simt), ref):.2e}")
+
+
+@pytest.mark.parametrize("name", ["corr_pwc", "corr_pwc_c196", "corr_wide_splitk", "corr_wide_tiled"])
+def test_correlation_tensor_core_path_reproduces_reference_fixtures(lib, name):
+    """The golden fixtures of the reference's own correlation kernel, through the tensor-core path."""
+    import test_golden as TG
+    ins, ref = TG.load(name)
+    lib.debug_force_correlation_path("tensor")
+    c = TG.G.CASES[name]
+    out = lib.Correlation(c["pad"], c["k"], c["md"], c["s1"], c["s2"], 1)(cu(ins["input1"]), cu(ins["input2"]))
+    lib.debug_force_correlation_path(None)
+    TG.compare(name, dict(out=host(out)), {"out": ref["out"]}, ins)
+
+
 def test_correlation_of_ones_on_gpu(lib):
     f = torch.ones(1, 8, 10, 12, device="cuda")
     out = lib.Correlation(4, 1, 4, 1, 1, 1)(f, f)

@@ -5,7 +5,8 @@ repository root maps that name onto this directory).  Everything here is a thin 
 C ABI of libvfidkr_b200.so (include/vfidkr_b200.h); there is no CPU or framework fallback.
 """
 from . import _lib
-from ._lib import VfidkrError, abi_version, debug_force_forward_path, launch_count, trim_scratch
+from ._lib import (VfidkrError, abi_version, debug_force_correlation_path, debug_force_forward_path, launch_count,
+                   trim_scratch)
 from .correlation import Correlation, CorrelationFunction, correlation_output_shape, correlation_pair
 from .filter_interpolation import (FilterInterpolationBlendLayer, filter_interpolate_blend, filter_interpolate_into,
                                    FilterInterpolationLayer, FilterInterpolationLayerDeforConv,

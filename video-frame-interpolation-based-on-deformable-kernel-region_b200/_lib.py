@@ -61,6 +61,7 @@ _SIGNATURES = {
     "vfidkr_abi_version": [],
     "vfidkr_trim_scratch": [],
     "vfidkr_debug_force_forward_path": [_I],
+    "vfidkr_debug_force_correlation_path": [_I],
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + ["vfidkr_launch_count", "vfidkr_last_error"])
 
@@ -107,6 +108,14 @@ def debug_force_forward_path(path) -> int:
     prev = load().vfidkr_debug_force_forward_path(_PATHS[path])
     if prev < 0:
         raise VfidkrError("vfidkr_debug_force_forward_path rejected the value")
+    return prev
+
+
+def debug_force_correlation_path(path) -> int:
+    """TEST / MEASUREMENT HOOK: None/"auto", "simt" or "tensor" (tcgen05 kind::tf32, 3 x TF32) for the correlation forward."""
+    prev = load().vfidkr_debug_force_correlation_path({None: 0, "auto": 0, "simt": 1, "tensor": 2}[path])
+    if prev < 0:
+        raise VfidkrError("vfidkr_debug_force_correlation_path rejected the value")
     return prev
 
 

@@ -21,7 +21,7 @@ OBJ_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "libvfidkr_b200.so"
 
 SOURCES = ["capi.cu", "filterinterpolation.cu", "fi_strip.cu", "fi_strip_dkr.cu", "fi_bigc.cu", "projection.cu", "interpolation.cu", "separableconv.cu",
-           "correlation.cu", "pwcwarp.cu", "frameio.cu"]
+           "correlation.cu", "correlation_tc.cu", "pwcwarp.cu", "frameio.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -17,13 +17,20 @@
 // tcgen05 is not used: the 9-wide band of the (T+8)-wide product wastes >= 89% of a GEMM tile and
 // 1e-5 parity needs a 3xTF32 split, which costs more tensor time than the SIMT kernel.
 #include <algorithm>
+#include <atomic>
 #include <cstring>
 
 #include "common.cuh"
 #include "tma.cuh"
 
 namespace vfidkr {
+
+int corr_forward_tc(const float *in1, const float *in2, float *out, int B, int C, int H, int W, cudaStream_t s);   // correlation_tc.cu; -1 = not applicable
+
 namespace {
+
+// test / measurement hook: 0 = automatic, 1 = SIMT kernels only, 2 = tensor-core kernel (tcgen05, 3 x TF32) wherever it applies
+std::atomic<int> g_corr_path{0};
 
 struct CorrShape {
     int kr, dr, ds, oc, oh, ow;
@@ -763,11 +770,21 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
     const CorrShape cs = corr_shape(H, W, pad, k, md, s1, s2);
     if (cs.oh <= 0 || cs.ow <= 0) return VFIDKR_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (k == 1 && s1 == 1 && s2 == 1 && md == 4 && pad == 4 && g_corr_path.load(std::memory_order_relaxed) == 2) {
+        const int e = corr_forward_tc(input1, input2, output, B, C, H, W, s);
+        if (e >= 0) return e;
+    }
     if (k == 1 && s1 == 1 && s2 == 1 && md == 4) return corr_forward_fast(input1, input2, output, nullptr, B, C, H, W, pad, md, cs, s);
     dim3 block(32, 8), grid(ceil_div(cs.ow, 32), ceil_div(cs.oh, 8), B);
     corr_forward_generic_kernel<<<grid, block, 0, s>>>(input1, input2, output, C, H, W, pad, k, md, s1, s2, cs);
     note_launch();
     return check_launch("correlation forward");
+}
+
+VFIDKR_API int vfidkr_debug_force_correlation_path(int path)
+{
+    if (path < 0 || path > 2) return -1;
+    return g_corr_path.exchange(path, std::memory_order_relaxed);
 }
 
 // Both temporal directions of a pyramid level at once: output12 = correlation(input1, input2), output21 =
