@@ -15,11 +15,11 @@
 //   warps 0-3  epilogue: TMEM -> registers (tcgen05.ld, a warp owns the 32 TMEM lanes = pixels of its quarter), the
 //              lane-dependent band extraction goes through a private shared-memory row, scaled stores to the 81 planes;
 //   warps 4-11 stagers: f1 patch / f2 neighbourhood chunk of 32 channels from global memory (L2), hi / lo split, written
-//              to shared memory in the canonical K-major no-swizzle core-matrix layout ([K/4][rows][4] floats: 8-row groups
-//              128 B apart, K groups rows*16 B apart) -- the split needs a register pass anyway, so no TMA / swizzle;
+//              to shared memory in the canonical K-major no-swizzle core-matrix layout ([K/4][rows/8][8][4] floats, 8-row
+//              groups 144 B apart) -- the split needs a register pass anyway, so no TMA / swizzle;
 //   warp 12    one thread issues the MMAs (12 per stage: 4 K-steps x 3 passes), commits stage-free and accumulator-full.
 // A unit of work is (patch, neighbourhood half); the two 192-column accumulators ping-pong in TMEM (512 columns), so the
-// epilogue of one unit overlaps the MMAs of the next; operand stages form a 2-deep ring (80 KB each).
+// epilogue of one unit overlaps the MMAs of the next; operand stages form a 2-deep ring (90 KB each).
 #include "common.cuh"
 #include "tma.cuh"
 
@@ -31,10 +31,16 @@ constexpr int PR = 8, PC = 16, M = PR * PC;                 // output patch
 constexpr int NR = 8, NC = PC + 8, NH = NR * NC;            // one neighbourhood half: 8 rows x 24 columns = 192
 constexpr int KC = 32, KG = KC / 4;                         // channels per stage, groups of four
 constexpr int STAGES = 2;
-constexpr int A_FLOATS = M * KC, B_FLOATS = NH * KC;
+// shared-memory operand layout (K-major, no swizzle): [K group of 4 channels][8-row group][8 rows][4 floats]; the 8-row
+// groups are SBO = 144 bytes apart instead of 128 -- 16 bytes of padding that make the stagers' 16-byte stores (lanes = groups
+// of four pixels, 64 bytes apart) conflict-free; K groups are LBO = (rows / 8) * SBO apart
+constexpr int SBO = 144, SBO_F = SBO / 4;
+constexpr int A_LBO = (M / 8) * SBO, B_LBO = (NH / 8) * SBO;
+constexpr int A_FLOATS = KG * A_LBO / 4, B_FLOATS = KG * B_LBO / 4;
 constexpr int STAGE_FLOATS = 2 * (A_FLOATS + B_FLOATS);     // hi + lo of both operands
+__host__ __device__ constexpr int row_off(int m) { return (m >> 3) * SBO_F + (m & 7) * 4; }   // float offset of row m inside a K group
 constexpr int EPI_WARPS = 4, STAGE_WARPS = 8, NTHREADS = (EPI_WARPS + STAGE_WARPS + 1) * 32;
-constexpr int EPI_PITCH = 25;
+constexpr int EPI_PITCH = 28;                               // 16-byte aligned rows, conflict-free 128-bit stores
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_FLOATS * sizeof(float) + (size_t)M * EPI_PITCH * sizeof(float) + 256;
 constexpr uint32_t TMEM_COLS = 512, ACC_STRIDE = 256;       // accumulator b lives at columns [256 b, 256 b + 192)
 
@@ -64,16 +70,21 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8])
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float to_tf32(float v)
+// 3 x TF32 split: hi = v with the mantissa cut to TF32's 10 bits (a mask: full-rate, where cvt.rna.tf32 issues at 1/8 of the
+// fp32 rate and there are two per operand element), lo = v - hi (exact in fp32; the tensor core reads its top 19 bits).
+// |v - hi - tf32(lo)| <= 2^-21 |v|: the dropped lo*lo term and this residual are ~1e-6 of a product, inside the 1e-5 parity bound.
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ bool try_wait_hint(uint64_t *bar, uint32_t parity)
 {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(2000u) : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void wait_phase(uint64_t *bar, uint32_t parity)
 {
-    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
-        if (spins > (1u << 26)) __trap();      // a protocol error traps instead of hanging the GPU
+    for (uint32_t spins = 0; !try_wait_hint(bar, parity); ++spins)     // suspended in hardware between probes: a waiting warp costs no issue slots
+        if (spins > (1u << 24)) __trap();      // a protocol error traps instead of hanging the GPU
 }
 // a whole warp waits: one lane polls, the warp re-converges behind it
 __device__ __forceinline__ void warp_wait_phase(uint64_t *bar, uint32_t parity, int lane)
@@ -85,7 +96,8 @@ __device__ __forceinline__ void warp_wait_phase(uint64_t *bar, uint32_t parity, 
 
 __global__ void __launch_bounds__(ctc::NTHREADS, 1)
 corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
-                       int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, const FastDiv div_tx, const FastDiv div_tile_img)
+                       int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, const FastDiv div_tx, const FastDiv div_tile_img,
+                       int vec4)
 {
     using namespace ctc;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -125,47 +137,111 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + STAGE_WARPS) {
         // ================================ stagers ================================
         const int st = tid - EPI_WARPS * 32;                         // 0 .. 255
-        constexpr int A_TASKS = KG * M, TASKS = KG * (M + NH), PER = TASKS / (STAGE_WARPS * 32);   // 2560 tasks, 10 per thread
-        static_assert(TASKS % (STAGE_WARPS * 32) == 0, "tasks per stager thread");
         int it = 0;
-        for (int i = 0; i < my_tiles; ++i) {
-            int b, y0, x0;
-            decode(i, b, y0, x0);
-            const float *f1 = in1 + (size_t)b * C * HW, *f2 = in2 + (size_t)b * C * HW;
-            for (int half = 0; half < 2; ++half)
-                for (int ch = 0; ch < nchunks; ++ch, ++it) {
-                    const int s = it % STAGES;
-                    if (it >= STAGES) warp_wait_phase(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1), lane);   // the MMAs that read this stage are done
-                    float *sa_hi = s_stage + s * STAGE_FLOATS, *sa_lo = sa_hi + A_FLOATS, *sb_hi = sa_lo + A_FLOATS, *sb_lo = sb_hi + B_FLOATS;
-                    float v[PER][4];
+        if (vec4) {
+            // Rows are whole float4s (W % 4 == 0, aligned bases): a task is (K group g of four channels, four adjacent
+            // pixels) = four 128-bit loads, one per channel plane, transposed in registers into four 16-byte rows
+            // [pixel][4 channels] of the operand layout.  Patch: 8 x 32 tasks (one per thread); neighbourhood half:
+            // 8 x 48 tasks (one per thread + one more for threads 0 .. 127).  Loop-invariant geometry first.
+            const int ga = st >> 5, pra = (st & 31) >> 2, pca = (st & 3) * 4;                       // A task
+            const int offa = ga * (A_LBO / 4) + row_off(pra * PC + pca);
+            int gb[2], nrb[2], ncb[2], offb[2];
 #pragma unroll
-                    for (int k = 0; k < PER; ++k) {      // every load of the stage before the first conversion / store
-                        const int q = st + k * (STAGE_WARPS * 32);
-                        const bool isA = k < A_TASKS / (STAGE_WARPS * 32);      // compile-time per k: tasks 0 .. 1023 are the patch
-                        const int qq = isA ? q : q - A_TASKS;
-                        const int g = isA ? qq / M : qq / NH, m = isA ? qq % M : qq % NH;
-                        // pixel of this row: patch (r, col) or neighbourhood (nr, nc) of this half, displaced by -4
-                        const int y = isA ? y0 + m / PC : y0 - 4 + half * NR + m / NC;
-                        const int x = isA ? x0 + m % PC : x0 - 4 + m % NC;
-                        const bool in = y >= 0 && y < H && x >= 0 && x < W;
-                        const float *src = (isA ? f1 : f2) + (size_t)(ch * KC + 4 * g) * HW + (in ? (size_t)y * W + x : 0);
+            for (int k = 0; k < 2; ++k) {
+                const int q = st + 256 * k;                                                        // B task (k = 1: q < 384 only)
+                gb[k] = q / 48; nrb[k] = (q % 48) / 6; ncb[k] = (q % 6) * 4;
+                offb[k] = gb[k] * (B_LBO / 4) + row_off(nrb[k] * NC + ncb[k]);
+            }
+            const bool second = st < 128;
+            for (int i = 0; i < my_tiles; ++i) {
+                int b, y0, x0;
+                decode(i, b, y0, x0);
+                const float *f1 = in1 + (size_t)b * C * HW, *f2 = in2 + (size_t)b * C * HW;
+                for (int half = 0; half < 2; ++half)
+                    for (int ch = 0; ch < nchunks; ++ch, ++it) {
+                        const int s = it % STAGES;
+                        if (it >= STAGES) warp_wait_phase(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1), lane);   // the MMAs that read this stage are done
+                        float *sa_hi = s_stage + s * STAGE_FLOATS, *sa_lo = sa_hi + A_FLOATS, *sb_hi = sa_lo + A_FLOATS, *sb_lo = sb_hi + B_FLOATS;
+                        float4 v[3][4];
+                        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        {   // every load of the stage before the first store
+                            const int y = y0 + pra, x = x0 + pca, c0 = ch * KC + 4 * ga;
+                            const bool in = y < H && x < W;
+                            const float *src = f1 + (size_t)c0 * HW + (in ? (size_t)y * W + x : 0);
 #pragma unroll
-                        for (int c = 0; c < 4; ++c) v[k][c] = (in && ch * KC + 4 * g + c < C) ? __ldg(src + (size_t)c * HW) : 0.0f;
+                            for (int c = 0; c < 4; ++c) v[0][c] = (in && c0 + c < C) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * HW)) : z4;
+                        }
+#pragma unroll
+                        for (int k = 0; k < 2; ++k) {
+                            const int y = y0 - 4 + half * NR + nrb[k], x = x0 - 4 + ncb[k], c0 = ch * KC + 4 * gb[k];
+                            const bool in = (k == 0 || second) && y >= 0 && y < H && x >= 0 && x < W;
+                            const float *src = f2 + (size_t)c0 * HW + (in ? (size_t)y * W + x : 0);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) v[1 + k][c] = (in && c0 + c < C) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * HW)) : z4;
+                        }
+                        auto put = [&](float *hi_base, float *lo_base, const float4 (&t)[4]) {
+                            const float px[4][4] = {{t[0].x, t[1].x, t[2].x, t[3].x}, {t[0].y, t[1].y, t[2].y, t[3].y},
+                                                    {t[0].z, t[1].z, t[2].z, t[3].z}, {t[0].w, t[1].w, t[2].w, t[3].w}};   // [pixel][channel]
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float4 hi, lo;
+                                hi.x = tf32_hi(px[j][0]); hi.y = tf32_hi(px[j][1]); hi.z = tf32_hi(px[j][2]); hi.w = tf32_hi(px[j][3]);
+                                lo.x = px[j][0] - hi.x; lo.y = px[j][1] - hi.y; lo.z = px[j][2] - hi.z; lo.w = px[j][3] - hi.w;
+                                *reinterpret_cast<float4 *>(hi_base + 4 * j) = hi;      // rows m .. m + 3 of one 8-row group: 16 bytes apart
+                                *reinterpret_cast<float4 *>(lo_base + 4 * j) = lo;
+                            }
+                        };
+                        put(sa_hi + offa, sa_lo + offa, v[0]);
+                        put(sb_hi + offb[0], sb_lo + offb[0], v[1]);
+                        if (second) put(sb_hi + offb[1], sb_lo + offb[1], v[2]);
+                        fence_proxy_async();             // this thread's operand stores -> visible to the tensor core (async proxy)
+                        mbar_arrive(&full[s]);
                     }
+            }
+        } else {
+            // any width / alignment: a task is (K group, one pixel), four scalar loads
+            constexpr int A_TASKS = KG * M, TASKS = KG * (M + NH), PER = TASKS / (STAGE_WARPS * 32);   // 2560 tasks, 10 per thread
+            static_assert(TASKS % (STAGE_WARPS * 32) == 0, "tasks per stager thread");
+            for (int i = 0; i < my_tiles; ++i) {
+                int b, y0, x0;
+                decode(i, b, y0, x0);
+                const float *f1 = in1 + (size_t)b * C * HW, *f2 = in2 + (size_t)b * C * HW;
+                for (int half = 0; half < 2; ++half)
+                    for (int ch = 0; ch < nchunks; ++ch, ++it) {
+                        const int s = it % STAGES;
+                        if (it >= STAGES) warp_wait_phase(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1), lane);
+                        float *sa_hi = s_stage + s * STAGE_FLOATS, *sa_lo = sa_hi + A_FLOATS, *sb_hi = sa_lo + A_FLOATS, *sb_lo = sb_hi + B_FLOATS;
+                        float v[PER][4];
 #pragma unroll
-                    for (int k = 0; k < PER; ++k) {
-                        const int q = st + k * (STAGE_WARPS * 32);
-                        const bool isA = k < A_TASKS / (STAGE_WARPS * 32);
-                        const int qq = isA ? q : q - A_TASKS;      // == (group g) * rows + row: the layout's own index
-                        float4 hi, lo;
-                        hi.x = to_tf32(v[k][0]); hi.y = to_tf32(v[k][1]); hi.z = to_tf32(v[k][2]); hi.w = to_tf32(v[k][3]);
-                        lo.x = to_tf32(v[k][0] - hi.x); lo.y = to_tf32(v[k][1] - hi.y); lo.z = to_tf32(v[k][2] - hi.z); lo.w = to_tf32(v[k][3] - hi.w);
-                        *reinterpret_cast<float4 *>((isA ? sa_hi : sb_hi) + 4 * qq) = hi;
-                        *reinterpret_cast<float4 *>((isA ? sa_lo : sb_lo) + 4 * qq) = lo;
+                        for (int k = 0; k < PER; ++k) {      // every load of the stage before the first store
+                            const int q = st + k * (STAGE_WARPS * 32);
+                            const bool isA = k < A_TASKS / (STAGE_WARPS * 32);      // compile-time per k: tasks 0 .. 1023 are the patch
+                            const int qq = isA ? q : q - A_TASKS;
+                            const int g = isA ? qq / M : qq / NH, m = isA ? qq % M : qq % NH;
+                            const int y = isA ? y0 + m / PC : y0 - 4 + half * NR + m / NC;
+                            const int x = isA ? x0 + m % PC : x0 - 4 + m % NC;
+                            const bool in = y >= 0 && y < H && x >= 0 && x < W;
+                            const float *src = (isA ? f1 : f2) + (size_t)(ch * KC + 4 * g) * HW + (in ? (size_t)y * W + x : 0);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) v[k][c] = (in && ch * KC + 4 * g + c < C) ? __ldg(src + (size_t)c * HW) : 0.0f;
+                        }
+#pragma unroll
+                        for (int k = 0; k < PER; ++k) {
+                            const int q = st + k * (STAGE_WARPS * 32);
+                            const bool isA = k < A_TASKS / (STAGE_WARPS * 32);
+                            const int qq = isA ? q : q - A_TASKS;
+                            const int g = isA ? qq / M : qq / NH, m = isA ? qq % M : qq % NH;
+                            const int off = g * ((isA ? A_LBO : B_LBO) / 4) + row_off(m);
+                            float4 hi, lo;
+                            hi.x = tf32_hi(v[k][0]); hi.y = tf32_hi(v[k][1]); hi.z = tf32_hi(v[k][2]); hi.w = tf32_hi(v[k][3]);
+                            lo.x = v[k][0] - hi.x; lo.y = v[k][1] - hi.y; lo.z = v[k][2] - hi.z; lo.w = v[k][3] - hi.w;
+                            *reinterpret_cast<float4 *>((isA ? sa_hi : sb_hi) + off) = hi;
+                            *reinterpret_cast<float4 *>((isA ? sa_lo : sb_lo) + off) = lo;
+                        }
+                        fence_proxy_async();
+                        mbar_arrive(&full[s]);
                     }
-                    fence_proxy_async();             // this thread's operand stores -> visible to the tensor core (async proxy)
-                    mbar_arrive(&full[s]);
-                }
+            }
         }
     } else if (warp == EPI_WARPS + STAGE_WARPS) {
         // ================================ MMA issuer ================================
@@ -185,9 +261,9 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
                         const uint32_t b_hi = a_lo + A_FLOATS * 4, b_lo = b_hi + B_FLOATS * 4;
 #pragma unroll
                         for (int ks = 0; ks < KC / 8; ++ks) {
-                            const uint32_t oa = ks * 2 * (M * 16), ob = ks * 2 * (NH * 16);       // two K groups per MMA (K = 8)
-                            const uint64_t dah = smem_desc(a_hi + oa, M * 16, 128), dal = smem_desc(a_lo + oa, M * 16, 128);
-                            const uint64_t dbh = smem_desc(b_hi + ob, NH * 16, 128), dbl = smem_desc(b_lo + ob, NH * 16, 128);
+                            const uint32_t oa = ks * 2 * A_LBO, ob = ks * 2 * B_LBO;       // two K groups per MMA (K = 8)
+                            const uint64_t dah = smem_desc(a_hi + oa, A_LBO, SBO), dal = smem_desc(a_lo + oa, A_LBO, SBO);
+                            const uint64_t dbh = smem_desc(b_hi + ob, B_LBO, SBO), dbl = smem_desc(b_lo + ob, B_LBO, SBO);
                             umma_tf32(d, dah, dbh, ch > 0 || ks > 0);
                             umma_tf32(d, dal, dbh, true);
                             umma_tf32(d, dah, dbl, true);
@@ -203,6 +279,7 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
         const int r = m / PC, col = m % PC;
         float *row = s_epi + m * EPI_PITCH;
         const float inv = 1.0f / (float)C;                      // nelems = kernel_size^2 * C (:104); one reciprocal, as in correlation.cu
+        const int r_lo = 2 * warp;                              // the warp's two patch rows: 2 warp, 2 warp + 1
         int u = 0;
         for (int i = 0; i < my_tiles; ++i) {
             int b, y0, x0;
@@ -217,21 +294,24 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
                 const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + ab * ACC_STRIDE;
 #pragma unroll 1
                 for (int nr = 0; nr < NR; ++nr) {
-                    uint32_t v[24];
-                    {
-                        uint32_t a[8], bq[8], c[8];
-                        tmem_ld8(taddr + nr * NC, a);
-                        tmem_ld8(taddr + nr * NC + 8, bq);
-                        tmem_ld8(taddr + nr * NC + 16, c);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { v[j] = a[j]; v[8 + j] = bq[j]; v[16 + j] = c[j]; }
-                    }
-                    // this neighbourhood row is displacement tj = (half * 8 + nr) - r - 4 of the thread's pixel
-                    const int tj = half * NR + nr - r - 4;
-#pragma unroll
-                    for (int j = 0; j < 24; ++j) row[j] = __uint_as_float(v[j]);
+                    // neighbourhood row half * 8 + nr is displacement tj = (half * 8 + nr) - r - 4 of a pixel in patch row r;
+                    // rows no pixel of this warp needs are skipped (warp-uniform)
+                    const int na = half * NR + nr;
+                    if (na < r_lo || na > r_lo + 9) continue;
+                    uint32_t a[8], bq[8], c[8];
+                    tmem_ld8(taddr + nr * NC, a);
+                    tmem_ld8(taddr + nr * NC + 8, bq);
+                    tmem_ld8(taddr + nr * NC + 16, c);
+                    tmem_wait_ld();
+                    float4 *row4 = reinterpret_cast<float4 *>(row);
+                    row4[0] = make_float4(__uint_as_float(a[0]), __uint_as_float(a[1]), __uint_as_float(a[2]), __uint_as_float(a[3]));
+                    row4[1] = make_float4(__uint_as_float(a[4]), __uint_as_float(a[5]), __uint_as_float(a[6]), __uint_as_float(a[7]));
+                    row4[2] = make_float4(__uint_as_float(bq[0]), __uint_as_float(bq[1]), __uint_as_float(bq[2]), __uint_as_float(bq[3]));
+                    row4[3] = make_float4(__uint_as_float(bq[4]), __uint_as_float(bq[5]), __uint_as_float(bq[6]), __uint_as_float(bq[7]));
+                    row4[4] = make_float4(__uint_as_float(c[0]), __uint_as_float(c[1]), __uint_as_float(c[2]), __uint_as_float(c[3]));
+                    row4[5] = make_float4(__uint_as_float(c[4]), __uint_as_float(c[5]), __uint_as_float(c[6]), __uint_as_float(c[7]));
                     __syncwarp();
+                    const int tj = na - r - 4;
                     if (live && tj >= -4 && tj <= 4) {
                         float *ot = o + (size_t)((tj + 4) * 9) * HW;
 #pragma unroll
@@ -264,8 +344,9 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, int B, int C
         return -1;
     }
     const int nblk = (int)std::min<long long>(num_tiles, (long long)sm_count());
+    const int vec4 = (W % 4 == 0 && aligned16(in1) && aligned16(in2)) ? 1 : 0;
     corr_forward_tc_kernel<<<nblk, NTHREADS, SMEM_BYTES, s>>>(in1, in2, out, C, H, W, tiles_x, tiles_y, (int)num_tiles,
-                                                              FastDiv((unsigned)tiles_x), FastDiv((unsigned)(tiles_x * tiles_y)));
+                                                              FastDiv((unsigned)tiles_x), FastDiv((unsigned)(tiles_x * tiles_y)), vec4);
     note_launch();
     return check_launch("correlation forward (tensor cores)");
 }
