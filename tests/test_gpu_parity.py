@@ -462,6 +462,42 @@ def test_correlation_tensor_core_path(lib, oracle, B, C, H, W):
           f"SIMT vs oracle: {U.max_err(host(simt), ref):.2e}")
 
 
+@pytest.mark.parametrize("B,C,H,W", [(2, 32, 40, 64), (8, 196, 18, 31), (1, 5, 9, 13), (2, 64, 33, 50)])
+def test_correlation_tensor_core_pair_launch(lib, oracle, B, C, H, W):
+    """Both directions in one launch of the tensor-core kernel: bit-identical to its two single launches, one launch."""
+    r = U.rng(1795 + C + W)
+    f1, f2 = U.image(r, B, C, H, W, "normal"), U.image(r, B, C, H, W, "normal")
+    mod = lib.Correlation(4, 1, 4, 1, 1, 1)
+    lib.debug_force_correlation_path("tensor")
+    before = lib.launch_count()
+    o12, o21 = mod.both_directions(cu(f1), cu(f2))
+    torch.cuda.synchronize()
+    launches = lib.launch_count() - before
+    a, b = mod(cu(f1), cu(f2)), mod(cu(f2), cu(f1))
+    lib.debug_force_correlation_path(None)
+    assert launches == 1
+    assert torch.equal(o12, a) and torch.equal(o21, b)
+    U.assert_close(host(o12), oracle.correlation_forward(f1, f2, 4, 1, 4, 1, 1), U.RTOL_FWD, "tensor pair: corr(f1, f2)")
+    U.assert_close(host(o21), oracle.correlation_forward(f2, f1, 4, 1, 4, 1, 1), U.RTOL_FWD, "tensor pair: corr(f2, f1)")
+
+
+def test_correlation_automatic_path_choice(lib):
+    """The automatic rule (correlation.cu: use_tensor_path): small deep maps -- PWC levels 6 and 5 -- go to the tensor-core kernel
+    (one launch, no split-K reduction), larger ones to the FFMA kernel; both agree to rounding."""
+    mod = lib.Correlation(4, 1, 4, 1, 1, 1)
+    for (B, C, H, W), tensor in (((8, 196, 18, 31), True), ((8, 128, 36, 62), True), ((8, 96, 72, 124), False), ((2, 32, 40, 64), False)):
+        a, b = torch.randn(B, C, H, W, device="cuda"), torch.randn(B, C, H, W, device="cuda")
+        before = lib.launch_count()
+        auto = mod(a, b)
+        n = lib.launch_count() - before
+        lib.debug_force_correlation_path("tensor" if tensor else "simt")
+        forced = mod(a, b)
+        lib.debug_force_correlation_path(None)
+        assert torch.equal(auto, forced), (B, C, H, W)
+        if tensor:
+            assert n == 1
+
+
 @pytest.mark.parametrize("name", ["corr_pwc", "corr_pwc_c196", "corr_wide_splitk", "corr_wide_tiled"])
 def test_correlation_tensor_core_path_reproduces_reference_fixtures(lib, name):
     """The golden fixtures of the reference's own correlation kernel, through the tensor-core path."""

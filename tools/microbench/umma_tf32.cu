@@ -23,16 +23,24 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n)
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);   // f32 accum, tf32 x tf32, K-major both
 }
 
+// MN = true: operands MN-major (the row index contiguous in groups of four, as NCHW feature maps are): element (row, k) at
+// [(row / 4)][k][row % 4] floats -- 16-byte chunks of four rows, the K values of a chunk 16 B apart (LBO = 128 B between groups
+// of eight K), chunks K * 16 B apart (SBO); with SPLIT the operands are NOT tf32-exact: pass 1 feeds the raw fp32 words (the
+// tensor core reads the top 19 bits), passes 2 / 3 add lo = v - trunc(v) terms (3 x TF32)
+template <bool MN, bool SPLIT, bool SWAP = false>
 __global__ void __launch_bounds__(128) umma_kernel(const float *A, const float *B, float *D, int reps, unsigned long long *cycles)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float *sA = reinterpret_cast<float *>(smem);            // [K/4][M][4]
     float *sB = sA + M * K;                                  // [K/4][N][4]
+    float *sAl = sB + N * K, *sBl = sAl + M * K;             // lo parts (SPLIT)
     __shared__ __align__(8) uint64_t bar;
     __shared__ uint32_t tmem_base;
     const int tid = threadIdx.x, warp = tid >> 5;
-    for (int i = tid; i < M * K; i += 128) { const int m = i / K, k = i % K; sA[((k >> 2) * M + m) * 4 + (k & 3)] = A[m * K + k]; }
-    for (int i = tid; i < N * K; i += 128) { const int n = i / K, k = i % K; sB[((k >> 2) * N + n) * 4 + (k & 3)] = B[n * K + k]; }
+    auto idx = [](int row, int k, int rows) { return MN ? ((row >> 2) * K + k) * 4 + (row & 3) : ((k >> 2) * rows + row) * 4 + (k & 3); };
+    auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+    for (int i = tid; i < M * K; i += 128) { const int m = i / K, k = i % K; sA[idx(m, k, M)] = A[m * K + k]; if (SPLIT) sAl[idx(m, k, M)] = lo_of(A[m * K + k]); }
+    for (int i = tid; i < N * K; i += 128) { const int n = i / K, k = i % K; sB[idx(n, k, N)] = B[n * K + k]; if (SPLIT) sBl[idx(n, k, N)] = lo_of(B[n * K + k]); }
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("fence.mbarrier_init.release.cluster;");
@@ -46,17 +54,23 @@ __global__ void __launch_bounds__(128) umma_kernel(const float *A, const float *
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t tmem = tmem_base;
-    const uint32_t idesc = make_idesc(M, N);
+    const uint32_t idesc = make_idesc(M, N) | (MN ? (1u << 15) | (1u << 16) : 0u);
     long long t0 = clock64();
     if (tid == 0) {
         for (int r = 0; r < reps; ++r)
             for (int ks = 0; ks < K / 8; ++ks) {
-                const uint64_t da = make_desc(smem_u32(sA) + ks * 2 * (M * 16), M * 16, 128);
-                const uint64_t db = make_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
-                const uint32_t acc = (r > 0 || ks > 0) ? 1u : 0u;
-                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                             "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                             ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                // K-major: two K groups of four per MMA, LBO = rows * 16; MN-major: one group of eight K per MMA (128 B), SBO = K * 16
+                const uint32_t offA = MN ? ks * 128 : ks * 2 * (M * 16), offB = MN ? ks * 128 : ks * 2 * (N * 16);
+                uint32_t lboA = MN ? 128 : M * 16, lboB = MN ? 128 : N * 16, sbo = MN ? K * 16 : 128, sboB = sbo;
+                if (SWAP) { lboA = K * 16; lboB = K * 16; sbo = 128; sboB = 128; }
+                auto mma = [&](const float *a, const float *b, uint32_t acc) {
+                    const uint64_t da = make_desc(smem_u32(a) + offA, lboA, sbo), db = make_desc(smem_u32(b) + offB, lboB, sboB);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                };
+                mma(sA, sB, (r > 0 || ks > 0) ? 1u : 0u);
+                if (SPLIT) { mma(sAl, sB, 1u); mma(sA, sBl, 1u); }
             }
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
     }
@@ -90,41 +104,51 @@ __global__ void __launch_bounds__(128) umma_kernel(const float *A, const float *
     if (tid == 0 && cycles) *cycles = (unsigned long long)(t1 - t0);
 }
 
-int main()
+template <bool MN, bool SPLIT, bool SWAP = false>
+static void run(const char *name, bool exact_inputs)
 {
-    std::vector<float> hA(M * K), hB(N * K), hD(M * N), ref(M * N);
+    std::vector<float> hA(M * K), hB(N * K), hD(M * N);
+    std::vector<double> ref(M * N);
     srand(1);
-    for (auto &v : hA) v = (float)(rand() % 17 - 8) / 8.0f;
-    for (auto &v : hB) v = (float)(rand() % 17 - 8) / 8.0f;
+    for (auto &v : hA) v = exact_inputs ? (float)(rand() % 17 - 8) / 8.0f : (float)rand() / RAND_MAX * 2.f - 1.f;
+    for (auto &v : hB) v = exact_inputs ? (float)(rand() % 17 - 8) / 8.0f : (float)rand() / RAND_MAX * 2.f - 1.f;
+    double scale = 0;
     for (int m = 0; m < M; ++m)
         for (int n = 0; n < N; ++n) {
             double s = 0;
             for (int k = 0; k < K; ++k) s += (double)hA[m * K + k] * hB[n * K + k];
-            ref[m * N + n] = (float)s;
+            ref[m * N + n] = s;
+            if (fabs(s) > scale) scale = fabs(s);
         }
     float *dA, *dB, *dD;
     unsigned long long *dc, hc = 0;
     cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dB, hB.size() * 4); cudaMalloc(&dD, hD.size() * 4); cudaMalloc(&dc, 8);
     cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice);
-    const size_t smem = (size_t)(M + N) * K * 4 + 128;
-    cudaFuncSetAttribute(umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    umma_kernel<<<1, 128, smem>>>(dA, dB, dD, 1, dc);
+    const size_t smem = (size_t)2 * (M + N) * K * 4 + 128;
+    cudaFuncSetAttribute(umma_kernel<MN, SPLIT, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma_kernel<MN, SPLIT, SWAP><<<1, 128, smem>>>(dA, dB, dD, 1, dc);
     cudaError_t e = cudaDeviceSynchronize();
-    printf("launch: %s\n", cudaGetErrorString(e));
-    if (e != cudaSuccess) return 1;
+    if (e != cudaSuccess) { printf("%s: launch failed: %s\n", name, cudaGetErrorString(e)); exit(1); }
     cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
     double maxerr = 0;
-    int bad = 0;
-    for (int i = 0; i < M * N; ++i) { const double d = fabs((double)hD[i] - ref[i]); if (d > maxerr) maxerr = d; if (d > 1e-4) ++bad; }
-    printf("D = A * B^T (tf32, M=%d N=%d K=%d): max |err| = %.3g, %d of %d entries off; D[0][0..3] = %g %g %g %g (ref %g %g %g %g)\n", M, N, K,
-           maxerr, bad, M * N, hD[0], hD[1], hD[2], hD[3], ref[0], ref[1], ref[2], ref[3]);
-    // rate: many MMAs back to back on one SM
+    for (int i = 0; i < M * N; ++i) { const double d = fabs((double)hD[i] - ref[i]); if (d > maxerr) maxerr = d; }
     const int reps = 2000;
-    umma_kernel<<<1, 128, smem>>>(dA, dB, dD, reps, dc);
+    umma_kernel<MN, SPLIT, SWAP><<<1, 128, smem>>>(dA, dB, dD, reps, dc);
     e = cudaDeviceSynchronize();
     cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
-    printf("rate: %s, %d x %d MMAs of %dx%dx8 in %llu cycles = %.1f MAC/clk/SM (tf32, cta_group::1)\n", cudaGetErrorString(e), reps, K / 8, M, N, hc,
-           (double)reps * (K / 8) * M * N * 8 / (double)hc);
-    return bad ? 2 : 0;
+    printf("%-44s max |err| / max |ref| = %.3g; %.1f MAC/clk/SM issued (%s)\n", name, maxerr / scale,
+           (double)reps * (K / 8) * (SPLIT ? 3 : 1) * M * N * 8 / (double)hc, cudaGetErrorString(e));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dc);
+}
+
+int main()
+{
+    run<false, false>("K-major, tf32-exact inputs, 1 pass", true);
+    run<true, false>("MN-major, tf32-exact inputs, 1 pass", true);
+    run<true, false, true>("MN-major (LBO <-> SBO swapped), exact, 1 pass", true);
+    run<true, false>("MN-major, fp32 inputs, 1 pass (truncation)", false);
+    run<true, true>("MN-major, fp32 inputs, 3 x TF32 (raw + lo)", false);
+    run<false, true>("K-major, fp32 inputs, 3 x TF32 (raw + lo)", false);
+    return 0;
 }

@@ -31,6 +31,10 @@ with torch.no_grad():
         for path in ("simt", "tensor"):
             V.debug_force_correlation_path(path)
             res[path] = timeit(lambda: corr(a, b))
+        pair = {}
+        for path in ("simt", "tensor"):
+            V.debug_force_correlation_path(path)
+            pair[path] = timeit(lambda: corr.both_directions(a, b))
         V.debug_force_correlation_path("tensor")
         t = corr(a, b)
         V.debug_force_correlation_path("simt")
@@ -38,5 +42,6 @@ with torch.no_grad():
         err = ((t - sref).abs().max() / sref.abs().max()).item()
         gf = 2 * 81 * C * B * (H // s) * (W // s) / 1e9
         print(f"C={C:3d} {H // s}x{W // s}: SIMT {res['simt']:7.1f} us ({gf / res['simt'] * 1e3:6.1f} TFLOP/s useful), tensor {res['tensor']:7.1f} us "
-              f"({gf / res['tensor'] * 1e3:6.1f} TFLOP/s useful); max |tensor - SIMT| / max = {err:.2e}")
+              f"({gf / res['tensor'] * 1e3:6.1f} TFLOP/s useful); " f"max |tensor - SIMT| / max = {err:.2e}; both directions in one launch: SIMT {pair['simt']:.1f} us, "
+              f"tensor {pair['tensor']:.1f} us")
 V.debug_force_correlation_path(None)

@@ -25,7 +25,7 @@
 
 namespace vfidkr {
 
-int corr_forward_tc(const float *in1, const float *in2, float *out, int B, int C, int H, int W, cudaStream_t s);   // correlation_tc.cu; -1 = not applicable
+int corr_forward_tc(const float *in1, const float *in2, float *out, float *out_b, int B, int C, int H, int W, cudaStream_t s);   // correlation_tc.cu; -1 = not applicable
 
 namespace {
 
@@ -760,6 +760,18 @@ static int corr_forward_fast(const float *input1, const float *input2, float *ou
     return check_launch("correlation forward");
 }
 
+// Which kernel serves a (pad = md = 4, k = 1) forward.  Measured on B200 (profiles/r02/time_corr_tensor_v3.log, B = 8):
+// the tcgen05 kernel wins where the maps are small and deep -- PWC levels 6 and 5, 196 x 18 x 31 and 128 x 36 x 62:
+// 34.8 vs 48.4 us and 37.0 vs 55.1 us, the FFMA kernel needing split-K plus a reduction there -- and loses from level 4
+// on (46 vs 40, 123 vs 95, 284 vs 198 us), where its operand staging (global -> registers -> hi / lo split ->
+// shared memory) and not the tensor pipe sets the pace.  path 1 / 2 (vfidkr_debug_force_correlation_path) force one.
+static bool use_tensor_path(int B, int C, int H, int W)
+{
+    const int path = g_corr_path.load(std::memory_order_relaxed);
+    if (path) return path == 2;
+    return C >= 96 && (long long)B * H * W <= 40000;
+}
+
 VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *input2, float *output,
                                           int B, int C, int H, int W, int pad, int k, int md, int s1, int s2,
                                           int corr_type_multiply, vfidkr_stream_t stream)
@@ -770,8 +782,8 @@ VFIDKR_API int vfidkr_correlation_forward(const float *input1, const float *inpu
     const CorrShape cs = corr_shape(H, W, pad, k, md, s1, s2);
     if (cs.oh <= 0 || cs.ow <= 0) return VFIDKR_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
-    if (k == 1 && s1 == 1 && s2 == 1 && md == 4 && pad == 4 && g_corr_path.load(std::memory_order_relaxed) == 2) {
-        const int e = corr_forward_tc(input1, input2, output, B, C, H, W, s);
+    if (k == 1 && s1 == 1 && s2 == 1 && md == 4 && pad == 4 && use_tensor_path(B, C, H, W)) {
+        const int e = corr_forward_tc(input1, input2, output, nullptr, B, C, H, W, s);
         if (e >= 0) return e;
     }
     if (k == 1 && s1 == 1 && s2 == 1 && md == 4) return corr_forward_fast(input1, input2, output, nullptr, B, C, H, W, pad, md, cs, s);
@@ -801,6 +813,10 @@ VFIDKR_API int vfidkr_correlation_forward_pair(const float *input1, const float 
     const CorrShape cs = corr_shape(H, W, pad, k, md, s1, s2);
     if (cs.oh <= 0 || cs.ow <= 0) return VFIDKR_ERR_ARG;
     cudaStream_t s = (cudaStream_t)stream;
+    if (k == 1 && s1 == 1 && s2 == 1 && md == 4 && pad == 4 && use_tensor_path(2 * B, C, H, W)) {
+        const int e = corr_forward_tc(input1, input2, output12, output21, B, C, H, W, s);
+        if (e >= 0) return e;
+    }
     if (k == 1 && s1 == 1 && s2 == 1 && md == 4) return corr_forward_fast(input1, input2, output12, output21, B, C, H, W, pad, md, cs, s);
     dim3 block(32, 8), grid(ceil_div(cs.ow, 32), ceil_div(cs.oh, 8), B);
     corr_forward_generic_kernel<<<grid, block, 0, s>>>(input1, input2, output12, C, H, W, pad, k, md, s1, s2, cs);

@@ -4,7 +4,7 @@
 // What is computed follows PWCNet/correlation_package_pytorch1_0/correlation_cuda_kernel.cu:74-147:
 //   out[b, (tj+4)*9 + (ti+4), y, x] = 1/C * sum_c f1[b,c,y,x] * f2[b,c,y+tj,x+ti],  zero outside the plane.
 // As a GEMM: for a PATCH of 8 x 16 output pixels (M = 128 rows) and its 16 x 24 pixel neighbourhood in f2 (N = 384 columns,
-// issued as two halves of 8 x 24 = 192), D[m][n] = sum_c f1[c, pixel m] * f2[c, position n]; the 81 displacements of a
+// issued as two interleaved halves -- even / odd rows -- of 8 x 24 = 192), D[m][n] = sum_c f1[c, pixel m] * f2[c, position n]; the 81 displacements of a
 // pixel are 81 of its row's 384 entries (21 % of the MMA work is useful -- the band structure of the op; a row-tile
 // formulation would use 9 of 136).  fp32 parity at 1e-5 needs more than TF32's 10 mantissa bits: each operand is split
 // into hi = tf32(v) and lo = tf32(v - hi) and the product is hi*hi + lo*hi + hi*lo (three MMAs, fp32 accumulation in TMEM).
@@ -14,10 +14,10 @@
 // One persistent CTA per SM, warp-specialised:
 //   warps 0-3  epilogue: TMEM -> registers (tcgen05.ld, a warp owns the 32 TMEM lanes = pixels of its quarter), the
 //              lane-dependent band extraction goes through a private shared-memory row, scaled stores to the 81 planes;
-//   warps 4-11 stagers: f1 patch / f2 neighbourhood chunk of 32 channels from global memory (L2), hi / lo split, written
+//   warps 4-19 stagers: f1 patch / f2 neighbourhood chunk of 32 channels from global memory (L2), hi / lo split, written
 //              to shared memory in the canonical K-major no-swizzle core-matrix layout ([K/4][rows/8][8][4] floats, 8-row
 //              groups 144 B apart) -- the split needs a register pass anyway, so no TMA / swizzle;
-//   warp 12    one thread issues the MMAs (12 per stage: 4 K-steps x 3 passes), commits stage-free and accumulator-full.
+//   warp 20    one thread issues the MMAs (12 per stage: 4 K-steps x 3 passes), commits stage-free and accumulator-full.
 // A unit of work is (patch, neighbourhood half); the two 192-column accumulators ping-pong in TMEM (512 columns), so the
 // epilogue of one unit overlaps the MMAs of the next; operand stages form a 2-deep ring (90 KB each).
 #include "common.cuh"
@@ -39,7 +39,7 @@ constexpr int A_LBO = (M / 8) * SBO, B_LBO = (NH / 8) * SBO;
 constexpr int A_FLOATS = KG * A_LBO / 4, B_FLOATS = KG * B_LBO / 4;
 constexpr int STAGE_FLOATS = 2 * (A_FLOATS + B_FLOATS);     // hi + lo of both operands
 __host__ __device__ constexpr int row_off(int m) { return (m >> 3) * SBO_F + (m & 7) * 4; }   // float offset of row m inside a K group
-constexpr int EPI_WARPS = 4, STAGE_WARPS = 8, NTHREADS = (EPI_WARPS + STAGE_WARPS + 1) * 32;
+constexpr int EPI_WARPS = 4, STAGE_WARPS = 16, NTHREADS = (EPI_WARPS + STAGE_WARPS + 1) * 32;
 constexpr int EPI_PITCH = 28;                               // 16-byte aligned rows, conflict-free 128-bit stores
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_FLOATS * sizeof(float) + (size_t)M * EPI_PITCH * sizeof(float) + 256;
 constexpr uint32_t TMEM_COLS = 512, ACC_STRIDE = 256;       // accumulator b lives at columns [256 b, 256 b + 192)
@@ -74,17 +74,10 @@ __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.
 // fp32 rate and there are two per operand element), lo = v - hi (exact in fp32; the tensor core reads its top 19 bits).
 // |v - hi - tf32(lo)| <= 2^-21 |v|: the dropped lo*lo term and this residual are ~1e-6 of a product, inside the 1e-5 parity bound.
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-__device__ __forceinline__ bool try_wait_hint(uint64_t *bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(2000u) : "memory");
-    return ok != 0;
-}
 __device__ __forceinline__ void wait_phase(uint64_t *bar, uint32_t parity)
 {
-    for (uint32_t spins = 0; !try_wait_hint(bar, parity); ++spins)     // suspended in hardware between probes: a waiting warp costs no issue slots
-        if (spins > (1u << 24)) __trap();      // a protocol error traps instead of hanging the GPU
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)     // try_wait suspends the thread for a hardware time slice per probe
+        if (spins > (1u << 26)) __trap();      // a protocol error traps instead of hanging the GPU
 }
 // a whole warp waits: one lane polls, the warp re-converges behind it
 __device__ __forceinline__ void warp_wait_phase(uint64_t *bar, uint32_t parity, int lane)
@@ -96,7 +89,7 @@ __device__ __forceinline__ void warp_wait_phase(uint64_t *bar, uint32_t parity, 
 
 __global__ void __launch_bounds__(ctc::NTHREADS, 1)
 corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
-                       int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, const FastDiv div_tx, const FastDiv div_tile_img,
+                       float *__restrict__ out_b, int bsplit, int C, int H, int W, int tiles_x, int tiles_y, int num_tiles, const FastDiv div_tx, const FastDiv div_tile_img,
                        int vec4)
 {
     using namespace ctc;
@@ -113,8 +106,9 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
     const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
     if (tid == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], STAGE_WARPS * 32); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS * 32); }
+        // one arrival per WARP (its lane 0, behind a __syncwarp): 256 arrivals on one shared-memory word serialise
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], STAGE_WARPS); mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], EPI_WARPS); }
         fence_mbar_init();
     }
     if (warp == EPI_WARPS + STAGE_WARPS) {       // the MMA warp owns the tensor-memory allocation
@@ -136,50 +130,56 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
 
     if (warp >= EPI_WARPS && warp < EPI_WARPS + STAGE_WARPS) {
         // ================================ stagers ================================
-        const int st = tid - EPI_WARPS * 32;                         // 0 .. 255
+        const int st = tid - EPI_WARPS * 32;                         // 0 .. 511
         int it = 0;
         if (vec4) {
             // Rows are whole float4s (W % 4 == 0, aligned bases): a task is (K group g of four channels, four adjacent
             // pixels) = four 128-bit loads, one per channel plane, transposed in registers into four 16-byte rows
-            // [pixel][4 channels] of the operand layout.  Patch: 8 x 32 tasks (one per thread); neighbourhood half:
-            // 8 x 48 tasks (one per thread + one more for threads 0 .. 127).  Loop-invariant geometry first.
-            const int ga = st >> 5, pra = (st & 31) >> 2, pca = (st & 3) * 4;                       // A task
-            const int offa = ga * (A_LBO / 4) + row_off(pra * PC + pca);
-            int gb[2], nrb[2], ncb[2], offb[2];
+            // [pixel][4 channels] of the operand layout.  Patch: 8 x 32 tasks; neighbourhood half: 8 x 48 tasks.
+            // 640 tasks per stage over 512 threads: thread st takes task st (patch tasks 0 .. 255, neighbourhood tasks 256 .. 639)
+            // and threads 0 .. 127 also task 512 + st.  Loop-invariant geometry first.
+            bool isA[2], has[2];
+            int gq[2], rq[2], cq[2], offq[2];
 #pragma unroll
             for (int k = 0; k < 2; ++k) {
-                const int q = st + 256 * k;                                                        // B task (k = 1: q < 384 only)
-                gb[k] = q / 48; nrb[k] = (q % 48) / 6; ncb[k] = (q % 6) * 4;
-                offb[k] = gb[k] * (B_LBO / 4) + row_off(nrb[k] * NC + ncb[k]);
+                const int q = st + 512 * k;
+                has[k] = q < 640;
+                isA[k] = q < 256;
+                const int qb = q - 256;
+                gq[k] = isA[k] ? q >> 5 : qb / 48;
+                rq[k] = isA[k] ? (q & 31) >> 2 : (qb % 48) / 6;          // patch row / neighbourhood row of this half
+                cq[k] = isA[k] ? (q & 3) * 4 : (qb % 6) * 4;             // first of the four columns
+                offq[k] = isA[k] ? gq[k] * (A_LBO / 4) + row_off(rq[k] * PC + cq[k]) : gq[k] * (B_LBO / 4) + row_off(rq[k] * NC + cq[k]);
             }
-            const bool second = st < 128;
             for (int i = 0; i < my_tiles; ++i) {
                 int b, y0, x0;
                 decode(i, b, y0, x0);
-                const float *f1 = in1 + (size_t)b * C * HW, *f2 = in2 + (size_t)b * C * HW;
+                // items b >= bsplit are the second problem of a pair launch: the same maps with their roles exchanged
+                const bool second = b >= bsplit;
+                const size_t boff = (size_t)(second ? b - bsplit : b) * C * HW;
+                const float *f1 = (second ? in2 : in1) + boff, *f2 = (second ? in1 : in2) + boff;
                 for (int half = 0; half < 2; ++half)
                     for (int ch = 0; ch < nchunks; ++ch, ++it) {
                         const int s = it % STAGES;
                         if (it >= STAGES) warp_wait_phase(&empty[s], (uint32_t)(((it / STAGES) - 1) & 1), lane);   // the MMAs that read this stage are done
                         float *sa_hi = s_stage + s * STAGE_FLOATS, *sa_lo = sa_hi + A_FLOATS, *sb_hi = sa_lo + A_FLOATS, *sb_lo = sb_hi + B_FLOATS;
-                        float4 v[3][4];
+                        float4 v[2][4];
                         const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                        {   // every load of the stage before the first store
-                            const int y = y0 + pra, x = x0 + pca, c0 = ch * KC + 4 * ga;
-                            const bool in = y < H && x < W;
-                            const float *src = f1 + (size_t)c0 * HW + (in ? (size_t)y * W + x : 0);
 #pragma unroll
-                            for (int c = 0; c < 4; ++c) v[0][c] = (in && c0 + c < C) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * HW)) : z4;
+                        for (int k = 0; k < 2; ++k) {      // every load of the stage before the first store
+                            const int y = isA[k] ? y0 + rq[k] : y0 - 4 + 2 * rq[k] + half;
+                            const int x = isA[k] ? x0 + cq[k] : x0 - 4 + cq[k];
+                            const int c0 = ch * KC + 4 * gq[k];
+                            const bool in = has[k] && y >= 0 && y < H && x >= 0 && x < W;
+                            const float *src = (isA[k] ? f1 : f2) + (size_t)c0 * HW + (in ? (size_t)y * W + x : 0);
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) v[k][c] = (in && c0 + c < C) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * HW)) : z4;
                         }
 #pragma unroll
                         for (int k = 0; k < 2; ++k) {
-                            const int y = y0 - 4 + half * NR + nrb[k], x = x0 - 4 + ncb[k], c0 = ch * KC + 4 * gb[k];
-                            const bool in = (k == 0 || second) && y >= 0 && y < H && x >= 0 && x < W;
-                            const float *src = f2 + (size_t)c0 * HW + (in ? (size_t)y * W + x : 0);
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) v[1 + k][c] = (in && c0 + c < C) ? __ldg(reinterpret_cast<const float4 *>(src + (size_t)c * HW)) : z4;
-                        }
-                        auto put = [&](float *hi_base, float *lo_base, const float4 (&t)[4]) {
+                            if (!has[k]) continue;
+                            float *hi_base = (isA[k] ? sa_hi : sb_hi) + offq[k], *lo_base = (isA[k] ? sa_lo : sb_lo) + offq[k];
+                            const float4 (&t)[4] = v[k];
                             const float px[4][4] = {{t[0].x, t[1].x, t[2].x, t[3].x}, {t[0].y, t[1].y, t[2].y, t[3].y},
                                                     {t[0].z, t[1].z, t[2].z, t[3].z}, {t[0].w, t[1].w, t[2].w, t[3].w}};   // [pixel][channel]
 #pragma unroll
@@ -190,22 +190,23 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
                                 *reinterpret_cast<float4 *>(hi_base + 4 * j) = hi;      // rows m .. m + 3 of one 8-row group: 16 bytes apart
                                 *reinterpret_cast<float4 *>(lo_base + 4 * j) = lo;
                             }
-                        };
-                        put(sa_hi + offa, sa_lo + offa, v[0]);
-                        put(sb_hi + offb[0], sb_lo + offb[0], v[1]);
-                        if (second) put(sb_hi + offb[1], sb_lo + offb[1], v[2]);
+                        }
                         fence_proxy_async();             // this thread's operand stores -> visible to the tensor core (async proxy)
-                        mbar_arrive(&full[s]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
                     }
             }
         } else {
             // any width / alignment: a task is (K group, one pixel), four scalar loads
-            constexpr int A_TASKS = KG * M, TASKS = KG * (M + NH), PER = TASKS / (STAGE_WARPS * 32);   // 2560 tasks, 10 per thread
+            constexpr int A_TASKS = KG * M, TASKS = KG * (M + NH), PER = TASKS / (STAGE_WARPS * 32);   // 2560 tasks, 5 per thread
             static_assert(TASKS % (STAGE_WARPS * 32) == 0, "tasks per stager thread");
             for (int i = 0; i < my_tiles; ++i) {
                 int b, y0, x0;
                 decode(i, b, y0, x0);
-                const float *f1 = in1 + (size_t)b * C * HW, *f2 = in2 + (size_t)b * C * HW;
+                // items b >= bsplit are the second problem of a pair launch: the same maps with their roles exchanged
+                const bool second = b >= bsplit;
+                const size_t boff = (size_t)(second ? b - bsplit : b) * C * HW;
+                const float *f1 = (second ? in2 : in1) + boff, *f2 = (second ? in1 : in2) + boff;
                 for (int half = 0; half < 2; ++half)
                     for (int ch = 0; ch < nchunks; ++ch, ++it) {
                         const int s = it % STAGES;
@@ -218,7 +219,7 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
                             const bool isA = k < A_TASKS / (STAGE_WARPS * 32);      // compile-time per k: tasks 0 .. 1023 are the patch
                             const int qq = isA ? q : q - A_TASKS;
                             const int g = isA ? qq / M : qq / NH, m = isA ? qq % M : qq % NH;
-                            const int y = isA ? y0 + m / PC : y0 - 4 + half * NR + m / NC;
+                            const int y = isA ? y0 + m / PC : y0 - 4 + 2 * (m / NC) + half;
                             const int x = isA ? x0 + m % PC : x0 - 4 + m % NC;
                             const bool in = y >= 0 && y < H && x >= 0 && x < W;
                             const float *src = (isA ? f1 : f2) + (size_t)(ch * KC + 4 * g) * HW + (in ? (size_t)y * W + x : 0);
@@ -239,7 +240,8 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
                             *reinterpret_cast<float4 *>((isA ? sa_lo : sb_lo) + off) = lo;
                         }
                         fence_proxy_async();
-                        mbar_arrive(&full[s]);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&full[s]);
                     }
             }
         }
@@ -286,7 +288,7 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
             decode(i, b, y0, x0);
             const int y = y0 + r, x = x0 + col;
             const bool live = y < H && x < W;
-            float *o = out + (size_t)b * 81 * HW + (size_t)y * W + x;
+            float *o = (b >= bsplit ? out_b + (size_t)(b - bsplit) * 81 * HW : out + (size_t)b * 81 * HW) + (size_t)y * W + x;
             for (int half = 0; half < 2; ++half, ++u) {
                 const int ab = u & 1;
                 warp_wait_phase(&acc_full[ab], (uint32_t)((u >> 1) & 1), lane);
@@ -294,9 +296,11 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
                 const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + ab * ACC_STRIDE;
 #pragma unroll 1
                 for (int nr = 0; nr < NR; ++nr) {
-                    // neighbourhood row half * 8 + nr is displacement tj = (half * 8 + nr) - r - 4 of a pixel in patch row r;
-                    // rows no pixel of this warp needs are skipped (warp-uniform)
-                    const int na = half * NR + nr;
+                    // row nr of this half is neighbourhood row na = 2 nr + half (the halves INTERLEAVE the 16 rows, so that every
+                    // warp needs five rows of each -- with the rows split 0-7 / 8-15 the warps needed 8, 6, 4, 2 of one half and
+                    // the unit took as long as the busiest warp); it is displacement tj = na - r - 4 of a pixel in patch row r.
+                    // Rows no pixel of this warp needs are skipped (warp-uniform).
+                    const int na = 2 * nr + half;
                     if (na < r_lo || na > r_lo + 9) continue;
                     uint32_t a[8], bq[8], c[8];
                     tmem_ld8(taddr + nr * NC, a);
@@ -320,7 +324,8 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
                     __syncwarp();
                 }
                 tc_fence_before();
-                mbar_arrive(&acc_empty[ab]);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&acc_empty[ab]);
             }
         }
     }
@@ -333,11 +338,12 @@ corr_forward_tc_kernel(const float *__restrict__ in1, const float *__restrict__ 
 }  // namespace
 
 // Returns VFIDKR_OK / VFIDKR_ERR_CUDA when the kernel was launched, -1 when it does not apply.
-int corr_forward_tc(const float *in1, const float *in2, float *out, int B, int C, int H, int W, cudaStream_t s)
+// out_b != nullptr: a pair launch, out_b = correlation(in2, in1) next to out = correlation(in1, in2).
+int corr_forward_tc(const float *in1, const float *in2, float *out, float *out_b, int B, int C, int H, int W, cudaStream_t s)
 {
     using namespace ctc;
     const int tiles_x = ceil_div(W, PC), tiles_y = ceil_div(H, PR);
-    const long long num_tiles = (long long)tiles_x * tiles_y * B;
+    const long long num_tiles = (long long)tiles_x * tiles_y * B * (out_b ? 2 : 1);
     if (num_tiles >= (1ll << 30) || (long long)C * H * W >= (1ll << 31)) return -1;
     if (cudaFuncSetAttribute(corr_forward_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
         (void)cudaGetLastError();
@@ -345,7 +351,7 @@ int corr_forward_tc(const float *in1, const float *in2, float *out, int B, int C
     }
     const int nblk = (int)std::min<long long>(num_tiles, (long long)sm_count());
     const int vec4 = (W % 4 == 0 && aligned16(in1) && aligned16(in2)) ? 1 : 0;
-    corr_forward_tc_kernel<<<nblk, NTHREADS, SMEM_BYTES, s>>>(in1, in2, out, C, H, W, tiles_x, tiles_y, (int)num_tiles,
+    corr_forward_tc_kernel<<<nblk, NTHREADS, SMEM_BYTES, s>>>(in1, in2, out, out_b, out_b ? B : 2 * B, C, H, W, tiles_x, tiles_y, (int)num_tiles,
                                                               FastDiv((unsigned)tiles_x), FastDiv((unsigned)(tiles_x * tiles_y)), vec4);
     note_launch();
     return check_launch("correlation forward (tensor cores)");
