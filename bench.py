@@ -376,7 +376,7 @@ def bench_ours(args):
 
         # ---- the dominant kernel on SURVEY 8d's stated flow distributions (outside the timed step; rank 0) ----
         other_flows = {}
-        if rank == 0:
+        if rank == 0 and not args.timed_only:
             g = torch.Generator(device=device)
             g.manual_seed(77)
             B, H, W = PAIRS_PER_GPU, PAD_H, PAD_W
@@ -969,7 +969,11 @@ def main():
                     help="1080p_b8: the headline line (BASELINE config 4); 4k_stream: config 5, pair-sharded with an NCCL gather")
     ap.add_argument("--pairs", type=int, default=16, help="4k_stream: pairs in the stream (same for every N: strong scaling)")
     ap.add_argument("--no-check", action="store_true", help="skip the pre-timing comparison against the reference's kernels")
+    ap.add_argument("--timed-only", action="store_true",
+                    help="warm-up + timed steps only (no check, flow variants, end-to-end or CPU legs): the command the ncu launch list is taken of")
     args = ap.parse_args()
+    if args.timed_only:
+        args.no_check = args.no_e2e = args.no_cpu_baseline = True
     # stdout carries exactly ONE line, the JSON result: everything else a library may print there (NCCL's version banner
     # under NCCL_DEBUG=VERSION, for instance) is sent to stderr, and the result goes to a private copy of the real stdout
     global _RESULT_FD
