@@ -910,6 +910,20 @@ def op_table(torch, V, device, path):
                                                               ptr(gx), ptr(o1), ptr(o2), ptr(o3), ptr(o4), Bx, 3, Hx, Wx, 4, sp), iters=20), 436, pxx)
         del Ix, flx, ftx, offx, depx, gx, o1, o2, o3, o4
         torch.cuda.empty_cache()
+    # BASELINE config 1 (one 256x448 frame pair, the reference's CPU-runnable case): a latency, not a bandwidth -- the op is a
+    # single wave of 18 us of work, so the row reports microseconds through the C ABI and through the autograd Function
+    gen.manual_seed(79)
+    I1 = torch.rand(1, 3, 256, 448, device=device)
+    fl1 = scene_flow(torch, gen, device, 1, 256, 448)
+    ft1 = torch.softmax(torch.randn(1, 16, 256, 448, device=device), 1)
+    o1 = torch.empty_like(I1)
+    add("FI_ori_fwd_C3_cfg1_B1_256x448_c_abi", timeit(lambda: _lib.call("vfidkr_filterinterpolation_forward_ori", ptr(I1), ptr(fl1), ptr(ft1),
+                                                                         ptr(o1), 1, 3, 256, 448, 4, sp), iters=200), 96, 256 * 448)
+    rows[-1]["latency_us"] = rows[-1]["ms"] * 1e3
+    with torch.no_grad():
+        add("FI_ori_fwd_C3_cfg1_B1_256x448_python", timeit(lambda: V.FilterInterpolationLayer.apply(I1, fl1, ft1), iters=200), 96, 256 * 448)
+    rows[-1]["latency_us"] = rows[-1]["ms"] * 1e3
+    del I1, fl1, ft1, o1
     # SeparableConv at F = 51 (the reference's own test size, test_module.py:903-907) is arithmetic-bound:
     # the row carries the fp32 rate next to the (irrelevant) byte rate.  3*C*F*F multiply-adds per output pixel forward,
     # three times that backward.
