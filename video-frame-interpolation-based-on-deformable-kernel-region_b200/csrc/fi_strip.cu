@@ -77,7 +77,7 @@ __device__ __forceinline__ float window_from_smem(const float *__restrict__ ring
     return qTL * Q[0] + qTR * Q[1] + qBL * Q[2] + qBR * Q[3];
 }
 
-template <int CG>
+template <int CG, bool BLEND>
 __global__ void __launch_bounds__(NTHREADS, 1)
 fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const __grid_constant__ CUtensorMap map_img,
                             const float *__restrict__ in1, const float *__restrict__ in2, float *__restrict__ out,
@@ -85,7 +85,9 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                             const FastDiv div_tiles_x, const FastDiv div_nseg, int *__restrict__ work_counter,
                             float scale, int accumulate, size_t out_bs)
 {
-    // epilogue (warp both directions and blend): output = scale * result (+ what output held)
+    // BLEND: the epilogue of SURVEY.md 8f rank 1 (warp both directions and blend): output = scale * result (+ what output
+    // held), batch items out_bs elements apart.  The plain instantiation carries none of it: predicated off, those ~35
+    // instructions per tile still took issue slots of warps whose own instruction stream is the critical path.
     constexpr int SF = stages<CG>();
     constexpr int ROWF = row_floats<CG>();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -294,10 +296,12 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             c.h_i = ty0 * TH + tyy;   // rows past the frame (ragged last segment) are >= H by construction
             c.pix = (unsigned)(c.h_i * W + c.w_i);
         };
-        auto advance = [&](Cursor &c) {
-            if (c.left == 0) return;
-            if (--c.left == 0) { ++c.item_no; start_item(c); }
-            else { c.h_i += TH; c.pix += tile_step; }
+        // returns true when the cursor entered a new item (its running pointers have to be re-derived)
+        auto advance = [&](Cursor &c) -> bool {
+            if (c.left == 0) return false;
+            if (--c.left == 0) { ++c.item_no; start_item(c); return true; }
+            c.h_i += TH; c.pix += tile_step;
+            return false;
         };
         auto has_pixel = [&](const Cursor &c) { return c.w_i < W && c.h_i < H; };
 
@@ -307,11 +311,17 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         Cursor cur{0, 0, 0, 0, 0, 0};
         start_item(cur);
         Cursor fold = cur, req = cur;
+        // (Running 64-bit pointers stepped per tile instead of these per-tile products were measured: 25 fewer instructions
+        // per tile, 20-28 bytes of spills at the 96-register cap, -1 % on smooth and +3 % on rough flows.  Not kept.)
+        const size_t out_item = BLEND ? out_bs : (size_t)CG * HW;
+        auto flow_ptr = [&](const Cursor &c) { return in2 + ((size_t)c.b * 2 * HW + c.pix); };
+        auto out_ptr = [&](const Cursor &c) { return out + ((size_t)c.b * out_item + c.pix); };
+        auto advance_req = [&]() { advance(req); };
 
         auto request_flow = [&](const Cursor &c, float &fx, float &fy) {
             fx = 0.0f; fy = 0.0f;
             if (has_pixel(c)) {
-                const float *f = in2 + ((size_t)c.b * 2 * HW + c.pix);
+                const float *f = flow_ptr(c);
                 fx = ld_stream(f);
                 fy = ld_stream(f + HW);
             }
@@ -351,10 +361,10 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 #pragma unroll
         for (int k = 0; k < LEAD; ++k) {
             request_flow(req, qx[k], qy[k]);
-            advance(req);
+            advance_req();
         }
         request_flow(req, nx, ny);
-        advance(req);
+        advance_req();
 #pragma unroll
         for (int k = 0; k < LEAD; ++k) {
             fold_box(fold, k, qx[k], qy[k]);
@@ -368,7 +378,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             fold_box(fold, j + LEAD, qx[LEAD], qy[LEAD]);
             advance(fold);
             request_flow(req, nx, ny);
-            advance(req);
+            advance_req();
 
             const int sf = j % SF, sb = j % NB;
             const float *ft = s_filt + sf * FILT_FLOATS + tid;
@@ -376,8 +386,8 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             float prev[CG];
 #pragma unroll
             for (int c = 0; c < CG; ++c) prev[c] = 0.0f;
-            if (accumulate && has_pixel(cur)) {
-                const float *op = out + (size_t)cur.b * out_bs + cur.pix;   // out_bs: elements between batch items of the output
+            if (BLEND && accumulate && has_pixel(cur)) {
+                const float *op = out_ptr(cur);
 #pragma unroll
                 for (int c = 0; c < CG; ++c) prev[c] = __ldcs(op + (size_t)c * HW);
             }
@@ -402,12 +412,12 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
             if (lane == 0) mbar_arrive_a(a_filt_free + sf * 8);   // release: this warp's reads of stage sf are complete
 
             if (has_pixel(cur)) {
-                float *o = out + (size_t)cur.b * out_bs + cur.pix;
+                float *o = out_ptr(cur);
                 const float x2 = qx[0], y2 = qy[0];
                 if (x2 < 0.0f) {   // out of range: :2814-2819 copies input1
                     const float *img = in1 + (size_t)cur.b * CG * HW + cur.pix;
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, scale * __ldg(img + (size_t)c * HW) + prev[c]);
+                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, BLEND ? scale * __ldg(img + (size_t)c * HW) + prev[c] : __ldg(img + (size_t)c * HW));
                 } else {
                     const int ix = (int)x2, iy = (int)y2;
                     const int L = ix - 1, T = iy - 1;                       // window origin for F = 4 (:2745-2748)
@@ -459,7 +469,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                         }
                     }
 #pragma unroll
-                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, scale * res[c] + prev[c]);
+                    for (int c = 0; c < CG; ++c) st_stream(o + (size_t)c * HW, BLEND ? scale * res[c] + prev[c] : res[c]);
                 }
             }
             __syncwarp();
@@ -472,7 +482,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
     }
 }
 
-template <int CG>
+template <int CG, bool BLEND>
 static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, float *out, int B, int H, int W,
                   float scale, int accumulate, size_t out_bs, cudaStream_t s)
 {
@@ -484,7 +494,7 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
     const int sms = sm_count();
     const int nseg = choose_segments(B, tiles_x, tiles_y, sms), segt = (tiles_y + nseg - 1) / nseg;
     const long long items = (long long)B * tiles_x * nseg;
-    auto kernel = fi_forward_ori_strip_kernel<CG>;
+    auto kernel = fi_forward_ori_strip_kernel<CG, BLEND>;
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<CG>()) != cudaSuccess) {
         (void)cudaGetLastError();   // smaller shared-memory carve-out (MIG, ...): let the caller run the generic kernels
         return -1;
@@ -527,11 +537,20 @@ int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, f
     if (!aligned16(in1) || !aligned16(in3)) return -1;
     CUtensorMap mfilt;
     if (!encode_tensor_map_3d(&mfilt, in3, W, H, (uint64_t)B * 16, TW, TH, 16)) return -1;
+    const bool blend = scale != 1.0f || accumulate != 0 || out_bs != (size_t)C * H * W;
+    if (blend) {
+        switch (C) {
+        case 1: return launch<1, true>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+        case 2: return launch<2, true>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+        case 3: return launch<3, true>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+        default: return launch<4, true>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+        }
+    }
     switch (C) {
-    case 1: return launch<1>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
-    case 2: return launch<2>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
-    case 3: return launch<3>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
-    default: return launch<4>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+    case 1: return launch<1, false>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+    case 2: return launch<2, false>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+    case 3: return launch<3, false>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
+    default: return launch<4, false>(mfilt, in1, in2, out, B, H, W, scale, accumulate, out_bs, s);
     }
 }
 
