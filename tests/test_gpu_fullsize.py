@@ -84,6 +84,31 @@ def test_fullsize_ori_forward_both_items_and_rough_flow(lib, oracle):
                    "ori forward 1080p, up4 flow")
 
 
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("C,Wc", [(4, W), (3, 1920), (2, 1152), (4, 448), (3, 176)])
+def test_fullsize_ori_forward_other_channel_counts_and_widths(lib, oracle, C, Wc):
+    """The strip kernel's other instantiations on many tiles per CTA: 4 channels run with fewer filter stages than the
+    look-ahead distance (2 with 144-column tiles, 3 with 128) -- the configuration in which the producer's "tile done" ring
+    aliased tiles t-4 and t-1 and the pipeline dead-locked at this size (round 2; small shapes never showed it) -- and
+    other widths: ragged last strips (1920, 448) and one below the 144-column kernel's window (176: 128-column kernel)."""
+    import bench
+    Bc = 4
+    g = gen(4300 + C + Wc)
+    I = torch.rand((Bc, C, H, Wc), generator=g, device="cuda")
+    fl = bench.scene_flow(torch, g, torch.device("cuda"), Bc, H, Wc)
+    ft = torch.softmax(torch.randn((Bc, 16, H, Wc), generator=g, device="cuda"), dim=1)
+    with torch.no_grad():
+        lib.debug_force_forward_path("strip")
+        out = lib.FilterInterpolationLayer.apply(I, fl, ft)
+        lib.debug_force_forward_path("direct")
+        direct = lib.FilterInterpolationLayer.apply(I, fl, ft)
+        lib.debug_force_forward_path(None)
+    torch.cuda.synchronize()
+    assert U.max_err(host(out), host(direct).astype(np.float64)) < 2e-6
+    i = Bc - 1
+    U.assert_close(sl(out, i), oracle.fi_forward("ori", sl(I, i), sl(fl, i), sl(ft, i)), U.RTOL_FWD, f"ori forward C={C} W={Wc}")
+
+
 @pytest.mark.parametrize("variant", ["ori", "dkr", "deforconv"])
 def test_fullsize_fi_backward(lib, oracle, variant):
     """FilterInterpolation backward at 8 x 3 x 1152 x 1984 through the C ABI (what the operator table times)."""

@@ -609,7 +609,7 @@ STRIP_CASES = [  # B, C, H, W, flow
     (1, 3, 200, 160, "shear"),
     (1, 3, 120, 224, "wild"),
     (1, 3, 160, 288, "jump_back"),
-    (2, 1, 64, 160, "gauss"),             # narrowest width the path accepts
+    (2, 1, 64, 160, "gauss"),             # narrowest width the path accepts (128-column instantiation)
     (1, 2, 70, 196, "unit"),
     (1, 4, 90, 164, "gauss"),
     (3, 3, 8, 640, "gauss"),              # very short strips: many strip changes per CTA

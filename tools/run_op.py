@@ -52,6 +52,8 @@ gi1, gi2, gi3, gi4 = torch.empty_like(I), torch.empty_like(fl), torch.empty_like
 out = torch.empty_like(I)
 ops = {
     "fi_ori_fwd": lambda: _lib.call("vfidkr_filterinterpolation_forward_ori", ptr(I), ptr(fl), ptr(ft), ptr(out), B, C, H, W, 4, sp),
+    "fi_ori_blend": lambda: (_lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(I), ptr(fl), ptr(ft), ptr(out), B, C, H, W, 4, 0.5, 0, 0, sp),
+                             _lib.call("vfidkr_filterinterpolation_forward_ori_blend", ptr(I), ptr(fl), ptr(ft), ptr(out), B, C, H, W, 4, 0.5, 1, 0, sp)),
     "fi_ori_fwd_py": lambda: V.FilterInterpolationLayer.apply(I, fl, ft),
     "fi_dkr_fwd": lambda: V.FilterInterpolationLayerDKR.apply(I, fl, ft, off),
     "fi_deforconv_fwd": lambda: V.FilterInterpolationLayerDeforConv.apply(I, fl, ft, off),

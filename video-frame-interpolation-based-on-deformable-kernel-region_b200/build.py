@@ -20,8 +20,11 @@ INCLUDE = PKG_DIR.parent / "include"
 OBJ_DIR = PKG_DIR / "_build"
 LIB_PATH = PKG_DIR / "libvfidkr_b200.so"
 
-SOURCES = ["capi.cu", "filterinterpolation.cu", "fi_strip.cu", "fi_strip_dkr.cu", "fi_bigc.cu", "projection.cu", "interpolation.cu", "separableconv.cu",
+SOURCES = ["capi.cu", "filterinterpolation.cu", "fi_strip.cu", "fi_strip_w128.cu", "fi_strip_dkr.cu", "fi_bigc.cu", "projection.cu", "interpolation.cu", "separableconv.cu",
            "correlation.cu", "correlation_tc.cu", "pwcwarp.cu", "frameio.cu"]
+
+# sources that #include another source (same kernel, other compile-time geometry)
+INCLUDES_SOURCE = {"fi_strip_w128.cu": ["fi_strip.cu"]}
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -61,7 +64,7 @@ def build_library(force: bool = False, verbose: bool = False) -> Path:
     jobs = []
     for name in SOURCES:
         src, obj = CSRC / name, OBJ_DIR / (name + ".o")
-        if force or _stale(obj, [src] + headers):
+        if force or _stale(obj, [src] + [CSRC / d for d in INCLUDES_SOURCE.get(name, [])] + headers):
             jobs.append((src, obj))
 
     def compile_one(job):

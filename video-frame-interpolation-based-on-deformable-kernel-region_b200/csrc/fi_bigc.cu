@@ -33,6 +33,7 @@ constexpr uint32_t STAGE_BYTES = CG * PLANE * sizeof(float);
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 128;
 }  // namespace bigc
 
+template <bool BLEND>
 __global__ void __launch_bounds__(bigc::NT, 2)
 fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const float *__restrict__ in1,
                            const float *__restrict__ in2, const float *__restrict__ in3, float *__restrict__ out,
@@ -42,9 +43,12 @@ fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const fl
     // (+ what output held), batch items of the output out_bs elements apart -- the warped context features of
     // DAIN_slowmotion.py:167-181 land directly in their channel slice of the 437-channel rectify input
     using namespace bigc;
+    // (a separate instantiation: carried by the plain kernel as run-time flags the epilogue cost it 10 %)
     auto put = [&](float *dst, float v) {
-        v *= scale;
-        if (accumulate) v += __ldcs(dst);
+        if (BLEND) {
+            v *= scale;
+            if (accumulate) v += __ldcs(dst);
+        }
         st_stream(dst, v);
     };
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -193,12 +197,14 @@ int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, fl
     if (C <= 4 || W % 4 != 0 || !aligned16(in1) || ceil_div(H, TH) > 65535u) return -1;
     CUtensorMap mimg;
     if (!encode_tensor_map_4d(&mimg, in1, W, H, C, B, RW, RH, CG)) return -1;
-    if (cudaFuncSetAttribute(fi_forward_ori_bigc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
+    const bool blend = scale != 1.0f || accumulate != 0 || out_bs != (size_t)C * H * W;
+    auto kernel = blend ? fi_forward_ori_bigc_kernel<true> : fi_forward_ori_bigc_kernel<false>;
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) {
         (void)cudaGetLastError();
         return -1;
     }
     dim3 grid(ceil_div(W, TW), ceil_div(H, TH), B);
-    fi_forward_ori_bigc_kernel<<<grid, NT, SMEM_BYTES, s>>>(mimg, in1, in2, in3, out, C, H, W, scale, accumulate, out_bs);
+    kernel<<<grid, NT, SMEM_BYTES, s>>>(mimg, in1, in2, in3, out, C, H, W, scale, accumulate, out_bs);
     note_launch();
     return check_launch("filterinterpolation forward (many channels)");
 }

@@ -28,10 +28,21 @@
 #include <algorithm>
 #include <climits>
 
+// Tile width of THIS translation unit.  The file is compiled twice: as itself (144 columns: 18 compute warps + the producer
+// = 19 warps, five per scheduler at most, which is what a 96-register budget allows -- 7.6 % faster at 1080p than 128
+// columns / 16 warps, whose 17th warp cost the same budget) and through fi_strip_w128.cu (128 columns, window of 160
+// columns), which serves images narrower than the 192-column window of this one.  filterinterpolation.cu picks per launch.
+#ifndef VFIDKR_ORI_TW
+#define VFIDKR_ORI_TW 144
+#define VFIDKR_ORI_ENTRY fi_strip_forward_ori_w144
+#define VFIDKR_STRIP_NS strip_w144
+#define VFIDKR_ORI_PRIMARY 1
+#endif
+#define VFIDKR_STRIP_TW VFIDKR_ORI_TW
 #include "fi_strip_common.cuh"
 
 namespace vfidkr {
-namespace strip {
+namespace VFIDKR_STRIP_NS {
 
 // Optional pipeline statistics (build with -DVFIDKR_STRIP_STATS; read with vfidkr_debug_strip_stats): cycles the
 // producer spends in each kind of wait and the compute warps at the two "full" barriers.  Off in production builds.
@@ -54,8 +65,14 @@ constexpr uint32_t FILT_BYTES = FILT_FLOATS * sizeof(float);
 // filter pipeline depth: as deep as shared memory allows next to the window ring
 // (5 stages with a 35-row window were measured: no gain on smooth flows -- bytes in flight are not the limit -- and
 // 8 % slower on the bench flow, whose boxes need the rows)
-template <int CG> __host__ __device__ constexpr int stages() { return CG <= 3 ? 4 : 3; }
-template <int CG> __host__ __device__ constexpr size_t smem_bytes()
+constexpr size_t SMEM_LIMIT = 227 * 1024;
+template <int CG> static __host__ __device__ constexpr int stages()
+{
+    // as many as fit next to the window ring, at most 4
+    int n = (int)((SMEM_LIMIT - 1024 - (size_t)RROWS * row_floats<CG>() * sizeof(float)) / FILT_BYTES);
+    return n > 4 ? 4 : n;
+}
+template <int CG> static __host__ __device__ constexpr size_t smem_bytes()
 {
     return (size_t)stages<CG>() * FILT_BYTES + (size_t)RROWS * row_floats<CG>() * sizeof(float) + 1024;
 }
@@ -94,9 +111,11 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
     float *s_filt = reinterpret_cast<float *>(smem_raw);                              // [SF][16][TH][TW]
     float *s_ring = s_filt + SF * FILT_FLOATS;                                         // [RROWS][CG][WB]
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + RROWS * ROWF);
-    uint64_t *filt_full = s_bar, *tile_done = s_bar + SF, *bbox_done = s_bar + 2 * SF, *img_full = bbox_done + NB;
-    uint64_t *filt_free = img_full + NB;                                              // [SF]
-    Box *s_box = reinterpret_cast<Box *>(filt_free + SF);                             // [NB]
+    // tile_done is a ring of NB (> LEAD) barriers of its own: the producer waits on the last LEAD tiles, which must map to
+    // distinct barriers -- indexed by filter stage it aliased tiles t-4 and t-1 whenever a kernel has fewer than 4 stages
+    uint64_t *filt_full = s_bar, *filt_free = s_bar + SF, *tile_done = s_bar + 2 * SF;   // [SF], [SF], [NB]
+    uint64_t *bbox_done = tile_done + NB, *img_full = bbox_done + NB;                    // [NB], [NB]
+    Box *s_box = reinterpret_cast<Box *>(img_full + NB);                              // [NB]
     TileMeta *s_meta = reinterpret_cast<TileMeta *>(s_box + NB);                      // [NB]
     int *s_need = reinterpret_cast<int *>(s_meta + NB);                               // [NB], producer private
     ItemQueue *s_queue = reinterpret_cast<ItemQueue *>(s_need + NB);
@@ -109,10 +128,10 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
         prefetch_tensormap(&map_img);
         for (int s = 0; s < SF; ++s) {
             mbar_init(&filt_full[s], 1);
-            mbar_init(&tile_done[s], NCOMP_WARPS);
             mbar_init(&filt_free[s], NCOMP_WARPS);
         }
         for (int s = 0; s < NB; ++s) {
+            mbar_init(&tile_done[s], NCOMP_WARPS);
             mbar_init(&bbox_done[s], NCOMP_WARPS);
             mbar_init(&img_full[s], 1);
             s_box[s] = Box{INT_MAX, INT_MIN, INT_MAX, INT_MIN};
@@ -249,7 +268,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                         int need = my_need;
                         for (int q = oldest; q < t; ++q) need = min(need, s_need[q % NB]);
                         if (wr_after - need <= RROWS) break;
-                        STAT_TIME(2, wait_pumping(&tile_done[oldest % SF], (uint32_t)((oldest / SF) & 1)));   // oldest < t here
+                        STAT_TIME(2, wait_pumping(&tile_done[oldest % NB], (uint32_t)((oldest / NB) & 1)));   // oldest < t here
                         ++oldest;
                     }
                     load_lo = max(hi, bb.ymin);
@@ -473,7 +492,7 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive_a(a_tile_done + sf * 8);   // this warp is done with the window rows of tile j
+            if (lane == 0) mbar_arrive_a(a_tile_done + sb * 8);   // this warp is done with the window rows of tile j
             advance(cur);
 #pragma unroll
             for (int k = 0; k < LEAD; ++k) { qx[k] = qx[k + 1]; qy[k] = qy[k + 1]; }
@@ -515,24 +534,24 @@ static int launch(const CUtensorMap &mfilt, const float *in1, const float *in2, 
     return e ? e : e2;
 }
 
-}  // namespace strip
+}  // namespace VFIDKR_STRIP_NS
 
-#ifdef VFIDKR_STRIP_STATS
+#if defined(VFIDKR_STRIP_STATS) && defined(VFIDKR_ORI_PRIMARY)
 // debug builds only: reads and clears the pipeline statistics (16 counters, see STAT_DECL comments)
 extern "C" __attribute__((visibility("default"))) int vfidkr_debug_strip_stats(unsigned long long *out16)
 {
     unsigned long long zero[16] = {0};
     if (cudaDeviceSynchronize() != cudaSuccess) return 1;
-    if (cudaMemcpyFromSymbol(out16, strip::g_stats, sizeof zero) != cudaSuccess) return 1;
-    return cudaMemcpyToSymbol(strip::g_stats, zero, sizeof zero) != cudaSuccess;
+    if (cudaMemcpyFromSymbol(out16, VFIDKR_STRIP_NS::g_stats, sizeof zero) != cudaSuccess) return 1;
+    return cudaMemcpyToSymbol(VFIDKR_STRIP_NS::g_stats, zero, sizeof zero) != cudaSuccess;
 }
 #endif
 
 // Returns VFIDKR_OK / VFIDKR_ERR_CUDA when the strip kernel was launched, -1 when it does not apply.
-int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
+int VFIDKR_ORI_ENTRY(const float *in1, const float *in2, const float *in3, float *out,
                          int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s)
 {
-    using namespace strip;
+    using namespace VFIDKR_STRIP_NS;
     if (C < 1 || C > 4 || W % 4 != 0 || W < WB) return -1;
     if (!aligned16(in1) || !aligned16(in3)) return -1;
     CUtensorMap mfilt;

@@ -9,19 +9,33 @@
 #include "fi_common.cuh"
 #include "tma.cuh"
 
-namespace vfidkr {
-namespace strip {
+// Every translation unit that includes this header names its own namespace (VFIDKR_STRIP_NS): the kernels are templates with
+// external linkage, and two units with different tile widths must not share symbols.
+#ifndef VFIDKR_STRIP_NS
+#define VFIDKR_STRIP_NS strip
+#endif
 
-constexpr int TW = 128, TH = 4, NPIX = TW * TH;    // tile = 512 pixels, one per compute thread
-constexpr int NCOMP_WARPS = NPIX / 32;             // 16 compute warps
+namespace vfidkr {
+namespace VFIDKR_STRIP_NS {
+
+// Tile width: a translation unit may choose its own (VFIDKR_STRIP_TW before the include; everything here has internal
+// linkage, so the "_ori" and the DKR kernels can differ).  Threads are numbered along the tile's rows; when the width is
+// not a multiple of 32 a warp straddles two rows, which nothing below depends on.
+#ifndef VFIDKR_STRIP_TW
+#define VFIDKR_STRIP_TW 128
+#endif
+constexpr int TW = VFIDKR_STRIP_TW, TH = 4, NPIX = TW * TH;   // tile: one pixel per compute thread
+static_assert(NPIX % 32 == 0 && TW % 8 == 0, "tile = whole warps, TMA boxes of whole sectors");
+constexpr int NCOMP_WARPS = NPIX / 32;             // compute warps
 constexpr int NTHREADS = NPIX + 32;                // + 1 producer warp
 constexpr int LEAD = 4;                            // flow / bounding box / image window run this many tiles ahead
 constexpr int NB = 8;                              // ring of bounding boxes and tile descriptors (> LEAD)
-constexpr int WB = 160;                            // columns held by the rolling window (tile + 16 either side)
+constexpr int WB = (TW + 32 + 31) / 32 * 32;       // columns held by the rolling window: tile + >= 16 either side; a multiple of 32 so
+                                                   // that every row slot of the ring ([C][WB] floats) is a 128-byte aligned TMA destination
 constexpr int RROWS = 48;                          // rows held by the rolling window (a ring indexed by y % RROWS)
 enum { MODE_NONE = 0, MODE_SMEM = 1, MODE_GLOBAL = 2 };
 
-template <int CG> __host__ __device__ constexpr int row_floats() { return CG * WB; }   // one window row: [C][WB]
+template <int CG> static __host__ __device__ constexpr int row_floats() { return CG * WB; }   // one window row: [C][WB]
 
 struct TileMeta { int mode, xorg, soff, pad_; };   // window descriptor of one tile: x origin and slot offset (row y -> slot (y + soff) mod RROWS)
 struct Box { int xmin, xmax, ymin, ymax; };
@@ -98,5 +112,5 @@ inline int choose_segments(int B, int tiles_x, int tiles_y, int sms)
     return best_nseg;
 }
 
-}  // namespace strip
+}  // namespace VFIDKR_STRIP_NS
 }  // namespace vfidkr

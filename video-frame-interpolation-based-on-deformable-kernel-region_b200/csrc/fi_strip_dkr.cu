@@ -21,18 +21,29 @@
 // falls back to the direct kernels of filterinterpolation.cu.
 #include <algorithm>
 
+// tile width of THESE kernels (fi_strip.cu chooses its own)
+#ifndef VFIDKR_DKR_TW
+#define VFIDKR_DKR_TW 128
+#endif
+#define VFIDKR_STRIP_TW VFIDKR_DKR_TW
+#define VFIDKR_STRIP_NS strip_dkr
 #include "fi_strip_common.cuh"
 
 namespace vfidkr {
-namespace strip {
+namespace VFIDKR_STRIP_NS {
 
 constexpr int LEAD_D = 3;                                        // lookahead of THIS kernel: 4 (fi_strip.cu's) costs registers it does not have
 constexpr int SUB_PLANES = 12;                                   // 4 filter + 4 offY + 4 offX planes per sub-stage
 constexpr int SUB_FLOATS = SUB_PLANES * NPIX;
 constexpr int GROUP_FLOATS = 4 * NPIX;                           // one TMA box: 4 planes x tile
 constexpr uint32_t GROUP_BYTES = GROUP_FLOATS * sizeof(float);
-template <int CG> __host__ __device__ constexpr int sub_stages() { return CG <= 3 ? 5 : 4; }
-template <int CG> __host__ __device__ constexpr size_t dkr_smem_bytes()
+template <int CG> static __host__ __device__ constexpr int sub_stages()
+{
+    // as many as fit next to the window ring (227 KB per CTA), at most 5
+    int n = (int)((227 * 1024 - 1024 - (size_t)RROWS * row_floats<CG>() * sizeof(float)) / (SUB_FLOATS * sizeof(float)));
+    return n > 5 ? 5 : n;
+}
+template <int CG> static __host__ __device__ constexpr size_t dkr_smem_bytes()
 {
     return (size_t)sub_stages<CG>() * SUB_FLOATS * sizeof(float) + (size_t)RROWS * row_floats<CG>() * sizeof(float) + 1024;
 }
@@ -447,14 +458,14 @@ static int dispatch_dkr(const float *in1, const float *in2, const float *filt, c
     }
 }
 
-}  // namespace strip
+}  // namespace VFIDKR_STRIP_NS
 
 // Returns VFIDKR_OK / VFIDKR_ERR_CUDA when the strip kernel was launched, -1 when it does not apply.
 // variant: V_DKR / V_DEFOR (filt = input3 [B,16,H,W], offs = input4 [B,32,H,W]) or V_NOFILT (offs = input3, filt unused).
 int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
                          int B, int C, int H, int W, cudaStream_t s)
 {
-    using namespace strip;
+    using namespace VFIDKR_STRIP_NS;
     if (C < 1 || C > 4 || W % 4 != 0 || W < WB) return -1;
     if (!aligned16(in1) || !aligned16(offs) || (variant != V_NOFILT && !aligned16(filt))) return -1;
     switch (variant) {

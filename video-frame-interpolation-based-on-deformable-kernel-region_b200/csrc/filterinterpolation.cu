@@ -27,8 +27,26 @@
 
 namespace vfidkr {
 
-int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
-                         int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s);   // fi_strip.cu; -1 = not applicable
+// fi_strip.cu / fi_strip_w128.cu: the same kernel with 144- and 128-column tiles; -1 = not applicable
+int fi_strip_forward_ori_w144(const float *in1, const float *in2, const float *in3, float *out,
+                              int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s);
+int fi_strip_forward_ori_w128(const float *in1, const float *in2, const float *in3, float *out,
+                              int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s);
+// Tile width per launch.  Measured on B200 (profiles/r02/strip_width_ab_v1.log, 128 | 144 columns): 8 x 3 x 1152 x 1984
+// 399 | 369 us, blend pair 813 | 790, 8 x 4 x 1152 x 1984 433 | 422, 8 x 3 x 736 x 1280 199 | 185, 16 x 3 x 256 x 448
+// 101 | 73, 4K x 2 368 | 356, 4K x 1 201 | 208 -- the 144-column kernel (19 instead of 17 warps per SM at the same
+// register budget, never more strips than the 128-column one) wins everywhere except a single 4K frame (3 %), so it is
+// taken whenever it applies (W >= 192); the 128-column kernel serves 160 <= W < 192.
+static int fi_strip_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
+                                int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s)
+{
+    static const int forced_tw = [] { const char *e = getenv("VFIDKR_FI_STRIP_TW"); return e ? atoi(e) : 0; }();   // 128 / 144: experiments
+    if (forced_tw != 128) {
+        const int e = fi_strip_forward_ori_w144(in1, in2, in3, out, B, C, H, W, scale, accumulate, out_bs, s);
+        if (e >= 0) return e;
+    }
+    return fi_strip_forward_ori_w128(in1, in2, in3, out, B, C, H, W, scale, accumulate, out_bs, s);
+}
 int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, float *out,
                         int B, int C, int H, int W, float scale, int accumulate, size_t out_bs, cudaStream_t s);    // fi_bigc.cu (C > 4); -1 = not applicable
 int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const float *filt, const float *offs, float *out,
