@@ -32,7 +32,10 @@ constexpr int LEAD = 4;                            // flow / bounding box / imag
 constexpr int NB = 8;                              // ring of bounding boxes and tile descriptors (> LEAD)
 constexpr int WB = (TW + 32 + 31) / 32 * 32;       // columns held by the rolling window: tile + >= 16 either side; a multiple of 32 so
                                                    // that every row slot of the ring ([C][WB] floats) is a 128-byte aligned TMA destination
-constexpr int RROWS = 48;                          // rows held by the rolling window (a ring indexed by y % RROWS)
+#ifndef VFIDKR_STRIP_RROWS
+#define VFIDKR_STRIP_RROWS 48
+#endif
+constexpr int RROWS = VFIDKR_STRIP_RROWS;           // rows held by the rolling window (a ring indexed by y % RROWS)
 enum { MODE_NONE = 0, MODE_SMEM = 1, MODE_GLOBAL = 2 };
 
 template <int CG> static __host__ __device__ constexpr int row_floats() { return CG * WB; }   // one window row: [C][WB]
