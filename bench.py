@@ -436,6 +436,11 @@ def bench_ours(args):
     t_ms = torch.tensor([ms_total], dtype=torch.float64, device=device)
     units = torch.tensor([float(args.steps * PAIRS_PER_GPU)], dtype=torch.float64, device=device)   # frames out
     nl = torch.tensor([float(launches)], dtype=torch.float64, device=device)
+    per_rank_ms = None
+    if world > 1:   # the spread behind the max: every rank's own device time per step (GPUs of one box are not identical)
+        allt = [torch.zeros_like(t_ms) for _ in range(world)]
+        dist.all_gather(allt, t_ms)
+        per_rank_ms = [round(float(t.item()) / args.steps, 4) for t in allt]
     reduce_timing(t_ms, units)
     if world > 1:
         dist.all_reduce(nl, op=dist.ReduceOp.SUM)
@@ -458,6 +463,8 @@ def bench_ours(args):
                      "frac_iid_flow": alg / (other_flows["iid"] * 1e-3) / 1e9 / peak if other_flows else None},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(nl.item()), "check": check,
     }
+    if per_rank_ms is not None:
+        line["ms_per_step_by_rank"] = per_rank_ms
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_reference_arm(steps=5, warmup=1)
