@@ -27,6 +27,9 @@
 #endif
 #define VFIDKR_STRIP_TW VFIDKR_DKR_TW
 #define VFIDKR_STRIP_NS strip_dkr
+#ifndef VFIDKR_DKR_MAX_SUB
+#define VFIDKR_DKR_MAX_SUB 5
+#endif
 #include "fi_strip_common.cuh"
 
 namespace vfidkr {
@@ -39,9 +42,9 @@ constexpr int GROUP_FLOATS = 4 * NPIX;                           // one TMA box:
 constexpr uint32_t GROUP_BYTES = GROUP_FLOATS * sizeof(float);
 template <int CG> static __host__ __device__ constexpr int sub_stages()
 {
-    // as many as fit next to the window ring (227 KB per CTA), at most 5
+    // as many as fit next to the window ring (227 KB per CTA), at most VFIDKR_DKR_MAX_SUB
     int n = (int)((227 * 1024 - 1024 - (size_t)RROWS * row_floats<CG>() * sizeof(float)) / (SUB_FLOATS * sizeof(float)));
-    return n > 5 ? 5 : n;
+    return n > VFIDKR_DKR_MAX_SUB ? VFIDKR_DKR_MAX_SUB : n;
 }
 template <int CG> static __host__ __device__ constexpr size_t dkr_smem_bytes()
 {
