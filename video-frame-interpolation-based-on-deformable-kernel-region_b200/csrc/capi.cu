@@ -199,3 +199,25 @@ VFIDKR_API int vfidkr_trim_scratch(void)
     if (vfidkr::g_pool_state[dev].load(std::memory_order_acquire) != 1) return VFIDKR_OK;
     return vfidkr::set_error(cudaMemPoolTrimTo(vfidkr::g_pool[dev], 0), "trim scratch pool");
 }
+
+#ifdef VFIDKR_BOUNDS_CHECK
+namespace vfidkr {
+int bounds_counts_strip_w144(unsigned long long *), bounds_counts_strip_w128(unsigned long long *);
+int bounds_counts_strip_dkr(unsigned long long *), bounds_counts_bigc(unsigned long long *);
+}
+// debug builds only (-DVFIDKR_BOUNDS_CHECK): out2[0] = window checks executed so far, out2[1] = checks failed
+extern "C" __attribute__((visibility("default"))) int vfidkr_debug_bounds_counts(unsigned long long *out2)
+{
+    if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+    out2[0] = out2[1] = 0;
+    int (*const parts[])(unsigned long long *) = {vfidkr::bounds_counts_strip_w144, vfidkr::bounds_counts_strip_w128,
+                                                  vfidkr::bounds_counts_strip_dkr, vfidkr::bounds_counts_bigc};
+    for (auto f : parts) {
+        unsigned long long c[2] = {0, 0};
+        if (f(c)) return 1;
+        out2[0] += c[0];
+        out2[1] += c[1];
+    }
+    return 0;
+}
+#endif

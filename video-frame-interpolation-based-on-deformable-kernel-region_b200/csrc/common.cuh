@@ -73,4 +73,31 @@ __device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long 
 // fire-and-forget float add (RED.E.ADD.F32)
 __device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
 
+
+// ---- debug build -DVFIDKR_BOUNDS_CHECK (compute-sanitizer is not available on every pool): the kernels that read images
+// through shared-memory windows verify, tap by tap, (1) that the shared-memory index lies inside the window ring / region
+// and (2) that the value found there is bit-identical to the image value in global memory it stands for -- a stale or
+// not-yet-filled window row (a pipeline race) or a wrong index cannot pass.  Counters are per translation unit;
+// vfidkr_debug_bounds_counts (capi.cu) adds them up.  Production builds compile none of this.
+#ifdef VFIDKR_BOUNDS_CHECK
+namespace {
+__device__ unsigned long long g_bounds_counts[2];   // [0] checks executed, [1] checks failed (this translation unit)
+}
+__device__ __forceinline__ void bounds_check(bool ok)
+{
+    const unsigned m = __activemask(), bad = __ballot_sync(m, !ok);
+    unsigned lane;
+    asm("mov.u32 %0, %%laneid;" : "=r"(lane));
+    if (lane == (unsigned)(__ffs(m) - 1)) {
+        atomicAdd(&g_bounds_counts[0], (unsigned long long)__popc(m));
+        if (bad) atomicAdd(&g_bounds_counts[1], (unsigned long long)__popc(bad));
+    }
+}
+#define VFIDKR_BOUNDS_ACCESSOR(name)                                                                             \
+    namespace vfidkr { int name(unsigned long long *out2) {                                                      \
+        return cudaMemcpyFromSymbol(out2, g_bounds_counts, 2 * sizeof(unsigned long long)) != cudaSuccess; } }
+#else
+#define VFIDKR_BOUNDS_ACCESSOR(name)
+#endif
+
 }  // namespace vfidkr

@@ -167,6 +167,15 @@ fi_forward_ori_bigc_kernel(const __grid_constant__ CUtensorMap map_img, const fl
                             Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)] =
                                 fmaf(pl[so[p][j] + sc[p][i]], w[p][j * 4 + i], Q[(j < 2 ? 0 : 2) + (i < 2 ? 0 : 1)]);
                     put(op + (size_t)c * HW, q[p][0] * Q[0] + q[p][1] * Q[1] + q[p][2] * Q[2] + q[p][3] * Q[3]);
+#ifdef VFIDKR_BOUNDS_CHECK
+                    for (int j = 0; j < 4; ++j)
+                        for (int i = 0; i < 4; ++i) {
+                            const int idx = so[p][j] + sc[p][i];
+                            const bool inside = idx >= 0 && idx < PLANE;
+                            const float want = __ldg(img + (size_t)(g * CG + c) * HW + (size_t)(so[p][j] / RW + by0) * W + (sc[p][i] + bx0));
+                            bounds_check(inside && __float_as_uint(pl[inside ? idx : 0]) == __float_as_uint(want));
+                        }
+#endif
                 }
             } else {   // pixel far from the tile's mean flow: clamped gathers from the plane
                 for (int c = 0; c < nc; ++c) {
@@ -210,3 +219,5 @@ int fi_bigc_forward_ori(const float *in1, const float *in2, const float *in3, fl
 }
 
 }  // namespace vfidkr
+
+VFIDKR_BOUNDS_ACCESSOR(bounds_counts_bigc)

@@ -456,6 +456,16 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 #pragma unroll
                             for (int c = 0; c < CG; ++c)
                                 res[c] = window_from_smem<true>(s_ring + c * WB, off, co, w, qTL, qTR, qBL, qBR);
+#ifdef VFIDKR_BOUNDS_CHECK
+                            for (int c = 0; c < CG; ++c)
+                                for (int r = 0; r < 4; ++r)
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int idx = c * WB + off[r] + i;
+                                        const bool inside = idx >= 0 && idx < RROWS * ROWF;
+                                        const float want = __ldg(in1 + (size_t)cur.b * CG * HW + (size_t)c * HW + (size_t)(T + r) * W + (L + i));
+                                        bounds_check(inside && __float_as_uint(s_ring[inside ? idx : 0]) == __float_as_uint(want));
+                                    }
+#endif
                         } else {
 #pragma unroll
                             for (int r = 0; r < 4; ++r) {
@@ -465,6 +475,17 @@ fi_forward_ori_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
 #pragma unroll
                             for (int c = 0; c < CG; ++c)
                                 res[c] = window_from_smem<false>(s_ring + c * WB, off, co, w, qTL, qTR, qBL, qBR);
+#ifdef VFIDKR_BOUNDS_CHECK
+                            for (int c = 0; c < CG; ++c)
+                                for (int r = 0; r < 4; ++r)
+                                    for (int i = 0; i < 4; ++i) {
+                                        const int idx = c * WB + off[r] + co[i];
+                                        const bool inside = idx >= 0 && idx < RROWS * ROWF;
+                                        const float want = __ldg(in1 + (size_t)cur.b * CG * HW + (size_t)c * HW +
+                                                                 (size_t)clampi(T + r, 0, H - 1) * W + clampi(L + i, 0, W - 1));
+                                        bounds_check(inside && __float_as_uint(s_ring[inside ? idx : 0]) == __float_as_uint(want));
+                                    }
+#endif
                         }
                     } else {
                         // the tile's windows do not fit the rolling window: clamped gathers from global memory
@@ -574,3 +595,9 @@ int VFIDKR_ORI_ENTRY(const float *in1, const float *in2, const float *in3, float
 }
 
 }  // namespace vfidkr
+
+#ifdef VFIDKR_ORI_PRIMARY
+VFIDKR_BOUNDS_ACCESSOR(bounds_counts_strip_w144)
+#else
+VFIDKR_BOUNDS_ACCESSOR(bounds_counts_strip_w128)
+#endif

@@ -360,6 +360,21 @@ fi_forward_dkr_strip_kernel(const __grid_constant__ CUtensorMap map_filt, const 
                                 v[i][0][c] = pTL[c * WB]; v[i][1][c] = pTR[c * WB];
                                 v[i][2][c] = pBL[c * WB]; v[i][3][c] = pBR[c * WB];
                             }
+#ifdef VFIDKR_BOUNDS_CHECK
+                            {   // the same four corners by the direct kernel's clamp-to-plane rule, from global memory
+                                const int t = clampi(Top[i], 0, H - 1), bm = clampi(min(Top[i], H - 1) + 1, 0, H - 1);
+                                const int l = clampi(Left[i], 0, W - 1), r = clampi(min(Left[i], W - 1) + 1, 0, W - 1);
+                                const int ids[4] = {rt + cl, rt + cr, rbm + cl, rbm + cr};
+                                const int gs[4] = {t * W + l, t * W + r, bm * W + l, bm * W + r};
+                                for (int c = 0; c < CG; ++c)
+                                    for (int k = 0; k < 4; ++k) {
+                                        const int idx = ids[k] + c * WB;
+                                        const bool inside = idx >= 0 && idx < RROWS * ROWF;
+                                        const float want = __ldg(img + (size_t)c * HW + gs[k]);
+                                        bounds_check(inside && __float_as_uint(s_ring[inside ? idx : 0]) == __float_as_uint(want));
+                                    }
+                            }
+#endif
                         }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -480,3 +495,5 @@ int fi_strip_forward_dkr(int variant, const float *in1, const float *in2, const 
 }
 
 }  // namespace vfidkr
+
+VFIDKR_BOUNDS_ACCESSOR(bounds_counts_strip_dkr)
