@@ -6,17 +6,18 @@
 // is what bounds the straightforward kernels (L1 tag/sector throughput and 1.8 cycles per LDG of LSU issue),
 // so here the gathers are served from SHARED memory:
 //
-//   * one persistent CTA per SM walks 128 x 4 pixel tiles DOWN a 128-column strip segment of one frame; segments
-//     are dealt to CTAs so that neighbouring CTAs work on neighbouring strips at the same rows at the same
-//     time (their overlapping window columns then hit in L2 instead of being fetched from HBM twice);
-//   * 16 compute warps, one pixel per thread, warps along x.  A thread loads the flow of ITS pixel for the tile
-//     LEAD (= 3) tiles ahead straight into registers, derives the clamped extent of that pixel's gather window
-//     and folds it into the tile's bounding box (warp min/max reduction + 4 shared-memory atomics per warp);
-//   * a producer warp (a) streams the 16 filter planes of the next tiles into a 4-stage ring with TMA
-//     (cp.async.bulk.tensor, ~100 KB in flight per SM = HBM latency x bandwidth), and (b) as soon as a tile's
-//     bounding box is complete tops up a ROLLING WINDOW of image rows -- a ring of 48 rows x C channels x 160
-//     columns, row y living in slot y % 48, also filled by TMA -- with just the rows the tile adds (about 4 per
-//     tile, so the image is fetched from L2 ~1.3x instead of the ~4-6x of per-tile halos), three tiles ahead;
+//   * one persistent CTA per SM walks TW x 4 pixel tiles (TW = 144, or 128 in the second instantiation) DOWN a strip
+//     segment of one frame; segments are drawn by the CTAs in an order that keeps neighbouring CTAs on neighbouring strips
+//     at the same rows at the same time (their overlapping window columns then hit in L2 instead of coming from HBM twice);
+//   * TW / 8 compute warps (18 / 16), one pixel per thread, threads numbered along the tile's rows.  A thread loads the
+//     flow of ITS pixel for the tile LEAD (= 4) tiles ahead straight into registers, derives the clamped extent of that
+//     pixel's gather window and folds it into the tile's bounding box (warp min/max reduction + 4 shared-memory atomics
+//     per warp);
+//   * a producer warp (a) streams the 16 filter planes of the next tiles into a ring of 3 (4) stages with TMA
+//     (cp.async.bulk.tensor, ~100 KB in flight per SM = several times HBM latency x bandwidth), and (b) as soon as a
+//     tile's bounding box is complete tops up a ROLLING WINDOW of image rows -- a ring of 48 rows x C channels x 192 (160)
+//     columns, row y living in slot y % 48, also filled by TMA -- with just the rows the tile adds (about 4 per tile, so
+//     the image is fetched from L2 ~1.3x instead of the ~4-6x of per-tile halos), four tiles ahead;
 //   * the compute warps then read taps and the 16 x C window values with LDS (conflict-free when the flow is
 //     locally smooth) and write the result with streaming stores;
 //   * hand-off is mbarrier based (filter full / tile done / bbox done / image full).  The window is re-based
@@ -24,7 +25,8 @@
 //     clamped global gathers -- correctness never depends on the flow.
 //
 // Preconditions for this path (checked by the launcher, which otherwise reports "not applicable" and the
-// caller uses the generic kernels): F == 4, 1 <= C <= 4, W % 4 == 0, W >= 160, 16-byte aligned bases.
+// caller uses the generic kernels): F == 4, 1 <= C <= 4, W % 4 == 0, W >= the window width (192 / 160), 16-byte
+// aligned bases.
 #include <algorithm>
 #include <climits>
 
