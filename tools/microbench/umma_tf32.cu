@@ -142,8 +142,134 @@ static void run(const char *name, bool exact_inputs)
     cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dc);
 }
 
+// ---- MN-major with the 64-byte swizzle: what a TMA box (16 pixels, K channels, m blocks) with CU_TENSOR_MAP_SWIZZLE_64B of
+// a channel-planar (NCHW) map delivers.  Element (mn, k) of an R-row operand: byte (mn / 16) * (K * 64) + k * 64 + (mn % 16) * 4,
+// then bits [4,6) ^= bits [7,9) (Swizzle<2,4,3>).  Descriptor: layout type 4, LBO = K * 64 (next block of 16 rows),
+// SBO = 512 (next group of 8 K); one MMA (K = 8) per 512-byte step of the start address.
+template <bool SPLIT>
+__global__ void __launch_bounds__(128) umma_mn64_kernel(const float *A, const float *B, float *D, int reps, unsigned long long *cycles, int amn = 1, int bmn = 1)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *base = smem + ((1024 - (smem_u32(smem) & 1023)) & 1023);
+    float *sA = reinterpret_cast<float *>(base), *sB = sA + M * K, *sAl = sB + N * K, *sBl = sAl + M * K;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    auto idx_mn = [](int row, int k) {
+        uint32_t byte = (uint32_t)(row >> 4) * (K * 64) + (uint32_t)k * 64 + (uint32_t)(row & 15) * 4;
+        byte ^= ((byte >> 7) & 3u) << 4;
+        return (int)(byte >> 2);
+    };
+    auto idx_k = [](int row, int k, int rows) { return ((k >> 2) * rows + row) * 4 + (k & 3); };
+    auto idxA = [&](int row, int k) { return amn ? idx_mn(row, k) : idx_k(row, k, M); };
+    auto idxB = [&](int row, int k) { return bmn ? idx_mn(row, k) : idx_k(row, k, N); };
+    auto lo_of = [](float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); };
+    for (int i = tid; i < M * K; i += 128) { const int m = i / K, k = i % K; sA[idxA(m, k)] = A[m * K + k]; if (SPLIT) sAl[idxA(m, k)] = lo_of(A[m * K + k]); }
+    for (int i = tid; i < N * K; i += 128) { const int n = i / K, k = i % K; sB[idxB(n, k)] = B[n * K + k]; if (SPLIT) sBl[idxB(n, k)] = lo_of(B[n * K + k]); }
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t tmem = tmem_base;
+    const uint32_t idesc = make_idesc(M, N) | (amn ? (1u << 15) : 0u) | (bmn ? (1u << 16) : 0u);
+    long long t0 = clock64();
+    if (tid == 0) {
+        for (int r = 0; r < reps; ++r)
+            for (int ks = 0; ks < K / 8; ++ks) {
+                auto mma = [&](const float *a, const float *b, uint32_t acc) {
+                    const uint64_t da = amn ? make_desc(smem_u32(a) + ks * 512, K * 64, 512) | (4ull << 61) : make_desc(smem_u32(a) + ks * 2 * (M * 16), M * 16, 128);
+                    const uint64_t db = bmn ? make_desc(smem_u32(b) + ks * 512, K * 64, 512) | (4ull << 61) : make_desc(smem_u32(b) + ks * 2 * (N * 16), N * 16, 128);
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+                };
+                mma(sA, sB, (r > 0 || ks > 0) ? 1u : 0u);
+                if (SPLIT) { mma(sAl, sB, 1u); mma(sA, sBl, 1u); }
+            }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
+    }
+    {
+        uint32_t ok = 0;
+        while (!ok)
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok) : "r"(smem_u32(&bar)) : "memory");
+    }
+    long long t1 = clock64();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]) : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+    if (tid == 0 && cycles) *cycles = (unsigned long long)(t1 - t0);
+}
+
+template <bool SPLIT>
+static void run_mn64(const char *name, bool exact_inputs, int amn = 1, int bmn = 1)
+{
+    std::vector<float> hA(M * K), hB(N * K), hD(M * N);
+    std::vector<double> ref(M * N);
+    srand(1);
+    for (auto &v : hA) v = exact_inputs ? (float)(rand() % 17 - 8) / 8.0f : (float)rand() / RAND_MAX * 2.f - 1.f;
+    for (auto &v : hB) v = exact_inputs ? (float)(rand() % 17 - 8) / 8.0f : (float)rand() / RAND_MAX * 2.f - 1.f;
+    double scale = 0;
+    for (int m = 0; m < M; ++m)
+        for (int n = 0; n < N; ++n) {
+            double s = 0;
+            for (int k = 0; k < K; ++k) s += (double)hA[m * K + k] * hB[n * K + k];
+            ref[m * N + n] = s;
+            if (fabs(s) > scale) scale = fabs(s);
+        }
+    float *dA, *dB, *dD;
+    unsigned long long *dc, hc = 0;
+    cudaMalloc(&dA, hA.size() * 4); cudaMalloc(&dB, hB.size() * 4); cudaMalloc(&dD, hD.size() * 4); cudaMalloc(&dc, 8);
+    cudaMemcpy(dA, hA.data(), hA.size() * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB.data(), hB.size() * 4, cudaMemcpyHostToDevice);
+    const size_t smem = (size_t)2 * (M + N) * K * 4 + 2048;
+    cudaFuncSetAttribute(umma_mn64_kernel<SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    umma_mn64_kernel<SPLIT><<<1, 128, smem>>>(dA, dB, dD, 1, dc, amn, bmn);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { printf("%s: launch failed: %s\n", name, cudaGetErrorString(e)); exit(1); }
+    cudaMemcpy(hD.data(), dD, hD.size() * 4, cudaMemcpyDeviceToHost);
+    double maxerr = 0;
+    for (int i = 0; i < M * N; ++i) { const double d = fabs((double)hD[i] - ref[i]); if (d > maxerr) maxerr = d; }
+    printf("  D[0][0..7]   :"); for (int j = 0; j < 8; ++j) printf(" %8.4f", hD[j]); printf("\n  ref[0][0..7] :"); for (int j = 0; j < 8; ++j) printf(" %8.4f", ref[j]);
+    printf("\n  D[1][0..7]   :"); for (int j = 0; j < 8; ++j) printf(" %8.4f", hD[N + j]); printf("\n  ref[1][0..7] :"); for (int j = 0; j < 8; ++j) printf(" %8.4f", ref[N + j]);
+    printf("\n  D[17][16..23]:"); for (int j = 16; j < 24; ++j) printf(" %8.4f", hD[17 * N + j]); printf("\n  ref[17][16..]:"); for (int j = 16; j < 24; ++j) printf(" %8.4f", ref[17 * N + j]); printf("\n");
+    {   // is D a permutation of ref?  look for ref[0][0] and D[0][0] in the other matrix
+        int hits = 0; for (int i = 0; i < M * N && hits < 6; ++i) if (fabs(hD[i] - ref[0]) < 1e-4) { printf("  ref[0][0] found in D at (%d, %d)\n", i / N, i % N); ++hits; }
+        hits = 0; for (int i = 0; i < M * N && hits < 6; ++i) if (fabs(ref[i] - hD[0]) < 1e-4) { printf("  D[0][0] equals ref at (%d, %d)\n", i / N, i % N); ++hits; }
+    }
+    const int reps = 2000;
+    umma_mn64_kernel<SPLIT><<<1, 128, smem>>>(dA, dB, dD, reps, dc, amn, bmn);
+    e = cudaDeviceSynchronize();
+    cudaMemcpy(&hc, dc, 8, cudaMemcpyDeviceToHost);
+    printf("%-44s max |err| / max |ref| = %.3g; %.1f MAC/clk/SM issued (%s)\n", name, maxerr / scale,
+           (double)reps * (K / 8) * (SPLIT ? 3 : 1) * M * N * 8 / (double)hc, cudaGetErrorString(e));
+    cudaFree(dA); cudaFree(dB); cudaFree(dD); cudaFree(dc);
+}
+
 int main()
 {
+    run_mn64<false>("both K-major through this kernel", true, 0, 0);
+    run_mn64<false>("A MN-major 64B swizzle, B K-major", true, 1, 0);
+    run_mn64<false>("A K-major, B MN-major 64B swizzle", true, 0, 1);
+    run_mn64<false>("MN-major 64B swizzle, tf32-exact, 1 pass", true);
+    return 0;
     run<false, false>("K-major, tf32-exact inputs, 1 pass", true);
     run<true, false>("MN-major, tf32-exact inputs, 1 pass", true);
     run<true, false, true>("MN-major (LBO <-> SBO swapped), exact, 1 pass", true);
