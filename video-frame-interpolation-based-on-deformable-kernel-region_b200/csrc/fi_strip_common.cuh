@@ -28,7 +28,10 @@ constexpr int TW = VFIDKR_STRIP_TW, TH = 4, NPIX = TW * TH;   // tile: one pixel
 static_assert(NPIX % 32 == 0 && TW % 8 == 0, "tile = whole warps, TMA boxes of whole sectors");
 constexpr int NCOMP_WARPS = NPIX / 32;             // compute warps
 constexpr int NTHREADS = NPIX + 32;                // + 1 producer warp
-constexpr int LEAD = 4;                            // flow / bounding box / image window run this many tiles ahead
+#ifndef VFIDKR_STRIP_LEAD
+#define VFIDKR_STRIP_LEAD 4
+#endif
+constexpr int LEAD = VFIDKR_STRIP_LEAD;                            // flow / bounding box / image window run this many tiles ahead
 constexpr int NB = 8;                              // ring of bounding boxes and tile descriptors (> LEAD)
 constexpr int WB = (TW + 32 + 31) / 32 * 32;       // columns held by the rolling window: tile + >= 16 either side; a multiple of 32 so
                                                    // that every row slot of the ring ([C][WB] floats) is a 128-byte aligned TMA destination
