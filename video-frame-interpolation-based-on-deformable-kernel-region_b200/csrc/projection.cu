@@ -172,7 +172,17 @@ __device__ __forceinline__ unsigned char *colmask_byte(unsigned long long *cm, i
 {
     return reinterpret_cast<unsigned char *>(cm + (size_t)x * colwords(H) + (seg >> 3)) + (seg & 7);
 }
-constexpr int FIN_ROWS = 8, FIN_WARPS = 4, FIN_UNROLL = 4;   // short segments: one frame per launch must still fill 148 SMs
+// FIN_UNROLL rows of loads are requested before the first is used.  Four in flight per lane looked right for a DRAM-bound
+// pass and was what round 1 shipped; measured with both libraries in one GPU call (profiles/r02/projection_finish_ab_v1.log)
+// it is the registers that matter: 1 row = 32 registers = 64 resident warps per SM, 4 rows = 53 registers = 36 warps --
+// DepthFlowProjection forward 364 -> 338 us (1: 338, 2: 350, 4: 364, 8: 412 us; 2 / 4 / 8 warps per block: no difference).
+#ifndef VFIDKR_FIN_WARPS
+#define VFIDKR_FIN_WARPS 4
+#endif
+#ifndef VFIDKR_FIN_UNROLL
+#define VFIDKR_FIN_UNROLL 1
+#endif
+constexpr int FIN_ROWS = 8, FIN_WARPS = VFIDKR_FIN_WARPS, FIN_UNROLL = VFIDKR_FIN_UNROLL;   // short segments: one frame per launch must still fill 148 SMs
 
 // raw loads of one row: this lane's cell and (lane 0 only) the cell left of the block
 // CG: the scratch image was written earlier in the SAME launch by other SMs (fused pipeline kernel below): read it
