@@ -357,7 +357,12 @@ __device__ __forceinline__ void fill_one(const float *__restrict__ cnb, float *_
 // sectors.  (Round 1 launched one CTA per 32 x 8 tile that re-read the count plane and compacted its holes: 71 k CTAs
 // at 1080p x 8, 75-180 us of CTA turnover for a few per cent of hole pixels.)
 constexpr int FILL_WARPS = 8;
-__global__ void __launch_bounds__(32 * FILL_WARPS)
+// eight resident blocks (32 registers, no spills) instead of the five that 46 registers allow: the scans are dependent
+// loads, more warps hide them (up4 flow: 388.6 -> 375.7 us for the whole DepthFlowProjection forward; scene 338.6 -> 336.6)
+#ifndef VFIDKR_FILL_MINB
+#define VFIDKR_FILL_MINB 8
+#endif
+__global__ void __launch_bounds__(32 * FILL_WARPS, VFIDKR_FILL_MINB)
 projection_fill_mask_kernel(const float *__restrict__ count, float *__restrict__ out, const unsigned *__restrict__ rowmask,
                             const unsigned long long *__restrict__ colmask, const unsigned *__restrict__ holemask,
                             int B, int H, int W, const FastDiv div_items, const FastDiv div_bw)
