@@ -67,8 +67,18 @@ __device__ __forceinline__ WarpGeom warp_geom(int w_i, int h_i, float fx, float 
     return g;
 }
 
+// Channel loop: 4 gathers per channel, so what pays is loads in flight -- eight channels unrolled at 64 registers (4 blocks
+// per SM) against four at 40 registers (6 blocks): 159 -> 89 us at 8 x 32 x 288 x 496; 16 / 32 channels unrolled are slower
+// again (193 / 250 us), and so is full occupancy at 32 registers (141 us) -- profiles/r02/pwc_warp_ab_v1.log.
+#ifndef VFIDKR_PWC_MINB
+#define VFIDKR_PWC_MINB 4
+#endif
+#ifndef VFIDKR_PWC_UNROLL
+#define VFIDKR_PWC_UNROLL 8
+#endif
+constexpr int PWC_UNROLL = VFIDKR_PWC_UNROLL;
 template <bool AC>
-__global__ void __launch_bounds__(BX *BY, 6)
+__global__ void __launch_bounds__(BX *BY, VFIDKR_PWC_MINB)
 pwcwarp_forward_kernel(const float *__restrict__ x, const float *__restrict__ flo, float *__restrict__ out, int C, int H, int W)
 {
     const int w_i = blockIdx.x * BX + threadIdx.x, h_i = blockIdx.y * BY + threadIdx.y;
@@ -81,7 +91,7 @@ pwcwarp_forward_kernel(const float *__restrict__ x, const float *__restrict__ fl
     const float *img = x + (size_t)b * C * HW;
     float *o = out + (size_t)b * C * HW + pix;
     const int a = g.y0 * W + g.x0;   // only dereferenced where the in_* flags allow
-#pragma unroll 4
+#pragma unroll PWC_UNROLL
     for (int c = 0; c < C; ++c) {
         const float *pl = img + (size_t)c * HW;
         float acc = 0.0f;            // grid_sampler_2d_kernel's order: nw, ne, sw, se
