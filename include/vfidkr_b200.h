@@ -34,7 +34,15 @@
  *     failed (the reference raises AT_ERROR("CUDA call failed") there).  The reference's
  *     correlation module inverts the convention (1 = success, correlation_cuda_kernel.cu:417-426);
  *     this ABI does not.
- *   - Thread-safe: no global mutable state except a relaxed launch counter.
+ *   - Thread-safe: no global mutable state except a relaxed launch counter, the per-device scratch
+ *     pool and the process-wide test hooks below.
+ *   - Environment (each read once, at first use): VFIDKR_SCRATCH_RETAIN_MB (above);
+ *     VFIDKR_FI_FWD_PATH = strip | tile | direct forces a FilterInterpolation forward
+ *     implementation (same as vfidkr_debug_force_forward_path); VFIDKR_FI_STRIP_TW = 128 | 144
+ *     forces the tile width of the "_ori" strip kernel (experiments; the default takes 144 columns
+ *     wherever the image is at least 192 wide).  Debug builds: -DVFIDKR_STRIP_STATS (pipeline
+ *     counters), -DVFIDKR_BOUNDS_CHECK (every shared-memory window tap verified against global
+ *     memory; vfidkr_debug_bounds_counts) -- neither symbol exists in a production build.
  */
 #ifndef VFIDKR_B200_H_
 #define VFIDKR_B200_H_
