@@ -52,24 +52,6 @@ __device__ __forceinline__ float4 ld_stream4(const float *p) { return __ldcs(rei
 __device__ __forceinline__ void st_stream(float *p, float v) { __stcs(p, v); }
 __device__ __forceinline__ void st_stream4(float *p, float4 v) { __stcs(reinterpret_cast<float4 *>(p), v); }
 
-// packed fp32 pairs for FFMA2 (fma.rn.f32x2, sm_100+): two independent IEEE fused multiply-adds per lane and instruction
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi)
-{
-    unsigned long long r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ float2 unpack2(unsigned long long v)
-{
-    float2 r;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
-    return r;
-}
-__device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long a, unsigned long long b)   // d += a * b, per half
-{
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
-}
-
 // fire-and-forget float add (RED.E.ADD.F32)
 __device__ __forceinline__ void red_add(float *p, float v) { atomicAdd(p, v); }
 
