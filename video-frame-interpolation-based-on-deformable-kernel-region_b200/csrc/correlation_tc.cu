@@ -16,7 +16,9 @@
 //              lane-dependent band extraction goes through a private shared-memory row, scaled stores to the 81 planes;
 //   warps 4-19 stagers: f1 patch / f2 neighbourhood chunk of 32 channels from global memory (L2), hi / lo split, written
 //              to shared memory in the canonical K-major no-swizzle core-matrix layout ([K/4][rows/8][8][4] floats, 8-row
-//              groups 144 B apart) -- the split needs a register pass anyway, so no TMA / swizzle;
+//              groups 144 B apart).  TMA cannot do this: the maps are channel-planar, i.e. MN-major operands, and kind::tf32
+//              with an MN-major operand returns zeros on sm_100a (tools/microbench/umma_tf32.cu) -- the transposition
+//              into K-major rows is what these warps are for, and what limits the kernel on large maps;
 //   warp 20    one thread issues the MMAs (12 per stage: 4 K-steps x 3 passes), commits stage-free and accumulator-full.
 // A unit of work is (patch, neighbourhood half); the two 192-column accumulators ping-pong in TMEM (512 columns), so the
 // epilogue of one unit overlaps the MMAs of the next; operand stages form a 2-deep ring (90 KB each).
